@@ -1,0 +1,65 @@
+"""ctypes binding of the C-ABI library (include/fiber_b200.h).
+
+The product path has no fallback: if libfiber_b200.so is missing or a call fails, a
+RuntimeError is raised.  `load()` does not need a GPU (the library only touches CUDA when an
+entry point runs), which lets the CPU test-suite check that every declared symbol is exported.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfiber_b200.so")
+
+_lib = None
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `fiber_gemm_args` (include/fiber_b200.h)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+        ("a_major", C.c_int32), ("b_major", C.c_int32),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("preact", C.c_void_p), ("ldp", C.c_int64),
+        ("scale", C.c_void_p),
+        ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
+        ("act", C.c_int32), ("out_mode", C.c_int32), ("splits", C.c_int32),
+    ]
+
+
+def declared_symbols():
+    """Every `fiber_*` function declared in include/fiber_b200.h (parsed from the header)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "fiber_b200.h")
+    with open(hdr) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fiber_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "fiber_b200: %s not found — build it with `python -m fiber_b200.build` "
+            "(there is no CPU or eager fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.fiber_last_error.restype = C.c_char_p
+    lib.fiber_launch_count.restype = C.c_int64
+    lib.fiber_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("fiber_b200.%s failed (%d): %s" % (what, rc, load().fiber_last_error().decode()))
+
+
+def launch_count():
+    return int(load().fiber_launch_count())

@@ -1,0 +1,74 @@
+/* fiber_b200 — C-ABI of the B200-native FIBER fusion-in-the-backbone hot path.
+ *
+ * The reference (microsoft/FIBER, coarse_grained/) has no FFI on this path: its boundary is the
+ * Python object protocol of fiber.modules.FIBERTransformerSS (fiber_module.py:26-367).  This
+ * header is the native boundary our Python mirror of that protocol binds with ctypes: one entry
+ * point per eager op (or fused group of ops) the reference issues on the path, each citing the
+ * reference lines it replaces.  Conventions for every entry point:
+ *   - plain pointers + sizes; all pointers are DEVICE pointers on the current device unless said
+ *     otherwise; activations are bf16 row-major, parameters fp32 masters or bf16 copies as stated;
+ *   - the caller allocates every buffer; entry points never allocate device memory and never
+ *     synchronise; work is enqueued on `stream`;
+ *   - returns 0 on success, negative on error; fiber_last_error() gives the message (thread-local).
+ */
+#ifndef FIBER_B200_H_
+#define FIBER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fiber_stream_t; /* cudaStream_t */
+
+const char* fiber_last_error(void);
+int fiber_version(void);
+/* Sets per-kernel attributes (max dynamic shared memory) for the current device.  Idempotent. */
+int fiber_init(void);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t fiber_launch_count(void);
+
+/* ---- GEMM on tcgen05 tensor cores --------------------------------------------------------
+ * C[M,N] = epilogue(A * B^T), bf16 operands, fp32 accumulate in TMEM.
+ * Replaces every nn.Linear on the path (swin_transformer.py:202,223,240,257 + timm Mlp;
+ * roberta.py:266-279,338,404,418; PatchEmbed conv as a K=48 GEMM; fiber_module.py:349-350)
+ * and their autograd backward (dgrad, wgrad).
+ *   a_major/b_major = 0: operand stored [rows, K] with K contiguous (forward, dgrad)
+ *                   = 1: operand stored [K, rows] with rows contiguous (wgrad: dW = dY^T X)
+ * Epilogue, applied in this order on v = acc:
+ *   v += bias[col]; if (preact) preact[row,col] = bf16(v);
+ *   act == 1: v = gelu_erf(v);  act == 2: v *= gelu_erf'(aux[row,col]);
+ *   if (scale) v *= *scale;  if (row_scale) v *= row_scale[row / rows_per_scale];
+ *   if (residual) v += residual[row,col];
+ *   out_mode 0: c = bf16(v); 1: c = f32(v); 2: atomicAdd(f32 c, v) (split-K allowed).
+ */
+typedef struct fiber_gemm_args {
+  const void* a;
+  const void* b;
+  void* c;
+  int32_t m, n, k;
+  int64_t lda, ldb, ldc; /* leading dimensions in elements */
+  int32_t a_major, b_major;
+  const float* bias;
+  const void* residual; /* bf16 [M, N] */
+  int64_t ldr;
+  const void* aux; /* bf16 [M, N] */
+  int64_t ldaux;
+  void* preact; /* bf16 [M, N] out */
+  int64_t ldp;
+  const float* scale;
+  const float* row_scale;
+  int32_t rows_per_scale;
+  int32_t act;
+  int32_t out_mode;
+  int32_t splits; /* 0 = choose */
+} fiber_gemm_args;
+
+int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIBER_B200_H_ */

@@ -1,0 +1,69 @@
+"""tcgen05 GEMM vs torch fp32 matmul on bf16-rounded operands (GPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# bf16 output rounding is 2^-9 relative; accumulation is fp32.
+RTOL, ATOL = 1.0e-2, 1.0e-2
+
+
+def _mk(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(torch.bfloat16)
+
+
+SHAPES = [
+    (128, 128, 64), (128, 128, 128), (256, 256, 256), (200, 384, 128), (1000, 512, 128),
+    (4096, 128, 512), (2560, 768, 768), (2560, 3072, 768), (2560, 768, 3072), (777, 1024, 1024),
+    (9216, 48 + 16, 128), (36864, 1536, 512), (64, 768, 768), (100, 8, 64), (333, 264, 200),
+]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_gemm_kmajor(cuda_dev, m, n, k):
+    from fiber_b200 import kernels as K
+    a = _mk((m, k), cuda_dev, 1)
+    b = _mk((n, k), cuda_dev, 2, k ** -0.5)
+    out = K.gemm(a, b)
+    ref = a.float() @ b.float().t()
+    torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 128, 4096), (128, 128, 64), (512, 128, 100000), (768, 3072, 2560),
+                                   (1536, 512, 36864), (264, 200, 333), (128, 48 + 16, 9216)])
+def test_gemm_mnmajor_wgrad(cuda_dev, m, n, k):
+    """dW[m,n] = dY[k,m]^T X[k,n] with fp32 atomic split-K accumulation."""
+    from fiber_b200 import kernels as K
+    dy = _mk((k, m), cuda_dev, 3, k ** -0.5)
+    x = _mk((k, n), cuda_dev, 4)
+    out = K.gemm(dy, x, mn_major=True, accumulate=True)
+    ref = dy.float().t() @ x.float()
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+    out1 = K.gemm(dy, x, mn_major=True, out_dtype=torch.float32)
+    torch.testing.assert_close(out1, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_gemm_epilogue(cuda_dev):
+    from fiber_b200 import kernels as K
+    m, n, k = 1000, 512, 128
+    a = _mk((m, k), cuda_dev, 5)
+    b = _mk((n, k), cuda_dev, 6, k ** -0.5)
+    bias = torch.randn(n, device=cuda_dev)
+    res = _mk((m, n), cuda_dev, 7)
+    scale = torch.tensor([0.5], device=cuda_dev)
+    row_scale = torch.rand(m // 100, device=cuda_dev) + 0.5
+    pre = torch.empty((m, n), device=cuda_dev, dtype=torch.bfloat16)
+    out = K.gemm(a, b, bias=bias, residual=res, preact=pre, scale=scale, row_scale=row_scale,
+                 rows_per_scale=100, act=K.ACT_GELU)
+    h = a.float() @ b.float().t() + bias
+    ref = torch.nn.functional.gelu(h) * 0.5 * row_scale.repeat_interleave(100)[:, None] + res.float()
+    torch.testing.assert_close(pre.float(), h, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
+    # GELU-grad epilogue: out = (a b^T) * gelu'(aux)
+    aux = _mk((m, n), cuda_dev, 8)
+    out2 = K.gemm(a, b, aux=aux, act=K.ACT_GELU_GRAD)
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ref2 = (a.float() @ b.float().t()) * x.grad
+    torch.testing.assert_close(out2.float(), ref2, rtol=RTOL, atol=ATOL)
