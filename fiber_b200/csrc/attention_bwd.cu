@@ -1,0 +1,395 @@
+// fiber_b200 — attention backward (recomputes P from Q, K and the saved log-sum-exp).
+//
+// One CTA (9 warps) owns all queries and keys of one (group, head) problem, so dQ/dK/dV need no
+// atomics:   per 144-key chunk { per 144-query chunk {
+//     phase A (warp = 16 query rows): S = QK^T, P = exp(S - lse), dP = dO V^T, dS = P*(dP - D),
+//                                     dQ += dS K ; P and dS go to shared memory as bf16
+//     phase B (warp = 16 key rows)  : dV += P^T dO, dK += dS^T Q  (transposed ldmatrix reads) } }
+// WINDOW mode additionally reduces d(relative-position-bias table): every thread owns fixed (i,j)
+// score positions, so dS is summed over all windows a CTA processes in registers and flushed once
+// (shared-memory atomics -> one global atomic per table entry per CTA).
+#include "attention.cuh"
+#include "../../include/fiber_b200.h"
+
+namespace fiber {
+
+void count_launch(int n = 1);
+int attn_check(const AttnParams& p, int hd);
+
+constexpr int BW_NWARPS = 9;
+constexpr int BW_QROWS = 16 * BW_NWARPS;  // 144
+constexpr int BW_SP = ATT_SKEYS + 8;       // pitch of the P / dS tiles (elements)
+
+template <int HD, bool WINDOW>
+__global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnParams p) {
+  constexpr int PITCH = HD + 8;
+  constexpr int CPR = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sdO = sQ + BW_QROWS * PITCH;
+  bf16* sK = sdO + BW_QROWS * PITCH;
+  bf16* sV = sK + ATT_SKEYS * PITCH;
+  bf16* sP = sV + ATT_SKEYS * PITCH;
+  bf16* sdS = sP + BW_QROWS * BW_SP;
+  float* sLse = reinterpret_cast<float*>(sdS + BW_QROWS * BW_SP);
+  float* sD = sLse + BW_QROWS;
+  float* sMask = sD + BW_QROWS;
+  float* sTbl = sMask + ATT_SKEYS;   // window only: bias table column of head h
+  float* sdTbl = sTbl + ATT_MAXTBL;  // window only: d(table) accumulator
+  int* sRow = reinterpret_cast<int*>(sdTbl + ATT_MAXTBL);
+  uint8_t* sTh = reinterpret_cast<uint8_t*>(sRow + ATT_MAXTOK);
+  uint8_t* sTw = sTh + ATT_MAXTOK;
+  uint8_t* sRid = sTw + ATT_MAXTOK;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x;
+  const int Lq = p.Lq, Lk = p.Lk;
+  const int ws = p.ws, tw2 = 2 * ws - 1;
+  const int nWw = WINDOW ? p.W / ws : 1, nW = WINDOW ? (p.H / ws) * nWw : 1;
+  const int n_groups = WINDOW ? p.G * nW : p.G;
+  const int nkc = (Lk + ATT_SKEYS - 1) / ATT_SKEYS;
+  const int nqc = (Lq + BW_QROWS - 1) / BW_QROWS;
+  const float keep_inv = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+  const int r_lo = lane >> 2;
+
+  float dbacc[WINDOW ? 18 : 1][4];
+  if (WINDOW) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) dbacc[i][0] = dbacc[i][1] = dbacc[i][2] = dbacc[i][3] = 0.f;
+    for (int t = tid; t < tw2 * tw2; t += blockDim.x) {
+      sTbl[t] = p.bias_table[t * p.nH + h];
+      sdTbl[t] = 0.f;
+    }
+    for (int i = tid; i < ATT_MAXTOK; i += blockDim.x) {
+      sTh[i] = i < Lq ? i / ws : 0;
+      sTw[i] = i < Lq ? i % ws : 0;
+    }
+  }
+
+  for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+    const long long qbase = static_cast<long long>(g) * Lq, kbase = static_cast<long long>(g) * Lk;
+    __syncthreads();
+    if (WINDOW) {
+      const int b = g / nW, w = g % nW, wh = w / nWw, ww = w % nWw;
+      for (int i = tid; i < ATT_MAXTOK; i += blockDim.x) {
+        int row = 0, rid = 0;
+        if (i < Lq) {
+          const int hp = wh * ws + i / ws, wp = ww * ws + i % ws;
+          row = b * p.H * p.W + ((hp + p.shift) % p.H) * p.W + (wp + p.shift) % p.W;
+          rid = 3 * ((hp >= p.H - ws) + (hp >= p.H - p.shift)) + (wp >= p.W - ws) + (wp >= p.W - p.shift);
+        }
+        sRow[i] = row; sRid[i] = rid;
+      }
+      __syncthreads();
+    }
+
+    float dq[HD / 8][4];  // persists over key chunks when there is a single query chunk
+
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int kc0 = kc * ATT_SKEYS;
+      const int nk = min(ATT_SKEYS, Lk - kc0);
+      const int nk_pad = ((nk + ATT_KCHUNK - 1) / ATT_KCHUNK) * ATT_KCHUNK;
+      const int n_ktiles = (nk + 15) / 16;
+      __syncthreads();
+      for (int c = tid; c < nk_pad * CPR; c += blockDim.x) {
+        const int r = c / CPR, cc = c % CPR, kj = kc0 + r;
+        const bool valid = kj < Lk;
+        const long long grow = valid ? (WINDOW ? sRow[kj] : kbase + kj) : 0;
+        cp_async16(smem_u32(sK + r * PITCH + cc * 8), p.k + grow * p.ldk + h * HD + cc * 8, valid);
+        cp_async16(smem_u32(sV + r * PITCH + cc * 8), p.v + grow * p.ldv + h * HD + cc * 8, valid);
+      }
+      if (!WINDOW) {
+        for (int j = tid; j < nk_pad; j += blockDim.x)
+          sMask[j] = (p.key_mask && kc0 + j < Lk) ? p.key_mask[kbase + kc0 + j] : 0.f;
+      }
+
+      float dkacc[HD / 8][4], dvacc[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        dkacc[i][0] = dkacc[i][1] = dkacc[i][2] = dkacc[i][3] = 0.f;
+        dvacc[i][0] = dvacc[i][1] = dvacc[i][2] = dvacc[i][3] = 0.f;
+      }
+
+      for (int qc = 0; qc < nqc; ++qc) {
+        const int q0 = qc * BW_QROWS;
+        const int nq = min(BW_QROWS, Lq - q0);
+        const int n_qtiles = (nq + 15) / 16;
+        __syncthreads();  // previous phase B done with sQ/sdO/sP/sdS
+        for (int c = tid; c < BW_QROWS * CPR; c += blockDim.x) {
+          const int r = c / CPR, cc = c % CPR, qi = q0 + r;
+          const bool valid = qi < Lq;
+          const long long grow = valid ? (WINDOW ? sRow[qi] : qbase + qi) : 0;
+          cp_async16(smem_u32(sQ + r * PITCH + cc * 8), p.q + grow * p.ldq + h * HD + cc * 8, valid);
+          cp_async16(smem_u32(sdO + r * PITCH + cc * 8), p.d_o + grow * p.lddo + h * HD + cc * 8, valid);
+        }
+        // D_i = sum_d dO[i,d] * O[i,d]; lse_i
+        for (int c = tid; c < BW_QROWS * CPR; c += blockDim.x) {
+          const int r = c / CPR, cc = c % CPR, qi = q0 + r;
+          float part = 0.f;
+          if (qi < Lq) {
+            const long long grow = WINDOW ? sRow[qi] : qbase + qi;
+            const uint4 a = *reinterpret_cast<const uint4*>(p.o + grow * p.ldo + h * HD + cc * 8);
+            const uint4 b = *reinterpret_cast<const uint4*>(p.d_o + grow * p.lddo + h * HD + cc * 8);
+            const uint32_t* au = reinterpret_cast<const uint32_t*>(&a);
+            const uint32_t* bu = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16(au[e]), y = unpack_bf16(bu[e]);
+              part += x.x * y.x + x.y * y.y;
+            }
+          }
+          // CPR (4 or 8) consecutive lanes hold one row
+#pragma unroll
+          for (int o = CPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (cc == 0) {
+            sD[r] = part;
+            sLse[r] = qi < Lq ? p.lse[(static_cast<long long>(g) * p.nH + h) * Lq + qi] : 0.f;
+          }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ================= phase A =================
+        if (warp < n_qtiles) {
+          uint32_t qf[HD / 16][4], dof[HD / 16][4];
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int col = ks * 16 + (lane >> 4) * 8;
+            ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+            ldsm_x4(smem_u32(sdO + row * PITCH + col), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
+          }
+          const int rl0 = warp * 16 + r_lo;  // local query row of fragment row 0
+          const float lse0 = sLse[rl0], lse1 = sLse[rl0 + 8];
+          const float D0 = sD[rl0], D1 = sD[rl0 + 8];
+          if (kc == 0 || nqc > 1) {
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+          }
+#pragma unroll
+          for (int sub = 0; sub < ATT_SKEYS / ATT_KCHUNK; ++sub) {
+            if (sub * ATT_KCHUNK < nk_pad) {
+              float s[6][4], dp[6][4];
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+                dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+              }
+#pragma unroll
+              for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+                for (int nt2 = 0; nt2 < 3; ++nt2) {
+                  const int row = sub * ATT_KCHUNK + nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
+                  const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+                  uint32_t b0, b1, b2, b3;
+                  ldsm_x4(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
+                  mma16816(s[2 * nt2], qf[ks], b0, b1);
+                  mma16816(s[2 * nt2 + 1], qf[ks], b2, b3);
+                  ldsm_x4(smem_u32(sV + row * PITCH + col), b0, b1, b2, b3);
+                  mma16816(dp[2 * nt2], dof[ks], b0, b1);
+                  mma16816(dp[2 * nt2 + 1], dof[ks], b2, b3);
+                }
+              }
+#pragma unroll
+              for (int nt = 0; nt < 6; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int jl = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2 + (e & 1);
+                  const int j = kc0 + jl;
+                  const int ql = rl0 + (e >> 1) * 8, qi = q0 + ql;
+                  float v = s[nt][e] * p.scale;
+                  if (WINDOW) {
+                    const int qq = qi < Lq ? qi : 0;
+                    const int jj = j < Lk ? j : 0;
+                    v += sTbl[(static_cast<int>(sTh[qq]) - static_cast<int>(sTh[jj]) + ws - 1) * tw2 +
+                              static_cast<int>(sTw[qq]) - static_cast<int>(sTw[jj]) + ws - 1];
+                    if (p.shift > 0 && sRid[qq] != sRid[jj]) v += -100.0f;
+                  } else {
+                    v += sMask[jl];
+                  }
+                  float pr = (j < Lk) ? __expf(v - ((e >> 1) ? lse1 : lse0)) : 0.f;
+                  float dpv = dp[nt][e];
+                  float pd = pr;  // P after dropout (feeds dV)
+                  if (p.drop_p > 0.f) {
+                    const unsigned long long idx =
+                        ((static_cast<unsigned long long>(g) * p.nH + h) * Lq + qi) * Lk + j;
+                    const bool keep = dropout_keep(p.seed, idx, p.drop_p);
+                    pd = keep ? pr * keep_inv : 0.f;
+                    dpv = keep ? dpv * keep_inv : 0.f;
+                  }
+                  const float ds = pr * (dpv - ((e >> 1) ? D1 : D0));
+                  s[nt][e] = pd;
+                  dp[nt][e] = ds;
+                  if (WINDOW) dbacc[sub * 6 + nt][e] += ds;
+                }
+              }
+              // P, dS -> smem (bf16) for phase B; dQ += dS K from registers
+#pragma unroll
+              for (int nt = 0; nt < 6; ++nt) {
+                const int col = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;
+                *reinterpret_cast<uint32_t*>(sP + rl0 * BW_SP + col) = pack_bf16(s[nt][0], s[nt][1]);
+                *reinterpret_cast<uint32_t*>(sP + (rl0 + 8) * BW_SP + col) = pack_bf16(s[nt][2], s[nt][3]);
+                *reinterpret_cast<uint32_t*>(sdS + rl0 * BW_SP + col) = pack_bf16(dp[nt][0], dp[nt][1]);
+                *reinterpret_cast<uint32_t*>(sdS + (rl0 + 8) * BW_SP + col) = pack_bf16(dp[nt][2], dp[nt][3]);
+              }
+#pragma unroll
+              for (int kk = 0; kk < 3; ++kk) {
+                uint32_t a[4];
+                a[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+                a[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+                a[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+                a[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+                for (int dt2 = 0; dt2 < HD / 16; ++dt2) {
+                  const int row = sub * ATT_KCHUNK + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                  const int col = dt2 * 16 + (lane >> 4) * 8;
+                  uint32_t b0, b1, b2, b3;
+                  ldsm_x4_t(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
+                  mma16816(dq[2 * dt2], a, b0, b1);
+                  mma16816(dq[2 * dt2 + 1], a, b2, b3);
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+
+        // ================= phase B =================
+        if (warp < n_ktiles) {
+          const int m0 = warp * 16;  // key tile inside the smem chunk
+          for (int kt = 0; kt < n_qtiles; ++kt) {
+            const int k0 = kt * 16;
+            uint32_t ap[4], as_[4];
+            {
+              const int row = k0 + (lane & 7) + ((lane >> 4) << 3);
+              const int col = m0 + ((lane >> 3) & 1) * 8;
+              ldsm_x4_t(smem_u32(sP + row * BW_SP + col), ap[0], ap[1], ap[2], ap[3]);
+              ldsm_x4_t(smem_u32(sdS + row * BW_SP + col), as_[0], as_[1], as_[2], as_[3]);
+            }
+#pragma unroll
+            for (int dt2 = 0; dt2 < HD / 16; ++dt2) {
+              const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+              const int col = dt2 * 16 + (lane >> 4) * 8;
+              uint32_t b0, b1, b2, b3;
+              ldsm_x4_t(smem_u32(sdO + row * PITCH + col), b0, b1, b2, b3);
+              mma16816(dvacc[2 * dt2], ap, b0, b1);
+              mma16816(dvacc[2 * dt2 + 1], ap, b2, b3);
+              ldsm_x4_t(smem_u32(sQ + row * PITCH + col), b0, b1, b2, b3);
+              mma16816(dkacc[2 * dt2], as_, b0, b1);
+              mma16816(dkacc[2 * dt2 + 1], as_, b2, b3);
+            }
+          }
+        }
+        // ---- dQ store (per query chunk when the key loop has one chunk, else after the last) ----
+        if (nqc > 1 || kc == nkc - 1) {
+          __syncthreads();  // phase B finished reading sQ
+          if (warp < n_qtiles) {
+#pragma unroll
+            for (int dt = 0; dt < HD / 8; ++dt) {
+              const int col = dt * 8 + (lane & 3) * 2;
+              *reinterpret_cast<uint32_t*>(sQ + (warp * 16 + r_lo) * PITCH + col) =
+                  pack_bf16(dq[dt][0] * p.scale, dq[dt][1] * p.scale);
+              *reinterpret_cast<uint32_t*>(sQ + (warp * 16 + r_lo + 8) * PITCH + col) =
+                  pack_bf16(dq[dt][2] * p.scale, dq[dt][3] * p.scale);
+            }
+            __syncwarp();
+            for (int c = lane; c < 16 * CPR; c += 32) {
+              const int r = c / CPR, cc = c % CPR, qi = q0 + warp * 16 + r;
+              if (qi < Lq) {
+                const long long grow = WINDOW ? sRow[qi] : qbase + qi;
+                *reinterpret_cast<uint4*>(p.dq + grow * p.lddq + h * HD + cc * 8) =
+                    *reinterpret_cast<const uint4*>(sQ + (warp * 16 + r) * PITCH + cc * 8);
+              }
+            }
+          }
+        }
+      }  // query chunks
+
+      // ---- dK / dV of this key chunk: stage through this warp's rows of sK / sV ----
+      __syncthreads();
+      if (warp < n_ktiles) {
+#pragma unroll
+        for (int dt = 0; dt < HD / 8; ++dt) {
+          const int col = dt * 8 + (lane & 3) * 2;
+          *reinterpret_cast<uint32_t*>(sK + (warp * 16 + r_lo) * PITCH + col) =
+              pack_bf16(dkacc[dt][0] * p.scale, dkacc[dt][1] * p.scale);
+          *reinterpret_cast<uint32_t*>(sK + (warp * 16 + r_lo + 8) * PITCH + col) =
+              pack_bf16(dkacc[dt][2] * p.scale, dkacc[dt][3] * p.scale);
+          *reinterpret_cast<uint32_t*>(sV + (warp * 16 + r_lo) * PITCH + col) = pack_bf16(dvacc[dt][0], dvacc[dt][1]);
+          *reinterpret_cast<uint32_t*>(sV + (warp * 16 + r_lo + 8) * PITCH + col) = pack_bf16(dvacc[dt][2], dvacc[dt][3]);
+        }
+        __syncwarp();
+        for (int c = lane; c < 16 * CPR; c += 32) {
+          const int r = c / CPR, cc = c % CPR, kj = kc0 + warp * 16 + r;
+          if (kj < Lk) {
+            const long long grow = WINDOW ? sRow[kj] : kbase + kj;
+            *reinterpret_cast<uint4*>(p.dk + grow * p.lddk + h * HD + cc * 8) =
+                *reinterpret_cast<const uint4*>(sK + (warp * 16 + r) * PITCH + cc * 8);
+            *reinterpret_cast<uint4*>(p.dv + grow * p.lddv + h * HD + cc * 8) =
+                *reinterpret_cast<const uint4*>(sV + (warp * 16 + r) * PITCH + cc * 8);
+          }
+        }
+      }
+    }  // key chunks
+  }    // groups
+
+  if (WINDOW) {
+    // flush the register-resident d(bias) sums: smem atomics, then one global atomic per entry
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 18; ++t) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = t * 8 + (lane & 3) * 2 + (e & 1);
+        const int qi = warp * 16 + r_lo + (e >> 1) * 8;
+        if (qi < Lq && j < Lk)
+          atomicAdd(&sdTbl[(static_cast<int>(sTh[qi]) - static_cast<int>(sTh[j]) + ws - 1) * tw2 +
+                           static_cast<int>(sTw[qi]) - static_cast<int>(sTw[j]) + ws - 1],
+                    dbacc[t][e]);
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < tw2 * tw2; t += blockDim.x) atomicAdd(&p.dbias_table[t * p.nH + h], sdTbl[t]);
+  }
+}
+
+template <int HD, bool WINDOW>
+static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
+  constexpr int PITCH = HD + 8;
+  const size_t smem = (2 * BW_QROWS + 2 * ATT_SKEYS) * PITCH * 2 + 2 * BW_QROWS * BW_SP * 2 +
+                      (2 * BW_QROWS + ATT_SKEYS) * 4 + 2 * ATT_MAXTBL * 4 + ATT_MAXTOK * 4 +
+                      3 * ATT_MAXTOK + 16;
+  auto kern = attn_bwd_kernel<HD, WINDOW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int n_groups = WINDOW ? p.G * (p.H / p.ws) * (p.W / p.ws) : p.G;
+  int gy = n_groups;
+  if (WINDOW) {  // persistent over windows so d(bias) is flushed once per CTA
+    const int target = (2 * num_sms() + p.nH - 1) / p.nH;
+    if (gy > target) gy = target;
+  }
+  dim3 grid(p.nH, gy);
+  kern<<<grid, BW_NWARPS * 32, smem, stream>>>(p);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int attn_bwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
+  if (attn_check(p, hd)) return -1;
+  FIBER_CHECK(p.d_o && p.dq && p.dk && p.dv && p.lse && p.o, "attention backward needs o, lse, d_o, dq, dk, dv");
+  FIBER_CHECK(p.Lq <= BW_QROWS || p.Lk <= ATT_SKEYS,
+              "attention backward: Lq > 144 together with Lk > 144 is not supported yet (Lq=%d, Lk=%d)",
+              p.Lq, p.Lk);
+  if (p.mode == 1) {
+    FIBER_CHECK(hd == 32, "window attention uses head_dim 32");
+    FIBER_CHECK(p.dbias_table != nullptr, "window backward needs dbias_table");
+    return launch_bwd<32, true>(p, stream);
+  }
+  return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);
+}
+
+}  // namespace fiber

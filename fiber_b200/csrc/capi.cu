@@ -1,5 +1,5 @@
 // fiber_b200 — extern "C" surface (see include/fiber_b200.h) and process-wide plumbing.
-#include "common.cuh"
+#include "attention.cuh"
 #include "../../include/fiber_b200.h"
 
 #include <atomic>
@@ -34,6 +34,25 @@ int num_sms() {
 }
 
 int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream);
+int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream);
+int attn_bwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream);
+
+static AttnParams to_params(const fiber_attn_args* a) {
+  AttnParams p;
+  p.q = reinterpret_cast<const bf16*>(a->q); p.k = reinterpret_cast<const bf16*>(a->k);
+  p.v = reinterpret_cast<const bf16*>(a->v); p.o = reinterpret_cast<bf16*>(a->o);
+  p.lse = a->lse;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.mode = a->mode; p.G = a->groups; p.nH = a->heads; p.Lq = a->lq; p.Lk = a->lk;
+  p.scale = a->scale; p.key_mask = a->key_mask;
+  p.H = a->h; p.W = a->w; p.ws = a->ws; p.shift = a->shift; p.bias_table = a->bias_table;
+  p.drop_p = a->drop_p; p.seed = a->seed;
+  p.d_o = reinterpret_cast<const bf16*>(a->d_o); p.dq = reinterpret_cast<bf16*>(a->dq);
+  p.dk = reinterpret_cast<bf16*>(a->dk); p.dv = reinterpret_cast<bf16*>(a->dv);
+  p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.dbias_table = a->dbias_table;
+  return p;
+}
 
 }  // namespace fiber
 
@@ -66,6 +85,15 @@ int fiber_init(void) {
 
 int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream) {
   return fiber::gemm_dispatch(args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fiber_attn_fwd(const fiber_attn_args* a, fiber_stream_t stream) {
+  if (!a) { fiber::set_last_error("null args"); return -1; }
+  return fiber::attn_fwd_dispatch(fiber::to_params(a), a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+int fiber_attn_bwd(const fiber_attn_args* a, fiber_stream_t stream) {
+  if (!a) { fiber::set_last_error("null args"); return -1; }
+  return fiber::attn_bwd_dispatch(fiber::to_params(a), a->head_dim, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

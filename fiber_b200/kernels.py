@@ -88,3 +88,54 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
     args.splits = splits
     _lib.check(_lib.load().fiber_gemm(C.byref(args), _stream()), "gemm")
     return out
+
+
+def _attn_args(q, k, v, o, lse, heads, head_dim, scale, *, window=None, groups=None, lq=None, lk=None,
+               key_mask=None, bias_table=None, drop_p=0.0, seed=0):
+    """window = (G, H, W, ws, shift) for mode 1; otherwise plain mode with (groups, lq, lk)."""
+    a = _lib.AttnArgs()
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        _req(t, BF16, name)
+        if t.stride(-1) != 1:
+            raise RuntimeError("fiber_b200.attention: %s must have unit inner stride" % name)
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(-2), k.stride(-2), v.stride(-2), o.stride(-2)
+    _req(lse, F32, "lse"); a.lse = lse.data_ptr()
+    a.heads, a.head_dim, a.scale = heads, head_dim, float(scale)
+    if window is not None:
+        G, H, W, ws, shift = window
+        a.mode, a.groups, a.h, a.w, a.ws, a.shift = 1, G, H, W, ws, shift
+        a.lq = a.lk = ws * ws
+        _req(bias_table, F32, "bias_table"); a.bias_table = bias_table.data_ptr()
+    else:
+        a.mode, a.groups, a.lq, a.lk = 0, groups, lq, lk
+        if key_mask is not None:
+            _req(key_mask, F32, "key_mask"); a.key_mask = key_mask.data_ptr()
+    a.drop_p, a.seed = float(drop_p), int(seed)
+    return a
+
+
+def attn_fwd(q, k, v, heads, head_dim, scale, **kw):
+    """Returns (o, lse).  q/k/v are 2-D row-major views (rows x channels, any row stride)."""
+    rows = q.shape[0]
+    o = torch.empty((rows, heads * head_dim), device=q.device, dtype=BF16)
+    if kw.get("window") is not None:
+        G, H, W, ws, _ = kw["window"]
+        lse = torch.empty((G * (H // ws) * (W // ws), heads, ws * ws), device=q.device, dtype=F32)
+    else:
+        lse = torch.empty((kw["groups"], heads, kw["lq"]), device=q.device, dtype=F32)
+    a = _attn_args(q, k, v, o, lse, heads, head_dim, scale, **kw)
+    _lib.check(_lib.load().fiber_attn_fwd(C.byref(a), _stream()), "attn_fwd")
+    return o, lse
+
+
+def attn_bwd(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, dbias_table=None, **kw):
+    """Writes dq/dk/dv (bf16 views with the layout of q/k/v); accumulates into dbias_table."""
+    a = _attn_args(q, k, v, o, lse, heads, head_dim, scale, **kw)
+    for name, t in (("d_o", d_o), ("dq", dq), ("dk", dk), ("dv", dv)):
+        _req(t, BF16, name)
+    a.d_o, a.dq, a.dk, a.dv = d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.lddo, a.lddq, a.lddk, a.lddv = d_o.stride(-2), dq.stride(-2), dk.stride(-2), dv.stride(-2)
+    if dbias_table is not None:
+        _req(dbias_table, F32, "dbias_table"); a.dbias_table = dbias_table.data_ptr()
+    _lib.check(_lib.load().fiber_attn_bwd(C.byref(a), _stream()), "attn_bwd")

@@ -30,6 +30,25 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    """Mirror of `fiber_attn_args` (include/fiber_b200.h)."""
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("lse", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("mode", C.c_int32), ("groups", C.c_int32), ("heads", C.c_int32), ("lq", C.c_int32),
+        ("lk", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float),
+        ("key_mask", C.c_void_p),
+        ("h", C.c_int32), ("w", C.c_int32), ("ws", C.c_int32), ("shift", C.c_int32),
+        ("bias_table", C.c_void_p),
+        ("drop_p", C.c_float),
+        ("seed", C.c_uint64),
+        ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("lddo", C.c_int64), ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
+        ("dbias_table", C.c_void_p),
+    ]
+
+
 def declared_symbols():
     """Every `fiber_*` function declared in include/fiber_b200.h (parsed from the header)."""
     import re
@@ -52,6 +71,8 @@ def load():
     lib.fiber_last_error.restype = C.c_char_p
     lib.fiber_launch_count.restype = C.c_int64
     lib.fiber_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.fiber_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.fiber_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     _lib = lib
     return lib
 

@@ -68,6 +68,43 @@ typedef struct fiber_gemm_args {
 
 int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream);
 
+/* ---- small-sequence attention (flash-style; scores never reach HBM) ------------------------
+ * mode 1 (window): Swin W-MSA/SW-MSA core, swin_transformer.py:205-222 with the roll /
+ *   window_partition / window_reverse of :363-387 and the bias gather of :208-217 folded into
+ *   the kernel's addressing.  q/k/v point into the IMAGE-ordered packed qkv activation
+ *   [G*H*W, 3C] (q = base, k = base + C, v = base + 2C, ld = 3C); o is image-ordered [G*H*W, C].
+ * mode 0 (plain): RoBERTa self-attention (roberta.py:284-322), t2i cross attention (no mask) and
+ *   i2t cross attention (swin_transformer.py:245-256); rows of group g are g*Lq + i / g*Lk + j;
+ *   key_mask is the additive [G, Lk] fp32 mask (0 / -10000) or NULL.
+ * Scores are scale * q.k (+ bias / mask); lse [G', nH, Lq] is written for the backward pass.
+ * Backward recomputes P; window mode accumulates d(bias table) into dbias_table (fp32, atomics).
+ */
+typedef struct fiber_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  int64_t ldq, ldk, ldv, ldo;
+  int32_t mode, groups, heads, lq, lk, head_dim;
+  float scale;
+  const float* key_mask;
+  int32_t h, w, ws, shift;
+  const float* bias_table; /* [(2ws-1)^2, heads] fp32 */
+  float drop_p;
+  uint64_t seed;
+  /* backward only */
+  const void* d_o;
+  void* dq;
+  void* dk;
+  void* dv;
+  int64_t lddo, lddq, lddk, lddv;
+  float* dbias_table;
+} fiber_attn_args;
+
+int fiber_attn_fwd(const fiber_attn_args* args, fiber_stream_t stream);
+int fiber_attn_bwd(const fiber_attn_args* args, fiber_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

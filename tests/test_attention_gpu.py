@@ -1,0 +1,120 @@
+"""Attention kernels (window + plain modes) vs the oracle's fp32 formulation on bf16 inputs (GPU)."""
+import math
+
+import pytest
+import torch
+
+from oracle import fiber_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(torch.bfloat16)
+
+
+def _close(a, b, tol, name):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * max(ref, 1e-3), "%s: max err %g vs ref max %g" % (name, err, ref)
+
+
+@pytest.mark.parametrize("B,H,ws,shift,nh", [(2, 24, 12, 0, 2), (2, 24, 12, 6, 2), (3, 14, 7, 3, 4), (1, 12, 12, 0, 3),
+                                             (2, 96, 12, 6, 4)])
+def test_window_attention_fwd_bwd(cuda_dev, B, H, ws, shift, nh):
+    from fiber_b200 import kernels as K
+    hd = 32
+    C = nh * hd
+    N = ws * ws
+    T = H * H
+    qkv = _rand((B * T, 3 * C), cuda_dev, 1)
+    table = (torch.randn((2 * ws - 1) ** 2, nh, generator=torch.Generator().manual_seed(2)) * 0.5).to(cuda_dev)
+    d_o = _rand((B * T, C), cuda_dev, 3)
+    scale = hd ** -0.5
+    win = (B, H, H, ws, shift)
+    o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], nh, hd, scale, window=win, bias_table=table)
+
+    # reference: the oracle's index maps + explicit softmax in fp32 on the same bf16 inputs
+    x = qkv.float().view(B, T, 3 * C).requires_grad_(True)
+    tb = table.clone().requires_grad_(True)
+    src = O.window_token_source(H, H, ws, shift).to(cuda_dev)
+    nW = src.shape[0]
+    xw = x[:, src.reshape(-1)].reshape(B * nW, N, 3, nh, hd).permute(2, 0, 3, 1, 4)
+    s = (xw[0] * scale) @ xw[1].transpose(-2, -1)
+    s = s + tb[O.relative_position_index(ws).to(cuda_dev).reshape(-1)].view(N, N, nh).permute(2, 0, 1)[None]
+    m = O.shift_attn_mask(H, H, ws, shift)
+    if m is not None:
+        s = (s.view(B, nW, nh, N, N) + m.to(cuda_dev)[None, :, None]).view(B * nW, nh, N, N)
+    ow = (torch.softmax(s, -1) @ xw[2]).transpose(1, 2).reshape(B, nW * N, C)
+    ref = torch.empty(B, T, C, device=cuda_dev)
+    ref = ref.index_copy(1, src.reshape(-1), ow)
+    _close(o.view(B, T, C), ref, 2e-2, "o")
+    _close(lse, torch.logsumexp(s, -1), 1e-2, "lse")
+    ref.backward(d_o.float().view(B, T, C))
+
+    dqkv = torch.empty_like(qkv)
+    dtable = torch.zeros_like(table)
+    K.attn_bwd(d_o, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, nh, hd, scale,
+               dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dbias_table=dtable, window=win, bias_table=table)
+    _close(dqkv.view(B, T, 3 * C), x.grad, 3e-2, "dqkv")
+    _close(dtable, tb.grad, 3e-2, "dtable")
+
+
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", [
+    (3, 12, 64, 40, 40, True),      # RoBERTa self-attention
+    (2, 12, 64, 50, 50, True),      # 50-token VQA text
+    (2, 12, 64, 40, 576, False),    # t2i stage 2
+    (2, 12, 64, 40, 144, False),    # t2i stage 3
+    (2, 16, 32, 576, 40, True),     # i2t stage 2
+    (2, 32, 32, 144, 40, True),     # i2t stage 3
+    (1, 4, 32, 1296, 50, True),     # i2t at 576 px
+])
+def test_plain_attention_fwd_bwd(cuda_dev, B, nh, hd, Lq, Lk, masked):
+    from fiber_b200 import kernels as K
+    C = nh * hd
+    q = _rand((B * Lq, C), cuda_dev, 1)
+    kv = _rand((B * Lk, 2 * C), cuda_dev, 2)
+    d_o = _rand((B * Lq, C), cuda_dev, 3)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, Lk, device=cuda_dev)
+        mask[0, Lk - 7:] = -10000.0
+    scale = 1.0 / math.sqrt(hd)
+    kw = dict(groups=B, lq=Lq, lk=Lk, key_mask=mask)
+    o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, scale, **kw)
+
+    qf = q.float().view(B, Lq, nh, hd).transpose(1, 2).requires_grad_(True)
+    kf = kv[:, :C].float().reshape(B, Lk, nh, hd).transpose(1, 2).requires_grad_(True)
+    vf = kv[:, C:].float().reshape(B, Lk, nh, hd).transpose(1, 2).requires_grad_(True)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Lq, C)
+    _close(o, ref, 2e-2, "o")
+    ref.backward(d_o.float())
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    K.attn_bwd(d_o, q, kv[:, :C], kv[:, C:], o, lse, nh, hd, scale, dq, dkv[:, :C], dkv[:, C:], **kw)
+    _close(dq.view(B, Lq, nh, hd).transpose(1, 2), qf.grad, 3e-2, "dq")
+    _close(dkv[:, :C].reshape(B, Lk, nh, hd).transpose(1, 2), kf.grad, 3e-2, "dk")
+    _close(dkv[:, C:].reshape(B, Lk, nh, hd).transpose(1, 2), vf.grad, 3e-2, "dv")
+
+
+def test_attention_dropout_statistics(cuda_dev):
+    """Probability dropout: E[o] is unchanged, the mask is identical in forward and backward."""
+    from fiber_b200 import kernels as K
+    B, nh, hd, L = 8, 12, 64, 40
+    C = nh * hd
+    q = _rand((B * L, C), cuda_dev, 1, 0.2)
+    kv = _rand((B * L, 2 * C), cuda_dev, 2, 0.2)
+    kv[:, C:] = 1.0  # v == 1  =>  o == sum of kept probabilities / keep
+    kw = dict(groups=B, lq=L, lk=L)
+    o, _ = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, 0.125, drop_p=0.1, seed=123, **kw)
+    o2, _ = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, 0.125, drop_p=0.1, seed=123, **kw)
+    assert torch.equal(o, o2)
+    o3, _ = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, 0.125, drop_p=0.1, seed=124, **kw)
+    assert not torch.equal(o, o3)
+    assert abs(o.float().mean().item() - 1.0) < 0.01
+    assert 0.02 < o.float().std().item() < 0.2
