@@ -54,7 +54,43 @@ static AttnParams to_params(const fiber_attn_args* a) {
   return p;
 }
 
+struct LnParams {
+  const bf16* in1; const bf16* in2; long long ld1, ld2; const float* gamma; const float* beta; float eps;
+  bf16* out; long long ldo; float* mean; float* rstd; bf16* sum_out; long long lds; long long rows; int C;
+  int merge, H, W, Cin;
+  const bf16* dy; long long lddy; const bf16* dres; long long lddres; bf16* dx; long long lddx;
+  float* dgamma; float* dbeta;
+};
+int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream);
+int colsum_dispatch(const bf16*, long long, long long, int, float*, const float*, const float*, int, cudaStream_t);
+int dot_dispatch(const bf16*, long long, const bf16*, long long, long long, int, float*, cudaStream_t);
+int rowwise_scale_dispatch(const bf16*, long long, bf16*, long long, long long, int, int, float, unsigned long long,
+                           const float*, int, cudaStream_t);
+int cast_dispatch(const float*, bf16*, long long, cudaStream_t);
+int cast_transpose_dispatch(const float*, long long, int, int, bf16*, long long, bf16*, long long, cudaStream_t);
+int patch_gather_dispatch(const float*, bf16*, int, int, cudaStream_t);
+int embed_dispatch(const long long*, int, int, int, int, const float*, const float*, const float*, bf16*, long long,
+                   cudaStream_t);
+int embed_scatter_dispatch(const long long*, int, int, int, int, const bf16*, long long, float*, float*, cudaStream_t);
+
+static LnParams to_ln(const fiber_ln_args* a) {
+  LnParams p;
+  p.in1 = reinterpret_cast<const bf16*>(a->in1); p.in2 = reinterpret_cast<const bf16*>(a->in2);
+  p.ld1 = a->ld1; p.ld2 = a->ld2; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps;
+  p.out = reinterpret_cast<bf16*>(a->out); p.ldo = a->ldo; p.mean = a->mean; p.rstd = a->rstd;
+  p.sum_out = reinterpret_cast<bf16*>(a->sum_out); p.lds = a->lds; p.rows = a->rows; p.C = a->c;
+  p.merge = a->merge; p.H = a->h; p.W = a->w; p.Cin = a->cin;
+  p.dy = reinterpret_cast<const bf16*>(a->dy); p.lddy = a->lddy;
+  p.dres = reinterpret_cast<const bf16*>(a->dres); p.lddres = a->lddres;
+  p.dx = reinterpret_cast<bf16*>(a->dx); p.lddx = a->lddx; p.dgamma = a->dgamma; p.dbeta = a->dbeta;
+  return p;
+}
+
 }  // namespace fiber
+
+#define FIBER_S(s) reinterpret_cast<cudaStream_t>(s)
+#define FIBER_B(p) reinterpret_cast<const fiber::bf16*>(p)
+#define FIBER_BM(p) reinterpret_cast<fiber::bf16*>(p)
 
 extern "C" {
 
@@ -94,6 +130,53 @@ int fiber_attn_fwd(const fiber_attn_args* a, fiber_stream_t stream) {
 int fiber_attn_bwd(const fiber_attn_args* a, fiber_stream_t stream) {
   if (!a) { fiber::set_last_error("null args"); return -1; }
   return fiber::attn_bwd_dispatch(fiber::to_params(a), a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fiber_layernorm_fwd(const fiber_ln_args* a, fiber_stream_t s) {
+  if (!a || !a->in1 || !a->out || !a->gamma || !a->beta) { fiber::set_last_error("layernorm_fwd: null argument"); return -1; }
+  return fiber::ln_dispatch(fiber::to_ln(a), false, FIBER_S(s));
+}
+int fiber_layernorm_bwd(const fiber_ln_args* a, fiber_stream_t s) {
+  if (!a || !a->in1 || !a->dy || !a->dx || !a->gamma || !a->mean || !a->rstd) {
+    fiber::set_last_error("layernorm_bwd: null argument"); return -1;
+  }
+  if ((a->dgamma == nullptr) != (a->dbeta == nullptr)) { fiber::set_last_error("layernorm_bwd: dgamma/dbeta go together"); return -1; }
+  return fiber::ln_dispatch(fiber::to_ln(a), true, FIBER_S(s));
+}
+int fiber_colsum(const void* x, int64_t ld, int64_t m, int32_t n, float* out, const float* scale,
+                 const float* row_scale, int32_t rps, fiber_stream_t s) {
+  return fiber::colsum_dispatch(FIBER_B(x), ld, m, n, out, scale, row_scale, rps, FIBER_S(s));
+}
+int fiber_dot(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int32_t n, float* out, fiber_stream_t s) {
+  return fiber::dot_dispatch(FIBER_B(a), lda, FIBER_B(b), ldb, m, n, out, FIBER_S(s));
+}
+int fiber_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, float p, uint64_t seed,
+                  fiber_stream_t s) {
+  return fiber::rowwise_scale_dispatch(FIBER_B(x), ldx, FIBER_BM(y), ldy, m, n, 0, p, seed, nullptr, 1, FIBER_S(s));
+}
+int fiber_scale_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, const float* row_scale,
+                     int32_t rps, fiber_stream_t s) {
+  return fiber::rowwise_scale_dispatch(FIBER_B(x), ldx, FIBER_BM(y), ldy, m, n, 1, 0.f, 0, row_scale, rps, FIBER_S(s));
+}
+int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t s) {
+  return fiber::cast_dispatch(x, FIBER_BM(y), n, FIBER_S(s));
+}
+int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void* w_out, int64_t ld_out, void* wt_out,
+                         int64_t ldt_out, fiber_stream_t s) {
+  return fiber::cast_transpose_dispatch(w, ldw, n, k, FIBER_BM(w_out), ld_out, FIBER_BM(wt_out), ldt_out, FIBER_S(s));
+}
+int fiber_patch_gather(const float* img, void* out, int32_t batch, int32_t r, fiber_stream_t s) {
+  return fiber::patch_gather_dispatch(img, FIBER_BM(out), batch, r, FIBER_S(s));
+}
+int fiber_embed_gather(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const float* word,
+                       const float* pos, const float* type, void* out, int64_t ldo, fiber_stream_t s) {
+  return fiber::embed_dispatch(reinterpret_cast<const long long*>(ids), batch, len, c, pad_id, word, pos, type,
+                               FIBER_BM(out), ldo, FIBER_S(s));
+}
+int fiber_embed_scatter(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const void* dsum,
+                        int64_t ldd, float* dword, float* dpos, fiber_stream_t s) {
+  return fiber::embed_scatter_dispatch(reinterpret_cast<const long long*>(ids), batch, len, c, pad_id, FIBER_B(dsum),
+                                       ldd, dword, dpos, FIBER_S(s));
 }
 
 }  // extern "C"

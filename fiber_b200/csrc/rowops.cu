@@ -1,0 +1,560 @@
+// fiber_b200 — HBM-bound row-wise kernels: LayerNorm fwd/bwd (optionally fused with a residual
+// add or with the PatchMerging 2x2 gather), bias-gradient column sums, dot products (gate
+// gradients), dropout, DropPath row scaling, fp32<->bf16 casts, weight cast+transpose,
+// PatchEmbed patch gather, RoBERTa embedding gather / scatter.
+// All are warp-per-row or grid-stride kernels with 128-bit accesses; fp32 math in registers.
+#include "common.cuh"
+#include "../../include/fiber_b200.h"
+
+namespace fiber {
+
+void count_launch(int n = 1);
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm
+// ---------------------------------------------------------------------------------------------
+struct LnParams {
+  const bf16* in1;
+  const bf16* in2;  // optional second addend (same layout as the output rows)
+  long long ld1, ld2;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  bf16* out;
+  long long ldo;
+  float* mean;
+  float* rstd;
+  bf16* sum_out;  // optional: in1 + in2
+  long long lds;
+  long long rows;
+  int C;
+  // PatchMerging gather (swin_transformer.py:420-427): rows = B*(H/2)*(W/2), C = 4*Cin
+  int merge, H, W, Cin;
+  // backward
+  const bf16* dy;
+  long long lddy;
+  const bf16* dres;  // optional gradient added to dx (residual branch)
+  long long lddres;
+  bf16* dx;
+  long long lddx;
+  float* dgamma;
+  float* dbeta;
+};
+
+__device__ __forceinline__ long long ln_src_offset(const LnParams& p, long long row, int col) {
+  if (!p.merge) return row * p.ld1 + col;
+  const int W2 = p.W / 2, H2 = p.H / 2;
+  const long long b = row / (H2 * W2);
+  const int rem = static_cast<int>(row % (H2 * W2));
+  const int h2 = rem / W2, w2 = rem % W2;
+  const int seg = col / p.Cin, cin = col % p.Cin;
+  const long long src = b * p.H * p.W + (2 * h2 + (seg & 1)) * p.W + (2 * w2 + (seg >> 1));
+  return src * p.ld1 + cin;
+}
+
+__device__ __forceinline__ void load8(const bf16* ptr, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(ptr);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16(w[e]);
+    x[2 * e] = f.x; x[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* ptr, const float (&x)[8]) {
+  uint4 u;
+  u.x = pack_bf16(x[0], x[1]); u.y = pack_bf16(x[2], x[3]);
+  u.z = pack_bf16(x[4], x[5]); u.w = pack_bf16(x[6], x[7]);
+  *reinterpret_cast<uint4*>(ptr) = u;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invC = 1.0f / p.C;
+  for (long long row = warp_global; row < p.rows; row += nwarps) {
+    float x[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+        load8(p.in1 + ln_src_offset(p, row, col), x[v]);
+        if (p.in2) {
+          float y[8];
+          load8(p.in2 + row * p.ld2 + col, y);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[v][e] += y[e];
+          if (p.sum_out) store8(p.sum_out + row * p.lds + col, x[v]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += x[v][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[v][e] = 0.f;
+      }
+    }
+    const float mean = warp_sum(sum) * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = x[v][e] - mean; var += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(var) * invC + p.eps);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+        float y[8];
+        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + col);
+        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + col + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(p.beta + col);
+        const float4 b1 = *reinterpret_cast<const float4*>(p.beta + col + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (x[v][e] - mean) * rstd * g[e] + b[e];
+        store8(p.out + row * p.ldo + col, y);
+      }
+    }
+    if (lane == 0) {
+      if (p.mean) p.mean[row] = mean;
+      if (p.rstd) p.rstd[row] = rstd;
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnParams p) {
+  extern __shared__ float s_acc[];  // [2][C]: dgamma, dbeta block partials
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invC = 1.0f / p.C;
+  float dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[v][e] = db[v][e] = 0.f;
+
+  for (long long row = warp_global; row < p.rows; row += nwarps) {
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float xh[VPL][8], gy[VPL][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+        load8(p.in1 + ln_src_offset(p, row, col), xh[v]);
+        if (p.in2) {
+          float y[8];
+          load8(p.in2 + row * p.ld2 + col, y);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xh[v][e] += y[e];
+        }
+        float dy[8];
+        load8(p.dy + row * p.lddy + col, dy);
+        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + col);
+        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + col + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[v][e] = (xh[v][e] - mean) * rstd;
+          gy[v][e] = dy[e] * g[e];
+          c1 += gy[v][e];
+          c2 += gy[v][e] * xh[v][e];
+          dg[v][e] += dy[e] * xh[v][e];
+          db[v][e] += dy[e];
+        }
+      }
+    }
+    c1 = warp_sum(c1) * invC;
+    c2 = warp_sum(c2) * invC;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+        float dx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dx[e] = rstd * (gy[v][e] - c1 - xh[v][e] * c2);
+        if (p.dres) {
+          float r[8];
+          load8(p.dres + (p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddres + (col % p.Cin)
+                                  : row * p.lddres + col), r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dx[e] += r[e];
+        }
+        const long long off = p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddx + (col % p.Cin)
+                                      : row * p.lddx + col;
+        store8(p.dx + off, dx);
+      }
+    }
+  }
+  if (p.dgamma) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (lane + 32 * v) * 8;
+      if (col < p.C) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(&s_acc[col + e], dg[v][e]);
+          atomicAdd(&s_acc[p.C + col + e], db[v][e]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      atomicAdd(p.dgamma + i, s_acc[i]);
+      atomicAdd(p.dbeta + i, s_acc[p.C + i]);
+    }
+  }
+}
+
+static int ln_grid(long long rows) {
+  const long long blocks = (rows + 7) / 8;  // 8 warps per block
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <int VPL>
+static int ln_launch(const LnParams& p, bool bwd, cudaStream_t stream) {
+  if (!bwd) {
+    ln_fwd_kernel<VPL><<<ln_grid(p.rows), 256, 0, stream>>>(p);
+  } else {
+    int grid = ln_grid(p.rows);
+    const int cap = num_sms() * 2;  // fewer blocks => fewer global atomics for dgamma/dbeta
+    if (grid > cap) grid = cap;
+    ln_bwd_kernel<VPL><<<grid, 256, 2 * p.C * sizeof(float), stream>>>(p);
+  }
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
+  FIBER_CHECK(p.C % 8 == 0 && p.C >= 8 && p.C <= 2048, "LayerNorm width must be a multiple of 8 in [8, 2048] (got %d)", p.C);
+  FIBER_CHECK(p.rows > 0, "LayerNorm needs rows > 0");
+  if (p.merge) {
+    FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
+                "bad PatchMerging LayerNorm geometry");
+  }
+  if (p.C <= 256) return ln_launch<1>(p, bwd, stream);
+  if (p.C <= 512) return ln_launch<2>(p, bwd, stream);
+  if (p.C <= 768) return ln_launch<3>(p, bwd, stream);
+  if (p.C <= 1024) return ln_launch<4>(p, bwd, stream);
+  return ln_launch<8>(p, bwd, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sum (bias gradients):  out[n] (+)= scale * sum_m rs[m / rps] * x[m, n]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* x, long long ld, long long M, int N, float* out,
+                                                     const float* scale, const float* row_scale, int rps,
+                                                     long long rows_per_block) {
+  __shared__ float s_part[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + tx) * 8;
+  const long long r0 = blockIdx.y * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, M);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      float v[8];
+      load8(x + r * ld + col, v);
+      const float s = row_scale ? row_scale[r / rps] : 1.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e] * s;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_part[ty][tx * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;  // 256 columns of this block
+  float t = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) t += s_part[y][c];
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < N) atomicAdd(out + gc, t * (scale ? *scale : 1.0f));
+}
+
+// dot(a, b) -> *out += sum a[i]*b[i]   (2-D, row-major with independent leading dimensions)
+__global__ void __launch_bounds__(256) dot_kernel(const bf16* a, long long lda, const bf16* b, long long ldb,
+                                                  long long M, int N, float* out) {
+  __shared__ float s_w[8];
+  const int vec_per_row = N / 8;
+  const long long total = M * vec_per_row;
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    float x[8], y[8];
+    load8(a + r * lda + c, x);
+    load8(b + r * ldb + c, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += x[e] * y[e];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = s_w[threadIdx.x];
+    t += __shfl_xor_sync(0xffu, t, 4);
+    t += __shfl_xor_sync(0xffu, t, 2);
+    t += __shfl_xor_sync(0xffu, t, 1);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool keep_elem(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<float>(static_cast<uint32_t>(z >> 40)) * (1.0f / 16777216.0f) >= p;
+}
+
+// mode 0: y = dropout(x; p, seed) (same mask for forward and backward)
+// mode 1: y = x * row_scale[row / rps]
+__global__ void __launch_bounds__(256) rowwise_scale_kernel(const bf16* x, long long ldx, bf16* y, long long ldy,
+                                                            long long M, int N, int mode, float p,
+                                                            unsigned long long seed, const float* row_scale, int rps) {
+  const int vec_per_row = N / 8;
+  const long long total = M * vec_per_row;
+  const float keep_inv = 1.0f / (1.0f - p);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    float v[8];
+    load8(x + r * ldx + c, v);
+    if (mode == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        v[e] = keep_elem(seed, static_cast<unsigned long long>(r) * N + c + e, p) ? v[e] * keep_inv : 0.f;
+    } else {
+      const float s = row_scale[r / rps];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= s;
+    }
+    store8(y + r * ldy + c, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* x, bf16* y, long long n) {
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<uint2*>(y + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else {
+      for (long long j = i; j < n; ++j) y[j] = __float2bfloat16(x[j]);
+    }
+  }
+}
+
+// w f32 [N, K] (ldw) -> w_out bf16 [N, K] (ld_out) and wt_out bf16 [K, N] (ldt_out), either optional
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* w, long long ldw, int N, int K, bf16* w_out,
+                                                             long long ld_out, bf16* wt_out, long long ldt_out) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[n * ldw + k];
+      if (w_out) w_out[n * ld_out + k] = __float2bfloat16(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (wt_out) {
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + tx;
+      if (n < N && k < K) wt_out[k * ldt_out + n] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+
+// PatchEmbed gather (timm PatchEmbed conv 4x4/s4 as a GEMM, fiber_module.py:311):
+// img f32 [B,3,R,R] -> patches bf16 [B*(R/4)^2, 64]; column = c*16 + kh*4 + kw, columns 48..63 = 0.
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float* img, bf16* out, int B, int R) {
+  const int P = R / 4;
+  const long long total = static_cast<long long>(B) * P * P * 16;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i & 15);
+    const long long patch = i >> 4;
+    uint2 o = make_uint2(0u, 0u);
+    if (j < 12) {
+      const int c = j >> 2, kh = j & 3;
+      const int pw = static_cast<int>(patch % P), ph = static_cast<int>((patch / P) % P);
+      const long long b = patch / (P * P);
+      const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * R + (ph * 4 + kh)) * R + pw * 4);
+      o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    *reinterpret_cast<uint2*>(out + patch * 64 + j * 4) = o;
+  }
+}
+
+// RoBERTa embeddings (roberta.py:169-196): out[t] = word[id] + pos[pid] + type[0]; pid from the
+// running count of non-pad tokens (roberta.py:877-888).  One warp per token.
+__device__ __forceinline__ int roberta_pos_id(const long long* ids_row, int l, int pad, int lane) {
+  int count = 0;
+  for (int base = 0; base <= l; base += 32) {
+    const int j = base + lane;
+    const bool nz = (j <= l) && (ids_row[j] != pad);
+    count += __popc(__ballot_sync(0xffffffffu, nz));
+  }
+  return ids_row[l] != pad ? count + pad : pad;
+}
+
+__global__ void __launch_bounds__(256) embed_gather_kernel(const long long* ids, int B, int L, int C, int pad,
+                                                           const float* word, const float* pos, const float* type,
+                                                           bf16* out, long long ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long t = warp_global; t < static_cast<long long>(B) * L; t += nwarps) {
+    const int b = static_cast<int>(t / L), l = static_cast<int>(t % L);
+    const long long id = ids[t];
+    const int pid = roberta_pos_id(ids + static_cast<long long>(b) * L, l, pad, lane);
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 w = *reinterpret_cast<const float4*>(word + id * C + c);
+      const float4 q = *reinterpret_cast<const float4*>(pos + static_cast<long long>(pid) * C + c);
+      const float4 y = *reinterpret_cast<const float4*>(type + c);
+      *reinterpret_cast<uint2*>(out + t * ldo + c) =
+          make_uint2(pack_bf16(w.x + q.x + y.x, w.y + q.y + y.y), pack_bf16(w.z + q.z + y.z, w.w + q.w + y.w));
+    }
+  }
+}
+
+// scatter-add of d(embedding sum) into the word / position tables (fp32 atomics); the pad row of
+// both tables receives no gradient (nn.Embedding(padding_idx=1), roberta.py:150,165).
+__global__ void __launch_bounds__(256) embed_scatter_kernel(const long long* ids, int B, int L, int C, int pad,
+                                                            const bf16* dsum, long long ldd, float* dword,
+                                                            float* dpos) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long t = warp_global; t < static_cast<long long>(B) * L; t += nwarps) {
+    const int b = static_cast<int>(t / L), l = static_cast<int>(t % L);
+    const long long id = ids[t];
+    const int pid = roberta_pos_id(ids + static_cast<long long>(b) * L, l, pad, lane);
+    for (int c = lane * 2; c < C; c += 64) {
+      const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dsum + t * ldd + c));
+      if (id != pad) {
+        atomicAdd(dword + id * C + c, g.x);
+        atomicAdd(dword + id * C + c + 1, g.y);
+      }
+      if (pid != pad) {
+        atomicAdd(dpos + static_cast<long long>(pid) * C + c, g.x);
+        atomicAdd(dpos + static_cast<long long>(pid) * C + c + 1, g.y);
+      }
+    }
+  }
+}
+
+static int ew_grid(long long work_items) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks > 0 ? blocks : 1);
+}
+
+int colsum_dispatch(const bf16* x, long long ld, long long M, int N, float* out, const float* scale,
+                    const float* row_scale, int rps, cudaStream_t stream) {
+  FIBER_CHECK(N % 8 == 0 && M > 0, "colsum: N must be a multiple of 8");
+  const int gx = (N + 255) / 256;
+  long long gy = (2LL * num_sms() + gx - 1) / gx;
+  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+  if (gy < 1) gy = 1;
+  const long long rpb = (M + gy - 1) / gy;
+  colsum_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, stream>>>(x, ld, M, N, out, scale, row_scale,
+                                                                        rps > 0 ? rps : 1, rpb);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int dot_dispatch(const bf16* a, long long lda, const bf16* b, long long ldb, long long M, int N, float* out,
+                 cudaStream_t stream) {
+  FIBER_CHECK(N % 8 == 0 && M > 0, "dot: N must be a multiple of 8");
+  int grid = ew_grid(M * (N / 8));
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  dot_kernel<<<grid, 256, 0, stream>>>(a, lda, b, ldb, M, N, out);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int rowwise_scale_dispatch(const bf16* x, long long ldx, bf16* y, long long ldy, long long M, int N, int mode,
+                           float p, unsigned long long seed, const float* row_scale, int rps, cudaStream_t stream) {
+  FIBER_CHECK(N % 8 == 0 && M > 0, "rowwise op: N must be a multiple of 8");
+  FIBER_CHECK(mode == 0 ? (p >= 0.f && p < 1.f) : row_scale != nullptr, "bad rowwise op arguments");
+  rowwise_scale_kernel<<<ew_grid(M * (N / 8)), 256, 0, stream>>>(x, ldx, y, ldy, M, N, mode, p, seed, row_scale,
+                                                                rps > 0 ? rps : 1);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int cast_dispatch(const float* x, bf16* y, long long n, cudaStream_t stream) {
+  FIBER_CHECK(n > 0, "cast: empty");
+  cast_f32_bf16_kernel<<<ew_grid((n + 3) / 4), 256, 0, stream>>>(x, y, n);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int cast_transpose_dispatch(const float* w, long long ldw, int N, int K, bf16* w_out, long long ld_out, bf16* wt_out,
+                            long long ldt_out, cudaStream_t stream) {
+  FIBER_CHECK(N > 0 && K > 0, "cast_transpose: empty");
+  cast_transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), 256, 0, stream>>>(w, ldw, N, K, w_out, ld_out, wt_out,
+                                                                              ldt_out);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int patch_gather_dispatch(const float* img, bf16* out, int B, int R, cudaStream_t stream) {
+  FIBER_CHECK(B > 0 && R % 4 == 0, "patch_gather: image size must be a multiple of 4");
+  patch_gather_kernel<<<ew_grid(static_cast<long long>(B) * (R / 4) * (R / 4) * 16), 256, 0, stream>>>(img, out, B, R);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int embed_dispatch(const long long* ids, int B, int L, int C, int pad, const float* word, const float* pos,
+                   const float* type, bf16* out, long long ldo, cudaStream_t stream) {
+  FIBER_CHECK(C % 4 == 0 && B > 0 && L > 0, "embed: width must be a multiple of 4");
+  embed_gather_kernel<<<ew_grid(static_cast<long long>(B) * L * 32), 256, 0, stream>>>(ids, B, L, C, pad, word, pos,
+                                                                                      type, out, ldo);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int embed_scatter_dispatch(const long long* ids, int B, int L, int C, int pad, const bf16* dsum, long long ldd,
+                           float* dword, float* dpos, cudaStream_t stream) {
+  FIBER_CHECK(C % 2 == 0 && B > 0 && L > 0, "embed_scatter: width must be even");
+  embed_scatter_kernel<<<ew_grid(static_cast<long long>(B) * L * 32), 256, 0, stream>>>(ids, B, L, C, pad, dsum, ldd,
+                                                                                       dword, dpos);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace fiber

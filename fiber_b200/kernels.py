@@ -139,3 +139,150 @@ def attn_bwd(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, dbias_tab
     if dbias_table is not None:
         _req(dbias_table, F32, "dbias_table"); a.dbias_table = dbias_table.data_ptr()
     _lib.check(_lib.load().fiber_attn_bwd(C.byref(a), _stream()), "attn_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# row-wise kernels
+# ---------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, *, add=None, want_sum=False, merge=None, save_stats=True):
+    """y = LN(x [+ add]).  merge=(B, H, W): x is [B*H*W, Cin] and rows are the 2x2-merged tokens.
+    Returns (y, mean, rstd, sum_or_None)."""
+    _req(x, BF16, "x"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta")
+    a = _lib.LnArgs()
+    a.in1, a.ld1 = x.data_ptr(), _rowmajor_2d(x, "x")
+    if merge is not None:
+        B, H, W = merge
+        cin = x.shape[1]
+        rows, c = B * (H // 2) * (W // 2), 4 * cin
+        a.merge, a.h, a.w, a.cin = 1, H, W, cin
+    else:
+        rows, c = x.shape
+    y = torch.empty((rows, c), device=x.device, dtype=BF16)
+    a.out, a.ldo, a.rows, a.c = y.data_ptr(), c, rows, c
+    a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
+    mean = rstd = s = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=F32)
+        rstd = torch.empty(rows, device=x.device, dtype=F32)
+        a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    if add is not None:
+        _req(add, BF16, "add"); a.in2, a.ld2 = add.data_ptr(), _rowmajor_2d(add, "add")
+        if want_sum:
+            s = torch.empty((rows, c), device=x.device, dtype=BF16)
+            a.sum_out, a.lds = s.data_ptr(), c
+    _lib.check(_lib.load().fiber_layernorm_fwd(C.byref(a), _stream()), "layernorm_fwd")
+    return y, mean, rstd, s
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, merge=None, dres=None, dgamma=None, dbeta=None):
+    """Returns dx (shape of x).  dgamma/dbeta (fp32) are accumulated into when given."""
+    _req(dy, BF16, "dy"); _req(x, BF16, "x")
+    a = _lib.LnArgs()
+    a.in1, a.ld1 = x.data_ptr(), _rowmajor_2d(x, "x")
+    rows, c = dy.shape
+    if merge is not None:
+        B, H, W = merge
+        a.merge, a.h, a.w, a.cin = 1, H, W, x.shape[1]
+    if add is not None:
+        a.in2, a.ld2 = add.data_ptr(), _rowmajor_2d(add, "add")
+    a.rows, a.c = rows, c
+    a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dy, a.lddy = dy.data_ptr(), _rowmajor_2d(dy, "dy")
+    dx = torch.empty_like(x)
+    a.dx, a.lddx = dx.data_ptr(), dx.stride(0)
+    if dres is not None:
+        _req(dres, BF16, "dres"); a.dres, a.lddres = dres.data_ptr(), _rowmajor_2d(dres, "dres")
+    if dgamma is not None:
+        _req(dgamma, F32, "dgamma"); _req(dbeta, F32, "dbeta")
+        a.dgamma, a.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    _lib.check(_lib.load().fiber_layernorm_bwd(C.byref(a), _stream()), "layernorm_bwd")
+    return dx
+
+
+def colsum(x, out=None, scale=None, row_scale=None, rows_per_scale=1):
+    _req(x, BF16, "x")
+    m, n = x.shape
+    if out is None:
+        out = torch.zeros(n, device=x.device, dtype=F32)
+    _lib.check(_lib.load().fiber_colsum(x.data_ptr(), _rowmajor_2d(x, "x"), m, n, out.data_ptr(), _ptr(scale),
+                                        _ptr(row_scale), rows_per_scale, _stream()), "colsum")
+    return out
+
+
+def dot(a, b, out=None):
+    _req(a, BF16, "a"); _req(b, BF16, "b")
+    m, n = a.shape
+    if out is None:
+        out = torch.zeros(1, device=a.device, dtype=F32)
+    _lib.check(_lib.load().fiber_dot(a.data_ptr(), _rowmajor_2d(a, "a"), b.data_ptr(), _rowmajor_2d(b, "b"), m, n,
+                                     out.data_ptr(), _stream()), "dot")
+    return out
+
+
+def dropout(x, p, seed, out=None):
+    _req(x, BF16, "x")
+    m, n = x.shape
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_dropout(x.data_ptr(), _rowmajor_2d(x, "x"), out.data_ptr(), out.stride(0), m, n,
+                                         float(p), int(seed), _stream()), "dropout")
+    return out
+
+
+def scale_rows(x, row_scale, rows_per_scale, out=None):
+    _req(x, BF16, "x"); _req(row_scale, F32, "row_scale")
+    m, n = x.shape
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_scale_rows(x.data_ptr(), _rowmajor_2d(x, "x"), out.data_ptr(), out.stride(0), m, n,
+                                            row_scale.data_ptr(), rows_per_scale, _stream()), "scale_rows")
+    return out
+
+
+def cast_bf16(x):
+    _req(x, F32, "x")
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast")
+    return y
+
+
+def cast_transpose(w, w_out=None, wt_out=None):
+    """fp32 [N,K] -> bf16 [N,K] view and/or bf16 [K,N] view (views may be slices of packed buffers)."""
+    _req(w, F32, "w")
+    n, k = w.shape
+    _lib.check(_lib.load().fiber_cast_transpose(
+        w.data_ptr(), _rowmajor_2d(w, "w"), n, k,
+        _ptr(w_out), 0 if w_out is None else w_out.stride(0),
+        _ptr(wt_out), 0 if wt_out is None else wt_out.stride(0), _stream()), "cast_transpose")
+
+
+def patch_gather(img):
+    _req(img, F32, "img")
+    img = img.contiguous()
+    b, ch, r, r2 = img.shape
+    if ch != 3 or r != r2:
+        raise RuntimeError("fiber_b200.patch_gather expects [B,3,R,R]")
+    out = torch.empty((b * (r // 4) ** 2, 64), device=img.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_patch_gather(img.data_ptr(), out.data_ptr(), b, r, _stream()), "patch_gather")
+    return out
+
+
+def embed_gather(ids, word, pos, type_, pad_id=1):
+    if ids.dtype != torch.int64 or not ids.is_cuda:
+        raise RuntimeError("fiber_b200.embed_gather: ids must be a CUDA int64 tensor")
+    ids = ids.contiguous()
+    b, l = ids.shape
+    c = word.shape[1]
+    out = torch.empty((b * l, c), device=ids.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_embed_gather(ids.data_ptr(), b, l, c, pad_id, word.data_ptr(), pos.data_ptr(),
+                                              type_.data_ptr(), out.data_ptr(), c, _stream()), "embed_gather")
+    return out
+
+
+def embed_scatter(ids, dsum, dword, dpos, pad_id=1):
+    ids = ids.contiguous()
+    b, l = ids.shape
+    _lib.check(_lib.load().fiber_embed_scatter(ids.data_ptr(), b, l, dsum.shape[1], pad_id, dsum.data_ptr(),
+                                               _rowmajor_2d(dsum, "dsum"), dword.data_ptr(), dpos.data_ptr(),
+                                               _stream()), "embed_scatter")

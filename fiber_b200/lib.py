@@ -49,6 +49,19 @@ class AttnArgs(C.Structure):
     ]
 
 
+class LnArgs(C.Structure):
+    """Mirror of `fiber_ln_args` (include/fiber_b200.h)."""
+    _fields_ = [
+        ("in1", C.c_void_p), ("in2", C.c_void_p), ("ld1", C.c_int64), ("ld2", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("sum_out", C.c_void_p), ("lds", C.c_int64), ("rows", C.c_int64), ("c", C.c_int32),
+        ("merge", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
+        ("dy", C.c_void_p), ("lddy", C.c_int64), ("dres", C.c_void_p), ("lddres", C.c_int64),
+        ("dx", C.c_void_p), ("lddx", C.c_int64), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
 def declared_symbols():
     """Every `fiber_*` function declared in include/fiber_b200.h (parsed from the header)."""
     import re
@@ -73,6 +86,18 @@ def load():
     lib.fiber_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.fiber_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.fiber_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    V, I64, I32, F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+    lib.fiber_layernorm_fwd.argtypes = [C.POINTER(LnArgs), V]
+    lib.fiber_layernorm_bwd.argtypes = [C.POINTER(LnArgs), V]
+    lib.fiber_colsum.argtypes = [V, I64, I64, I32, V, V, V, I32, V]
+    lib.fiber_dot.argtypes = [V, I64, V, I64, I64, I32, V, V]
+    lib.fiber_dropout.argtypes = [V, I64, V, I64, I64, I32, F, C.c_uint64, V]
+    lib.fiber_scale_rows.argtypes = [V, I64, V, I64, I64, I32, V, I32, V]
+    lib.fiber_cast_f32_bf16.argtypes = [V, V, I64, V]
+    lib.fiber_cast_transpose.argtypes = [V, I64, I32, I32, V, I64, V, I64, V]
+    lib.fiber_patch_gather.argtypes = [V, V, I32, I32, V]
+    lib.fiber_embed_gather.argtypes = [V, I32, I32, I32, I32, V, V, V, V, I64, V]
+    lib.fiber_embed_scatter.argtypes = [V, I32, I32, I32, I32, V, I64, V, V, V]
     _lib = lib
     return lib
 

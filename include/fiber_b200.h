@@ -105,6 +105,69 @@ typedef struct fiber_attn_args {
 int fiber_attn_fwd(const fiber_attn_args* args, fiber_stream_t stream);
 int fiber_attn_bwd(const fiber_attn_args* args, fiber_stream_t stream);
 
+/* ---- LayerNorm (nn.LayerNorm: swin_transformer.py:362,391,429,240; roberta.py:197,485,422) ---
+ * y = LN(in1 [+ in2]) * gamma + beta over the last dimension (width c, multiple of 8, <= 2048).
+ * merge != 0 fuses PatchMerging's 2x2 neighbour gather + concat (swin_transformer.py:420-427):
+ *   in1 is the image-ordered [B*H*W, cin] activation, rows = B*(H/2)*(W/2), c = 4*cin.
+ * Forward writes mean/rstd (fp32 per row) for the backward pass and optionally in1+in2 (sum_out).
+ * Backward: dx = LN'(dy) [+ dres]; dgamma/dbeta are ACCUMULATED (fp32 atomics; caller zeroes).
+ */
+typedef struct fiber_ln_args {
+  const void* in1;
+  const void* in2;
+  int64_t ld1, ld2;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  void* out;
+  int64_t ldo;
+  float* mean;
+  float* rstd;
+  void* sum_out;
+  int64_t lds;
+  int64_t rows;
+  int32_t c;
+  int32_t merge, h, w, cin;
+  /* backward only */
+  const void* dy;
+  int64_t lddy;
+  const void* dres;
+  int64_t lddres;
+  void* dx;
+  int64_t lddx;
+  float* dgamma;
+  float* dbeta;
+} fiber_ln_args;
+
+int fiber_layernorm_fwd(const fiber_ln_args* args, fiber_stream_t stream);
+int fiber_layernorm_bwd(const fiber_ln_args* args, fiber_stream_t stream);
+
+/* out[n] += (*scale) * sum_m row_scale[m / rows_per_scale] * x[m, n]   (nn.Linear bias gradients) */
+int fiber_colsum(const void* x, int64_t ld, int64_t m, int32_t n, float* out, const float* scale,
+                 const float* row_scale, int32_t rows_per_scale, fiber_stream_t stream);
+/* *out += sum_{m,n} a[m,n] * b[m,n]   (gradients of the alpha_i2t / alpha_t2i gates) */
+int fiber_dot(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int32_t n, float* out,
+              fiber_stream_t stream);
+/* y = dropout(x; p, seed): counter-based mask, identical for forward and backward (nn.Dropout,
+ * roberta.py:198,339,419) */
+int fiber_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, float p, uint64_t seed,
+                  fiber_stream_t stream);
+/* y[m,:] = x[m,:] * row_scale[m / rows_per_scale]   (timm DropPath, swin_transformer.py:390-391) */
+int fiber_scale_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, const float* row_scale,
+                     int32_t rows_per_scale, fiber_stream_t stream);
+int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t stream);
+/* fp32 master weight [n,k] -> bf16 copy [n,k] (ld_out) and/or transposed bf16 copy [k,n] (ldt_out) */
+int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void* w_out, int64_t ld_out, void* wt_out,
+                         int64_t ldt_out, fiber_stream_t stream);
+/* timm PatchEmbed im2row: img fp32 [B,3,R,R] -> bf16 [B*(R/4)^2, 64], col = c*16+kh*4+kw, cols 48..63 zero */
+int fiber_patch_gather(const float* img, void* out, int32_t batch, int32_t r, fiber_stream_t stream);
+/* RobertaEmbeddings sum (roberta.py:169-196): out[t] = word[ids[t]] + pos[pos_id(t)] + type[0] */
+int fiber_embed_gather(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const float* word,
+                       const float* pos, const float* type, void* out, int64_t ldo, fiber_stream_t stream);
+/* backward of the two gathers: dword[ids[t]] += dsum[t], dpos[pos_id(t)] += dsum[t] (pad rows skipped) */
+int fiber_embed_scatter(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const void* dsum,
+                        int64_t ldd, float* dword, float* dpos, fiber_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,125 @@
+"""Row-wise kernels vs torch fp32 on the same bf16 inputs (GPU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fiber_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, dev, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(dtype)
+
+
+def _close(a, b, tol, name):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * max(ref, 1e-3), "%s: max err %g vs ref max %g" % (name, err, ref)
+
+
+@pytest.mark.parametrize("rows,C,add", [(1000, 128, False), (333, 256, True), (77, 512, False), (2560, 768, True),
+                                        (500, 1024, False), (144, 2048, False), (9, 8, False)])
+def test_layernorm_fwd_bwd(cuda_dev, rows, C, add):
+    from fiber_b200 import kernels as K
+    x = _rand((rows, C), cuda_dev, 1)
+    x2 = _rand((rows, C), cuda_dev, 2) if add else None
+    g = _rand((C,), cuda_dev, 3, 0.1, torch.float32) + 1.0
+    b = _rand((C,), cuda_dev, 4, 0.1, torch.float32)
+    dy = _rand((rows, C), cuda_dev, 5)
+    dres = _rand((rows, C), cuda_dev, 6)
+    y, mean, rstd, s = K.layernorm_fwd(x, g, b, 1e-5, add=x2, want_sum=add)
+    xf = (x.float() + (x2.float() if add else 0)).requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xf, (C,), gf, bf, 1e-5)
+    _close(y, ref, 1e-2, "y")
+    if add:
+        _close(s, xf, 1e-2, "sum")
+    ref.backward(dy.float())
+    dg, db = torch.zeros_like(g), torch.zeros_like(b)
+    dx = K.layernorm_bwd(dy, x, mean, rstd, g, add=x2, dres=dres, dgamma=dg, dbeta=db)
+    _close(dx, xf.grad + dres.float(), 1.5e-2, "dx")
+    _close(dg, gf.grad, 1e-2, "dgamma")
+    _close(db, bf.grad, 1e-2, "dbeta")
+
+
+def test_layernorm_patch_merging(cuda_dev):
+    from fiber_b200 import kernels as K
+    B, H, C = 3, 12, 64
+    x = _rand((B * H * H, C), cuda_dev, 1)
+    g = _rand((4 * C,), cuda_dev, 3, 0.1, torch.float32) + 1.0
+    b = _rand((4 * C,), cuda_dev, 4, 0.1, torch.float32)
+    y, mean, rstd, _ = K.layernorm_fwd(x, g, b, 1e-5, merge=(B, H, H))
+    xf = x.float().view(B, H * H, C).requires_grad_(True)
+    xm = xf.view(B, H // 2, 2, H // 2, 2, C).permute(0, 1, 3, 4, 2, 5).reshape(B * (H // 2) ** 2, 4 * C)
+    ref = F.layer_norm(xm, (4 * C,), g, b, 1e-5)
+    _close(y, ref, 1e-2, "y")
+    dy = _rand(tuple(ref.shape), cuda_dev, 5)
+    ref.backward(dy.float())
+    dg, db = torch.zeros_like(g), torch.zeros_like(b)
+    dx = K.layernorm_bwd(dy, x, mean, rstd, g, merge=(B, H, H), dgamma=dg, dbeta=db)
+    _close(dx.view(B, H * H, C), xf.grad, 1.5e-2, "dx")
+
+
+def test_colsum_dot_scale_dropout_cast(cuda_dev):
+    from fiber_b200 import kernels as K
+    x = _rand((5000, 384), cuda_dev, 1)
+    rs = torch.rand(50, device=cuda_dev) + 0.5
+    sc = torch.tensor([0.25], device=cuda_dev)
+    out = K.colsum(x, scale=sc, row_scale=rs, rows_per_scale=100)
+    ref = (x.float() * rs.repeat_interleave(100)[:, None]).sum(0) * 0.25
+    _close(out, ref, 2e-3, "colsum")
+    out = K.colsum(x[:, 128:256])
+    _close(out, x[:, 128:256].float().sum(0), 2e-3, "colsum view")
+    y = _rand((5000, 384), cuda_dev, 2)
+    d = K.dot(x, y)
+    _close(d, (x.float() * y.float()).sum().view(1), 2e-3, "dot")
+    z = K.scale_rows(x, rs, 100)
+    _close(z, x.float() * rs.repeat_interleave(100)[:, None], 1e-2, "scale_rows")
+    dr = K.dropout(x, 0.1, 7)
+    dr2 = K.dropout(x, 0.1, 7)
+    assert torch.equal(dr, dr2)
+    kept = (dr != 0).float().mean().item()
+    assert abs(kept - 0.9) < 0.01
+    m = dr != 0
+    _close(dr[m], x.float()[m] / 0.9, 1e-2, "dropout scale")
+    f = torch.randn(1001, device=cuda_dev)
+    assert torch.equal(K.cast_bf16(f), f.to(torch.bfloat16))
+
+
+def test_cast_transpose_and_patch_gather(cuda_dev):
+    from fiber_b200 import kernels as K
+    w = torch.randn(100, 48, device=cuda_dev)
+    wo = torch.zeros(100, 64, device=cuda_dev, dtype=torch.bfloat16)
+    wt = torch.zeros(64, 104, device=cuda_dev, dtype=torch.bfloat16)
+    K.cast_transpose(w, wo, wt)
+    assert torch.equal(wo[:, :48], w.to(torch.bfloat16)) and float(wo[:, 48:].abs().sum()) == 0
+    assert torch.equal(wt[:48, :100], w.t().to(torch.bfloat16))
+    img = torch.randn(2, 3, 32, 32, device=cuda_dev)
+    p = K.patch_gather(img)
+    ref = img.view(2, 3, 8, 4, 8, 4).permute(0, 2, 4, 1, 3, 5).reshape(2 * 64, 48)
+    assert torch.equal(p[:, :48], ref.to(torch.bfloat16)) and float(p[:, 48:].abs().sum()) == 0
+
+
+def test_embeddings_gather_scatter(cuda_dev):
+    from fiber_b200 import kernels as K
+    V, C, L = 200, 768, 40
+    word = torch.randn(V, C, device=cuda_dev) * 0.1
+    pos = torch.randn(L + 2, C, device=cuda_dev) * 0.1
+    typ = torch.randn(1, C, device=cuda_dev) * 0.1
+    ids = torch.randint(3, V, (5, L), device=cuda_dev)
+    ids[1, 20:] = 1
+    ids[3, 33:] = 1
+    out = K.embed_gather(ids, word, pos, typ)
+    pid = O.roberta_position_ids(ids)
+    ref = word[ids] + pos[pid] + typ[0]
+    _close(out.view(5, L, C), ref, 1e-2, "embed")
+    d = _rand((5 * L, C), cuda_dev, 3)
+    dw, dp = torch.zeros_like(word), torch.zeros_like(pos)
+    K.embed_scatter(ids, d, dw, dp)
+    w2, p2 = word.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    (F.embedding(ids, w2, padding_idx=1) + F.embedding(pid, p2, padding_idx=1)).backward(d.float().view(5, L, C))
+    _close(dw, w2.grad, 1e-3, "dword")
+    _close(dp, p2.grad, 1e-3, "dpos")
