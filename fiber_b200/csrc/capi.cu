@@ -67,6 +67,8 @@ int dot_dispatch(const bf16*, long long, const bf16*, long long, long long, int,
 int rowwise_scale_dispatch(const bf16*, long long, bf16*, long long, long long, int, int, float, unsigned long long,
                            const float*, int, cudaStream_t);
 int cast_dispatch(const float*, bf16*, long long, cudaStream_t);
+int axpy_dispatch(const bf16*, long long, const bf16*, long long, const float*, bf16*, long long, long long, int,
+                  cudaStream_t);
 int cast_transpose_dispatch(const float*, long long, int, int, bf16*, long long, bf16*, long long, cudaStream_t);
 int patch_gather_dispatch(const float*, bf16*, int, int, cudaStream_t);
 int embed_dispatch(const long long*, int, int, int, int, const float*, const float*, const float*, bf16*, long long,
@@ -157,6 +159,10 @@ int fiber_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, i
 int fiber_scale_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, const float* row_scale,
                      int32_t rps, fiber_stream_t s) {
   return fiber::rowwise_scale_dispatch(FIBER_B(x), ldx, FIBER_BM(y), ldy, m, n, 1, 0.f, 0, row_scale, rps, FIBER_S(s));
+}
+int fiber_axpy(const void* x, int64_t ldx, const void* add, int64_t ldadd, const float* alpha, void* out, int64_t ldo,
+               int64_t m, int32_t n, fiber_stream_t s) {
+  return fiber::axpy_dispatch(FIBER_B(x), ldx, FIBER_B(add), ldadd, alpha, FIBER_BM(out), ldo, m, n, FIBER_S(s));
 }
 int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t s) {
   return fiber::cast_dispatch(x, FIBER_BM(y), n, FIBER_S(s));

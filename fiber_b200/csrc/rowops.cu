@@ -352,6 +352,25 @@ __global__ void __launch_bounds__(256) rowwise_scale_kernel(const bf16* x, long 
   }
 }
 
+// out = add + (*alpha) * x   (gate: a + alpha_t2i * c, roberta.py:483; plain residual add when alpha == null)
+__global__ void __launch_bounds__(256) axpy_kernel(const bf16* x, long long ldx, const bf16* add, long long lda,
+                                                   const float* alpha, bf16* out, long long ldo, long long M, int N) {
+  const int vec_per_row = N / 8;
+  const long long total = M * vec_per_row;
+  const float al = alpha ? *alpha : 1.0f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    float v[8], w[8];
+    load8(x + r * ldx + c, v);
+    load8(add + r * lda + c, w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = w[e] + al * v[e];
+    store8(out + r * ldo + c, v);
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* x, bf16* y, long long n) {
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
@@ -506,6 +525,15 @@ int rowwise_scale_dispatch(const bf16* x, long long ldx, bf16* y, long long ldy,
   FIBER_CHECK(mode == 0 ? (p >= 0.f && p < 1.f) : row_scale != nullptr, "bad rowwise op arguments");
   rowwise_scale_kernel<<<ew_grid(M * (N / 8)), 256, 0, stream>>>(x, ldx, y, ldy, M, N, mode, p, seed, row_scale,
                                                                 rps > 0 ? rps : 1);
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int axpy_dispatch(const bf16* x, long long ldx, const bf16* add, long long lda, const float* alpha, bf16* out,
+                  long long ldo, long long M, int N, cudaStream_t stream) {
+  FIBER_CHECK(N % 8 == 0 && M > 0, "axpy: N must be a multiple of 8");
+  axpy_kernel<<<ew_grid(M * (N / 8)), 256, 0, stream>>>(x, ldx, add, lda, alpha, out, ldo, M, N);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

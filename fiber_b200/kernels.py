@@ -286,3 +286,13 @@ def embed_scatter(ids, dsum, dword, dpos, pad_id=1):
     _lib.check(_lib.load().fiber_embed_scatter(ids.data_ptr(), b, l, dsum.shape[1], pad_id, dsum.data_ptr(),
                                                _rowmajor_2d(dsum, "dsum"), dword.data_ptr(), dpos.data_ptr(),
                                                _stream()), "embed_scatter")
+
+
+def axpy(x, add, alpha=None):
+    """add + alpha * x (alpha: 1-element fp32 device tensor or None for 1)."""
+    _req(x, BF16, "x"); _req(add, BF16, "add")
+    m, n = x.shape
+    out = torch.empty((m, n), device=x.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_axpy(x.data_ptr(), _rowmajor_2d(x, "x"), add.data_ptr(), _rowmajor_2d(add, "add"),
+                                      _ptr(alpha), out.data_ptr(), n, m, n, _stream()), "axpy")
+    return out

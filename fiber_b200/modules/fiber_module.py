@@ -1,0 +1,229 @@
+"""FIBERTransformerSS — host-side mirror of coarse_grained/fiber/modules/fiber_module.py:26-523.
+
+Same constructor argument (the sacred `_config` dict), sub-module names, state_dict keys and
+`infer` / `forward` / `training_step` contracts as the reference, so coarse_grained/run.py and the
+ITM / ITC / MLM / VQA objectives sit on top unchanged; the fused backbone underneath runs on the
+sm_100a kernels of this package (no eager or CPU fallback: calling it without the CUDA library or
+with CPU tensors raises)."""
+import torch
+import torch.nn as nn
+
+from . import fiber_utils, heads, objectives, roberta, swin_transformer
+from .lightning import LightningModule
+from .roberta import RobertaModel
+from .swin_transformer import FLinear
+
+
+@torch.no_grad()
+def concat_all_gather(tensor):
+    """fiber_module.py:12-24; a single process is its own world."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return tensor
+    tensors_gather = [torch.ones_like(tensor) for _ in range(torch.distributed.get_world_size())]
+    torch.distributed.all_gather(tensors_gather, tensor, async_op=False)
+    return torch.cat(tensors_gather, dim=0)
+
+
+def _flinear_fp32(i, o):
+    m = FLinear(i, o)
+    m.out_fp32 = True
+    return m
+
+
+class FIBERTransformerSS(LightningModule):
+    def __init__(self, config):
+        super().__init__()
+        self.save_hyperparameters(config=config) if not hasattr(self.hparams, "config") else None
+        self.hparams["config"] = config
+        self.config = config
+        hs = config["hidden_size"]
+        self.num_fuse_block = config["num_fuse_block"]
+        self.num_text_layer = config["num_layers"]
+        roberta.NUM_FUSE_BLOCK = swin_transformer.NUM_FUSE_BLOCK = self.num_fuse_block
+        roberta.DIM_IMG = config["input_image_embed_size"]
+
+        self.cross_modal_text_transform = _flinear_fp32(config["input_text_embed_size"], hs)
+        self.cross_modal_image_transform = _flinear_fp32(config["input_image_embed_size"], hs)
+        self.cross_modal_text_transform_itc = _flinear_fp32(config["input_text_embed_size"], hs)
+        self.cross_modal_image_transform_itc = _flinear_fp32(config["input_image_embed_size"], hs)
+        for m in (self.cross_modal_text_transform, self.cross_modal_image_transform,
+                  self.cross_modal_text_transform_itc, self.cross_modal_image_transform_itc):
+            m.apply(objectives.init_weights)
+
+        if config["loss_names"]["itc"] > 0:  # ALBEF queues, fiber_module.py:61-70
+            self.temp = nn.Parameter(torch.ones([]) * 0.07)
+            self.queue_size = 4096
+            self.register_buffer("image_queue", torch.randn(hs, self.queue_size))
+            self.register_buffer("text_queue", torch.randn(hs, self.queue_size))
+            self.register_buffer("image_input_queue",
+                                 torch.randn(self.queue_size, 3, config["image_size"], config["image_size"]))
+            self.register_buffer("text_input_queue", torch.zeros(self.queue_size, config["max_text_len"], dtype=torch.long))
+            self.register_buffer("text_input_mask_queue",
+                                 torch.zeros(self.queue_size, config["max_text_len"], dtype=torch.long))
+            self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+            self.register_buffer("queue_total", torch.zeros(1, dtype=torch.long))
+
+        self.vit_model = getattr(swin_transformer, config["vit"])(pretrained=config["pretrained_vit"], config=config)
+        self.avgpool = nn.AdaptiveAvgPool1d(1)
+        self.text_transformer = RobertaModel.from_pretrained(config["tokenizer"])
+
+        self.cross_modal_image_pooler = heads.Pooler(hs)
+        self.cross_modal_text_pooler = heads.Pooler(hs)
+        self.cross_modal_image_pooler.apply(objectives.init_weights)
+        self.cross_modal_text_pooler.apply(objectives.init_weights)
+        self.itc_pooler = config["itc_pooler"]
+        if self.itc_pooler:
+            self.cross_modal_image_pooler_itc = heads.Pooler(hs)
+            self.cross_modal_text_pooler_itc = heads.Pooler(hs)
+            self.cross_modal_image_pooler_itc.apply(objectives.init_weights)
+            self.cross_modal_text_pooler_itc.apply(objectives.init_weights)
+
+        ln = config["loss_names"]
+        for k in ("caption_mle", "caption_gold", "caption_cider", "nlvr2"):
+            if ln.get(k, 0) > 0:
+                raise NotImplementedError("%s is outside the B200 hot-path scope (SURVEY.md §8)" % k)
+        if ln["mlm"] > 0:
+            self.mlm_score = heads.MLMHead(hs, config["vocab_size"])
+            self.mlm_score.apply(objectives.init_weights)
+        if ln["itm"] > 0:
+            self.itm_score = heads.ITMHead(hs * 2)
+            self.itm_score.apply(objectives.init_weights)
+            self.rank_output = nn.Linear(hs, 1)  # aliases itm_score.fc row 1 (fiber_module.py:112-114)
+            self.rank_output.weight.data = self.itm_score.fc.weight.data[1:, :]
+            self.rank_output.bias.data = self.itm_score.fc.bias.data[1:]
+
+        if config["load_path"] != "" and not config["test_only"]:
+            self._load(config["load_path"])
+        if ln["vqa"] > 0:
+            vs = config["vqav2_label_size"]
+            self.vqa_classifier = nn.Sequential(nn.Linear(hs * 2, hs * 2), nn.LayerNorm(hs * 2), nn.GELU(),
+                                                nn.Linear(hs * 2, vs))
+            self.vqa_classifier.apply(objectives.init_weights)
+        fiber_utils.set_metrics(self)
+        self.current_tasks = list()
+        if config["load_path"] != "" and config["test_only"]:
+            self._load(config["load_path"])
+
+    def _load(self, path):
+        state_dict = torch.load(path, map_location="cpu")["state_dict"]
+        for key in ["image_queue", "text_queue", "queue_ptr", "queue_total", "image_input_queue", "text_input_queue",
+                    "text_input_mask_queue"]:
+            state_dict.pop(key, None)
+        self.load_state_dict(state_dict, strict=False)
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, image_feat, text_feat, image_input, text_input, text_input_mask):
+        """fiber_module.py:181-222 (ring buffer with wrap-around)."""
+        image_feats = concat_all_gather(image_feat)
+        text_feats = concat_all_gather(text_feat)
+        image_input = concat_all_gather(image_input)
+        text_input = concat_all_gather(text_input)
+        text_input_mask = concat_all_gather(text_input_mask)
+        n = image_feats.shape[0]
+        ptr, total = int(self.queue_ptr), int(self.queue_total)
+        idx = (ptr + torch.arange(n, device=image_feats.device)) % self.queue_size
+        self.image_queue[:, idx] = image_feats.T.float()
+        self.text_queue[:, idx] = text_feats.T.float()
+        self.image_input_queue[idx] = image_input
+        self.text_input_queue[idx] = text_input
+        self.text_input_mask_queue[idx] = text_input_mask
+        self.queue_ptr[0] = (ptr + n) % self.queue_size
+        self.queue_total[0] = total + n
+
+    def infer(self, batch, mask_text=False, mask_image=False, image_token_type_idx=1, img=None, text_only=False,
+              image_only=False):
+        if not text_only and img is None:
+            imgkey = f"image_{image_token_type_idx - 1}" if f"image_{image_token_type_idx - 1}" in batch else "image"
+            img = batch[imgkey][0]
+        text_ids = text_labels = text_masks = None
+        if not image_only:
+            do_mlm = "_mlm" if mask_text else ""
+            text_ids = batch[f"text_ids{do_mlm}"]
+            text_labels = batch[f"text_labels{do_mlm}"]
+            text_masks = batch["text_masks"]
+        tt, vit = self.text_transformer, self.vit_model
+
+        if text_only:  # fiber_module.py:249-276
+            text_embeds = tt.embeddings(input_ids=text_ids)
+            ext = tt.get_extended_attention_mask(text_masks, text_masks.size(), text_embeds.device)
+            for layer in tt.encoder.layer:
+                text_embeds = layer(text_embeds, ext)[0]
+            text_embeds = self.cross_modal_text_transform_itc(text_embeds)
+            cls = self.cross_modal_text_pooler_itc(text_embeds) if self.itc_pooler else text_embeds[:, 0]
+            cls = cls / cls.norm(dim=-1, keepdim=True)
+            return {"text_feats": text_embeds, "image_feats": None, "cls_feats": cls, "text_labels": text_labels,
+                    "text_ids": text_ids, "text_masks": text_masks, "image": None}
+
+        image_embeds = vit.pos_drop(vit.patch_embed(img))
+        if image_only:  # fiber_module.py:278-308
+            for layer in vit.layers:
+                image_embeds = layer(image_embeds)
+            image_embeds = self.cross_modal_image_transform_itc(vit.norm(image_embeds))
+            avg = image_embeds.mean(dim=1, keepdim=True)
+            cls = self.cross_modal_image_pooler_itc(avg) if self.itc_pooler else avg[:, 0]
+            cls = cls / cls.norm(dim=-1, keepdim=True)
+            return {"text_feats": None, "image_feats": image_embeds, "cls_feats": cls, "text_labels": None,
+                    "text_ids": None, "text_masks": None, "image": None}
+
+        # fused pass, fiber_module.py:310-367
+        for layer in vit.layers[:2]:
+            image_embeds = layer(image_embeds)
+        text_embeds = tt.embeddings(input_ids=text_ids)
+        ext = tt.get_extended_attention_mask(text_masks, text_masks.size(), text_embeds.device)
+        num_pre_text = self.num_text_layer - self.num_fuse_block
+        for layer in tt.encoder.layer[:num_pre_text]:
+            text_embeds = layer(text_embeds, ext)[0]
+        num_pre_block = 8 + num_pre_text
+        for blk_cnt, blk in enumerate(vit.layers[2].blocks):
+            if blk_cnt < num_pre_block:
+                image_embeds = blk(image_embeds)
+            else:  # the two towers exchange their PREVIOUS states (:330-334)
+                fuse_image_embeds = blk(image_embeds, text_embeds, ext)
+                text_embeds = tt.encoder.layer[blk_cnt - 8](text_embeds, ext, encoder_hidden_states=image_embeds)[0]
+                image_embeds = fuse_image_embeds
+        if vit.layers[2].downsample is not None:
+            image_embeds = vit.layers[2].downsample(image_embeds)
+        for blk_cnt, blk in enumerate(vit.layers[3].blocks):
+            fuse_image_embeds = blk(image_embeds, text_embeds, ext)
+            text_embeds = tt.encoder.layer[blk_cnt + 10](text_embeds, ext, encoder_hidden_states=image_embeds,
+                                                         last_norm=(blk_cnt == 0))[0]
+            image_embeds = fuse_image_embeds
+        text_embeds = self.cross_modal_text_transform(text_embeds)
+        image_embeds = self.cross_modal_image_transform(image_embeds)
+        cls_feats_text = self.cross_modal_text_pooler(text_embeds)
+        avg_image_feats = image_embeds.mean(dim=1, keepdim=True)
+        cls_feats_image = self.cross_modal_image_pooler(avg_image_feats)
+        cls_feats = torch.cat([cls_feats_text, cls_feats_image], dim=-1)
+        return {"text_feats": text_embeds, "image_feats": image_embeds, "cls_feats": cls_feats,
+                "text_labels": text_labels, "text_ids": text_ids, "text_masks": text_masks, "image": img}
+
+    def forward(self, batch):
+        ret = dict()
+        if len(self.current_tasks) == 0:
+            ret.update(self.infer(batch))
+            return ret
+        if "mlm" in self.current_tasks:
+            ret.update(objectives.compute_mlm(self, batch))
+        if "itc" in self.current_tasks:
+            ret_itc, image_neg, text_neg, text_mask_neg = objectives.compute_itc(self, batch)
+            ret.update(ret_itc)
+        if "itm" in self.current_tasks:
+            if "itc" in self.current_tasks:
+                ret.update(objectives.compute_itm_hardneg(self, batch, image_neg, text_neg, text_mask_neg))
+            else:
+                ret.update(objectives.compute_itm(self, batch))
+        if "vqa" in self.current_tasks:
+            ret.update(objectives.compute_vqa(self, batch))
+        return ret
+
+    def training_step(self, batch, batch_idx):
+        fiber_utils.set_task(self)
+        output = self(batch)
+        return sum([v for k, v in output.items() if "loss" in k])
+
+    def validation_step(self, batch, batch_idx):
+        fiber_utils.set_task(self)
+        return self(batch)
+
+    def configure_optimizers(self):
+        return fiber_utils.set_schedule(self)

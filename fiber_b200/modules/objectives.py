@@ -1,0 +1,136 @@
+"""Mirror of the objectives a FIBER training step calls (coarse_grained/fiber/modules/objectives.py):
+compute_mlm :17, compute_itm :44, compute_itm_hardneg :78, compute_itc :119, compute_vqa :182,
+init_weights :502.  They are callers of infer(); losses are ordinary torch ops on the fp32 features
+infer() returns.  One deliberate change: the 2*B `.item()` host syncs of the
+hard-negative sampling loop (:154-165) are replaced by one batched torch.multinomial per direction
+(same per-row distribution)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def init_weights(module):
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+    if isinstance(module, nn.Linear) and module.bias is not None:
+        module.bias.data.zero_()
+
+
+def _phase(pl_module):
+    return "train" if pl_module.training else "val"
+
+
+def compute_mlm(pl_module, batch):
+    infer = pl_module.infer(batch, mask_text=True, mask_image=False)
+    mlm_logits = pl_module.mlm_score(infer["text_feats"])
+    mlm_labels = infer["text_labels"]
+    mlm_loss = F.cross_entropy(mlm_logits.view(-1, pl_module.hparams.config["vocab_size"]).float(),
+                               mlm_labels.view(-1), ignore_index=-100)
+    ret = {"mlm_loss": mlm_loss, "mlm_logits": mlm_logits, "mlm_labels": mlm_labels, "mlm_ids": infer["text_ids"]}
+    phase = _phase(pl_module)
+    loss = getattr(pl_module, f"{phase}_mlm_loss")(ret["mlm_loss"])
+    acc = getattr(pl_module, f"{phase}_mlm_accuracy")(ret["mlm_logits"], ret["mlm_labels"])
+    pl_module.log(f"mlm/{phase}/loss", loss)
+    pl_module.log(f"mlm/{phase}/accuracy", acc)
+    return ret
+
+
+def _itm_tail(pl_module, infer, itm_labels):
+    itm_logits = pl_module.itm_score(infer["cls_feats"])
+    itm_loss = F.cross_entropy(itm_logits.float(), itm_labels.long())
+    ret = {"itm_loss": itm_loss, "itm_logits": itm_logits, "itm_labels": itm_labels}
+    phase = _phase(pl_module)
+    loss = getattr(pl_module, f"{phase}_itm_loss")(ret["itm_loss"])
+    acc = getattr(pl_module, f"{phase}_itm_accuracy")(ret["itm_logits"], ret["itm_labels"])
+    pl_module.log(f"itm/{phase}/loss", loss)
+    pl_module.log(f"itm/{phase}/accuracy", acc)
+    return ret
+
+
+def compute_itm(pl_module, batch, itm_labels=None):
+    n = len(batch["text"])
+    pos_len = n // 2
+    if itm_labels is None:
+        itm_labels = torch.cat([torch.ones(pos_len), torch.zeros(n - pos_len)])
+        itm_labels = itm_labels[torch.randperm(n)]
+    itm_labels = itm_labels.to(pl_module.device)
+    pick = (itm_labels == 1).view(-1, 1, 1, 1)
+    itm_images = [torch.where(pick, bti, bfi) for bti, bfi in zip(batch["image"], batch["false_image_0"])]
+    batch = {k: v for k, v in batch.items()}
+    batch["image"] = itm_images
+    infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    return _itm_tail(pl_module, infer, itm_labels)
+
+
+def compute_itm_hardneg(pl_module, batch, image_neg, text_neg, text_mask_neg):
+    pos_len = len(batch["text"])
+    itm_labels = torch.cat([torch.ones(pos_len), torch.zeros(2 * pos_len)]).to(pl_module.device)
+    batch = {k: v for k, v in batch.items()}
+    batch["image"] = [torch.cat([batch["image"][0], batch["image"][0], image_neg], dim=0)]
+    batch["text_masks"] = torch.cat([batch["text_masks"], text_mask_neg, batch["text_masks"]], dim=0)
+    batch["text_ids"] = torch.cat([batch["text_ids"], text_neg, batch["text_ids"]], dim=0)
+    batch["text_labels"] = torch.cat([batch["text_labels"]] * 3, dim=0)
+    infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    return _itm_tail(pl_module, infer, itm_labels)
+
+
+def compute_itc(pl_module, batch):
+    with torch.no_grad():
+        pl_module.temp.clamp_(0.001, 1.0)
+    infer_image = pl_module.infer(batch, mask_image=False, mask_text=False, image_only=True)
+    infer_text = pl_module.infer(batch, mask_image=False, mask_text=False, text_only=True)
+    image_feat, text_feat = infer_image["cls_feats"], infer_text["cls_feats"]
+    image_feat_all = torch.cat([image_feat.t().detach(), pl_module.image_queue.clone().detach()], dim=1)
+    text_feat_all = torch.cat([text_feat.t().detach(), pl_module.text_queue.clone().detach()], dim=1)
+    sim_i2t = image_feat @ text_feat_all / pl_module.temp
+    sim_t2i = text_feat @ image_feat_all / pl_module.temp
+    sim_targets = torch.zeros_like(sim_i2t)
+    sim_targets.fill_diagonal_(1)
+    loss_i2t = -torch.sum(F.log_softmax(sim_i2t, dim=1) * sim_targets, dim=1).mean()
+    loss_t2i = -torch.sum(F.log_softmax(sim_t2i, dim=1) * sim_targets, dim=1).mean()
+    loss_itc = (loss_i2t + loss_t2i) / 2.0
+    bs = image_feat.size(0)
+    qt = int(pl_module.queue_total[0])
+    with torch.no_grad():
+        weights_i2t = F.softmax(sim_i2t[:, :bs + qt], dim=1)
+        weights_t2i = F.softmax(sim_t2i[:, :bs + qt], dim=1)
+        weights_i2t.fill_diagonal_(0)
+        weights_t2i.fill_diagonal_(0)
+        img_idx = torch.multinomial(weights_t2i + 1e-9, 1).view(-1)
+        txt_idx = torch.multinomial(weights_i2t + 1e-9, 1).view(-1)
+        tot_image = torch.cat([batch["image"][0], pl_module.image_input_queue[:qt]], dim=0)
+        tot_text = torch.cat([batch["text_ids"], pl_module.text_input_queue[:qt]], dim=0)
+        tot_text_mask = torch.cat([batch["text_masks"], pl_module.text_input_mask_queue[:qt]], dim=0)
+        image_neg = tot_image[img_idx]
+        text_neg, text_mask_neg = tot_text[txt_idx], tot_text_mask[txt_idx]
+    if pl_module.training:
+        pl_module._dequeue_and_enqueue(image_feat.detach().clone(), text_feat.detach().clone(),
+                                       batch["image"][0].clone(), batch["text_ids"].clone(),
+                                       batch["text_masks"].clone())
+    ret = {"itc_loss": loss_itc}
+    phase = _phase(pl_module)
+    loss = getattr(pl_module, f"{phase}_itc_loss")(ret["itc_loss"])
+    pl_module.log(f"itc/{phase}/loss", loss)
+    return ret, image_neg, text_neg, text_mask_neg
+
+
+def compute_vqa(pl_module, batch):
+    infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    vqa_logits = pl_module.vqa_classifier(infer["cls_feats"])
+    vqa_targets = torch.zeros(len(vqa_logits), pl_module.hparams.config["vqav2_label_size"])
+    for i, (_label, _score) in enumerate(zip(batch["vqa_labels"], batch["vqa_scores"])):
+        for l, s in zip(_label, _score):
+            vqa_targets[i, l] = s
+    vqa_targets = vqa_targets.to(pl_module.device)
+    vqa_loss = F.binary_cross_entropy_with_logits(vqa_logits.float(), vqa_targets) * vqa_targets.shape[1]
+    ret = {"vqa_loss": vqa_loss, "vqa_logits": vqa_logits, "vqa_targets": vqa_targets,
+           "vqa_labels": batch["vqa_labels"], "vqa_scores": batch["vqa_scores"]}
+    phase = _phase(pl_module)
+    loss = getattr(pl_module, f"{phase}_vqa_loss")(ret["vqa_loss"])
+    score = getattr(pl_module, f"{phase}_vqa_score")(ret["vqa_logits"], ret["vqa_targets"])
+    pl_module.log(f"vqa/{phase}/loss", loss)
+    pl_module.log(f"vqa/{phase}/score", score)
+    return ret

@@ -1,0 +1,539 @@
+"""Block-level autograd Functions of the FIBER hot path, each a straight-line sequence of C-ABI
+kernel launches (fiber_b200.kernels) with a hand-written backward.
+
+Layout: every activation is a 2-D bf16 [rows, C] tensor in IMAGE order (rows = B*H*W) or text order
+(rows = B*L); Swin's roll / window_partition / window_reverse never happen as copies — the window
+attention kernel gathers through the closed-form map.  Parameters stay fp32 masters (reference
+state_dict layout); bf16 (and transposed) copies are cached per parameter version.
+
+Reference semantics restated here (file:line under coarse_grained/fiber/modules/):
+  SwinTransformerBlock.forward   swin_transformer.py:356-393   -> SwinBlockFn
+  WindowAttention.forward        swin_transformer.py:195-261   (inside SwinBlockFn)
+  PatchMerging.forward           swin_transformer.py:411-432   -> PatchMergeFn
+  timm PatchEmbed                fiber_module.py:311           -> PatchEmbedFn
+  RobertaEmbeddings.forward      roberta.py:169-199            -> RobertaEmbedFn
+  RobertaLayer.forward           roberta.py:441-502            -> RobertaLayerFn
+"""
+import itertools
+import math
+import weakref
+
+import torch
+
+from . import kernels as K
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+LN_EPS = 1e-5
+
+_seed_counter = itertools.count(1)
+_base_seed = 0x5EED
+
+
+def set_dropout_seed(seed):
+    global _base_seed, _seed_counter
+    _base_seed = int(seed)
+    _seed_counter = itertools.count(1)
+
+
+def _next_seed():
+    return (_base_seed * 1000003 + next(_seed_counter)) & 0x7FFFFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 weight cache
+# ---------------------------------------------------------------------------------------------
+class _WeightCache:
+    """bf16 [N,K] and transposed [K,N] copies of (packed) fp32 Linear weights; packed fp32 biases.
+    Refreshed whenever any source parameter's in-place version counter changes (optimizer step,
+    load_state_dict)."""
+
+    def __init__(self):
+        self._w = {}
+        self._b = {}
+
+    @staticmethod
+    def _key(ps):
+        return tuple(id(p) for p in ps), tuple((p._version, p.data_ptr()) for p in ps)
+
+    @staticmethod
+    def _alive(refs, ps):
+        return all(r() is p for r, p in zip(refs, ps))
+
+    def weights(self, ps, need_t=True, pad_k=0):
+        """ps: tuple of fp32 [N_i, K] (or conv [N, ...]) weights packed along N."""
+        ids, vers = self._key(ps)
+        hit = self._w.get(ids)
+        if hit is not None and hit[0] == vers and self._alive(hit[3], ps) and (hit[2] is not None or not need_t):
+            return hit[1], hit[2]
+        with torch.no_grad():
+            mats = [p.detach().reshape(p.shape[0], -1) for p in ps]
+            k = mats[0].shape[1]
+            kp = max(k, pad_k)
+            n_total = sum(m.shape[0] for m in mats)
+            dev = mats[0].device
+            w = (torch.zeros if kp != k else torch.empty)((n_total, kp), device=dev, dtype=BF16)
+            wt = torch.empty((k, n_total), device=dev, dtype=BF16) if need_t else None
+            n0 = 0
+            for m in mats:
+                n = m.shape[0]
+                K.cast_transpose(m, w[n0:n0 + n], None if wt is None else wt[:, n0:n0 + n])
+                n0 += n
+        self._w[ids] = (vers, w, wt, tuple(weakref.ref(p) for p in ps))
+        return w, wt
+
+    def bias(self, ps):
+        if len(ps) == 1:
+            return ps[0].detach()
+        ids, vers = self._key(ps)
+        hit = self._b.get(ids)
+        if hit is not None and hit[0] == vers and self._alive(hit[2], ps):
+            return hit[1]
+        with torch.no_grad():
+            b = torch.cat([p.detach() for p in ps])
+        self._b[ids] = (vers, b, tuple(weakref.ref(p) for p in ps))
+        return b
+
+    def clear(self):
+        self._w.clear()
+        self._b.clear()
+
+
+CACHE = _WeightCache()
+
+
+def _wgrad(dy, x, scale=None):
+    """dW[N,K] = dy[rows,N]^T x[rows,K]  (fp32, split-K atomics on a zeroed buffer)."""
+    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale)
+
+
+def _as2d(x):
+    return x.reshape(-1, x.shape[-1])
+
+
+def _to_bf16_2d(x):
+    x2 = _as2d(x)
+    if x2.dtype == F32:
+        return K.cast_bf16(x2)
+    if x2.dtype != BF16:
+        raise RuntimeError("fiber_b200: activations must be bf16 or fp32, got %s" % x2.dtype)
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# generic Linear / LayerNorm (tail of infer(): cross_modal_*_transform, poolers, vit_model.norm)
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_fp32):
+        x2 = _to_bf16_2d(x)
+        w, wt = CACHE.weights((weight,))
+        y = K.gemm(x2, w, bias=None if bias is None else bias.detach(),
+                   out_dtype=F32 if out_fp32 else BF16)
+        ctx.saved = (x2, wt, bias is not None, x.shape, x.dtype)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wt, has_bias, xshape, xdtype = ctx.saved
+        dy2 = _to_bf16_2d(dy)
+        dw = _wgrad(dy2, x2)
+        db = K.colsum(dy2) if has_bias else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dy2, wt, out_dtype=F32 if xdtype == F32 else BF16).view(xshape)
+        return dx, dw, db, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x2 = _to_bf16_2d(x)
+        y, mean, rstd, _ = K.layernorm_fwd(x2, weight.detach(), bias.detach(), eps)
+        ctx.saved = (x2, mean, rstd, weight.detach(), x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, g, xshape = ctx.saved
+        dg, db = torch.zeros_like(g), torch.zeros_like(g)
+        dx = K.layernorm_bwd(_to_bf16_2d(dy), x2, mean, rstd, g, dgamma=dg, dbeta=db)
+        return dx.view(xshape), dg, db, None
+
+
+# ---------------------------------------------------------------------------------------------
+# PatchEmbed: conv 4x4/s4 as a K=48(->64) GEMM + LayerNorm
+# ---------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, proj_w, proj_b, norm_w, norm_b):
+        B, _, R, _ = img.shape
+        patches = K.patch_gather(img.float())
+        w, _ = CACHE.weights((proj_w,), need_t=False, pad_k=64)
+        e = K.gemm(patches, w, bias=proj_b.detach())
+        x, mean, rstd, _ = K.layernorm_fwd(e, norm_w.detach(), norm_b.detach(), LN_EPS)
+        ctx.saved = (patches, e, mean, rstd, norm_w.detach(), proj_w.shape)
+        return x.view(B, (R // 4) ** 2, proj_w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dx):
+        patches, e, mean, rstd, g, wshape = ctx.saved
+        dg, db = torch.zeros_like(g), torch.zeros_like(g)
+        de = K.layernorm_bwd(_to_bf16_2d(dx), e, mean, rstd, g, dgamma=dg, dbeta=db)
+        dw = _wgrad(de, patches)[:, :48].reshape(wshape)
+        return None, dw, K.colsum(de), dg, db
+
+
+# ---------------------------------------------------------------------------------------------
+# PatchMerging: gather+LN fused kernel, then the 4C->2C reduction GEMM (no bias)
+# ---------------------------------------------------------------------------------------------
+class PatchMergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, norm_w, norm_b, red_w, H, W):
+        B, T, C = x.shape
+        x2 = _to_bf16_2d(x)
+        y, mean, rstd, _ = K.layernorm_fwd(x2, norm_w.detach(), norm_b.detach(), LN_EPS, merge=(B, H, W))
+        w, wt = CACHE.weights((red_w,))
+        out = K.gemm(y, w)
+        ctx.saved = (x2, y, mean, rstd, norm_w.detach(), wt, (B, H, W), x.shape)
+        return out.view(B, T // 4, 2 * C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, y, mean, rstd, g, wt, merge, xshape = ctx.saved
+        d2 = _to_bf16_2d(dout)
+        dw = _wgrad(d2, y)
+        dy = K.gemm(d2, wt)
+        dg, db = torch.zeros_like(g), torch.zeros_like(g)
+        dx = K.layernorm_bwd(dy, x2, mean, rstd, g, merge=merge, dgamma=dg, dbeta=db)
+        return dx.view(xshape), dg, db, dw, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# Swin block
+# ---------------------------------------------------------------------------------------------
+SWIN_PLAIN = ("norm1.weight", "norm1.bias", "attn.relative_position_bias_table", "attn.qkv.weight",
+              "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias", "norm2.weight", "norm2.bias",
+              "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+SWIN_FUSED = SWIN_PLAIN + ("attn.qkv_text_i2t.weight", "attn.qkv_text_i2t.bias", "attn.qkv_i2t.weight",
+                           "attn.qkv_i2t.bias", "attn.proj_i2t.weight", "attn.proj_i2t.bias", "attn.alpha_i2t",
+                           "attn.norm_i2t_i.weight", "attn.norm_i2t_i.bias")
+
+
+class SwinBlockFn(torch.autograd.Function):
+    """forward(x [B,T,C], text [B,L,Ct] | None, text_mask [B,L] f32 | None,
+               s_attn [B] | None, s_mlp [B] | None   (the two independent DropPath draws of :390-391),
+               geom=(H, W, ws, shift, heads), *params in SWIN_PLAIN / SWIN_FUSED order)"""
+
+    @staticmethod
+    def forward(ctx, x, text, text_mask, s_attn, s_mlp, geom, *params):
+        H, W, ws, shift, nh = geom
+        B, T, C = x.shape
+        hd = C // nh
+        fused = text is not None
+        names = SWIN_FUSED if fused else SWIN_PLAIN
+        p = dict(zip(names, (t.detach() for t in params)))
+        x2 = _to_bf16_2d(x)
+        s = s_attn
+        scale = hd ** -0.5
+        win = (B, H, W, ws, shift)
+        sv = {}
+
+        ln1, sv["mean1"], sv["rstd1"], _ = K.layernorm_fwd(x2, p["norm1.weight"], p["norm1.bias"], LN_EPS)
+        wqkv, sv["wqkv_t"] = CACHE.weights((params[names.index("attn.qkv.weight")],))
+        qkv = K.gemm(ln1, wqkv, bias=p["attn.qkv.bias"])
+        table = p["attn.relative_position_bias_table"]
+        ao, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], nh, hd, scale, window=win, bias_table=table)
+        wproj, sv["wproj_t"] = CACHE.weights((params[names.index("attn.proj.weight")],))
+        if not fused:
+            x1 = K.gemm(ao, wproj, bias=p["attn.proj.bias"], residual=x2, row_scale=s, rows_per_scale=T)
+        else:
+            t2 = _to_bf16_2d(text)
+            L = text.shape[1]
+            z = torch.empty_like(x2)
+            xz = K.gemm(ao, wproj, bias=p["attn.proj.bias"], preact=z, residual=x2, row_scale=s, rows_per_scale=T)
+            lnz, sv["meanz"], sv["rstdz"], _ = K.layernorm_fwd(z, p["attn.norm_i2t_i.weight"],
+                                                               p["attn.norm_i2t_i.bias"], LN_EPS)
+            wq2, sv["wq2_t"] = CACHE.weights((params[names.index("attn.qkv_i2t.weight")],))
+            q2 = K.gemm(lnz, wq2, bias=p["attn.qkv_i2t.bias"])
+            wkvt, sv["wkvt_t"] = CACHE.weights((params[names.index("attn.qkv_text_i2t.weight")],))
+            kvt = K.gemm(t2, wkvt, bias=p["attn.qkv_text_i2t.bias"])
+            km = None if text_mask is None else text_mask.contiguous()
+            ao2, lse2 = K.attn_fwd(q2, kvt[:, :C], kvt[:, C:], nh, hd, scale, groups=B, lq=T, lk=L, key_mask=km)
+            wp2, sv["wp2_t"] = CACHE.weights((params[names.index("attn.proj_i2t.weight")],))
+            y = torch.empty_like(x2)
+            x1 = K.gemm(ao2, wp2, bias=p["attn.proj_i2t.bias"], preact=y, scale=p["attn.alpha_i2t"], residual=xz,
+                        row_scale=s, rows_per_scale=T)
+            sv.update(t2=t2, z=z, lnz=lnz, q2=q2, kvt=kvt, ao2=ao2, lse2=lse2, y=y, km=km, L=L)
+        ln2, sv["mean2"], sv["rstd2"], _ = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], LN_EPS)
+        w1, sv["w1_t"] = CACHE.weights((params[names.index("mlp.fc1.weight")],))
+        h = torch.empty((B * T, 4 * C), device=x.device, dtype=BF16)
+        a = K.gemm(ln2, w1, bias=p["mlp.fc1.bias"], act=K.ACT_GELU, preact=h)
+        w2, sv["w2_t"] = CACHE.weights((params[names.index("mlp.fc2.weight")],))
+        out = K.gemm(a, w2, bias=p["mlp.fc2.bias"], residual=x1, row_scale=s_mlp, rows_per_scale=T)
+        sv.update(x2=x2, ln1=ln1, qkv=qkv, ao=ao, lse=lse, x1=x1, ln2=ln2, h=h, a=a, p=p, s=s, s_mlp=s_mlp, geom=geom,
+                  fused=fused, shape=(B, T, C), text_shape=None if text is None else text.shape)
+        ctx.sv = sv
+        return out.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.sv
+        p, s = sv["p"], sv["s"]
+        B, T, C = sv["shape"]
+        H, W, ws, shift, nh = sv["geom"]
+        hd = C // nh
+        scale = hd ** -0.5
+        fused = sv["fused"]
+        g = {}
+        d_out = _to_bf16_2d(dout)
+
+        # ---- MLP branch: out = x1 + s * fc2(gelu(fc1(LN2(x1)))) ----
+        dz = K.scale_rows(d_out, sv["s_mlp"], T) if sv["s_mlp"] is not None else d_out
+        g["mlp.fc2.weight"] = _wgrad(dz, sv["a"])
+        g["mlp.fc2.bias"] = K.colsum(dz)
+        dh = K.gemm(dz, sv["w2_t"], aux=sv["h"], act=K.ACT_GELU_GRAD)
+        g["mlp.fc1.weight"] = _wgrad(dh, sv["ln2"])
+        g["mlp.fc1.bias"] = K.colsum(dh)
+        dln2 = K.gemm(dh, sv["w1_t"])
+        g["norm2.weight"] = torch.zeros_like(p["norm2.weight"])
+        g["norm2.bias"] = torch.zeros_like(p["norm2.bias"])
+        dx1 = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
+                              dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
+        # ---- attention branch: x1 = x + s * (z [+ alpha * y]) ----
+        dZ = K.scale_rows(dx1, s, T) if s is not None else dx1
+        dtext = None
+        if fused:
+            alpha = p["attn.alpha_i2t"]
+            g["attn.alpha_i2t"] = K.dot(dZ, sv["y"])
+            g["attn.proj_i2t.weight"] = _wgrad(dZ, sv["ao2"], scale=alpha)
+            g["attn.proj_i2t.bias"] = K.colsum(dZ, scale=alpha)
+            dao2 = K.gemm(dZ, sv["wp2_t"], scale=alpha)
+            dq2 = torch.empty_like(sv["q2"])
+            dkvt = torch.empty_like(sv["kvt"])
+            K.attn_bwd(dao2, sv["q2"], sv["kvt"][:, :C], sv["kvt"][:, C:], sv["ao2"], sv["lse2"], nh, hd, scale,
+                       dq2, dkvt[:, :C], dkvt[:, C:], groups=B, lq=T, lk=sv["L"], key_mask=sv["km"])
+            g["attn.qkv_text_i2t.weight"] = _wgrad(dkvt, sv["t2"])
+            g["attn.qkv_text_i2t.bias"] = K.colsum(dkvt)
+            if ctx.needs_input_grad[1]:
+                dtext = K.gemm(dkvt, sv["wkvt_t"]).view(sv["text_shape"])
+            g["attn.qkv_i2t.weight"] = _wgrad(dq2, sv["lnz"])
+            g["attn.qkv_i2t.bias"] = K.colsum(dq2)
+            dlnz = K.gemm(dq2, sv["wq2_t"])
+            g["attn.norm_i2t_i.weight"] = torch.zeros_like(p["attn.norm_i2t_i.weight"])
+            g["attn.norm_i2t_i.bias"] = torch.zeros_like(p["attn.norm_i2t_i.bias"])
+            dzz = K.layernorm_bwd(dlnz, sv["z"], sv["meanz"], sv["rstdz"], p["attn.norm_i2t_i.weight"], dres=dZ,
+                                  dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"])
+        else:
+            dzz = dZ
+        g["attn.proj.weight"] = _wgrad(dzz, sv["ao"])
+        g["attn.proj.bias"] = K.colsum(dzz)
+        dao = K.gemm(dzz, sv["wproj_t"])
+        dqkv = torch.empty_like(sv["qkv"])
+        g["attn.relative_position_bias_table"] = torch.zeros_like(p["attn.relative_position_bias_table"])
+        qkv = sv["qkv"]
+        K.attn_bwd(dao, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sv["ao"], sv["lse"], nh, hd, scale,
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
+                   dbias_table=g["attn.relative_position_bias_table"], window=(B, H, W, ws, shift),
+                   bias_table=p["attn.relative_position_bias_table"])
+        g["attn.qkv.weight"] = _wgrad(dqkv, sv["ln1"])
+        g["attn.qkv.bias"] = K.colsum(dqkv)
+        dln1 = K.gemm(dqkv, sv["wqkv_t"])
+        g["norm1.weight"] = torch.zeros_like(p["norm1.weight"])
+        g["norm1.bias"] = torch.zeros_like(p["norm1.bias"])
+        dx = K.layernorm_bwd(dln1, sv["x2"], sv["mean1"], sv["rstd1"], p["norm1.weight"], dres=dx1,
+                             dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
+        ctx.sv = None
+        names = SWIN_FUSED if fused else SWIN_PLAIN
+        return (dx.view(B, T, C), dtext, None, None, None, None) + tuple(g[n] for n in names)
+
+
+# ---------------------------------------------------------------------------------------------
+# RoBERTa
+# ---------------------------------------------------------------------------------------------
+class RobertaEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, word, pos, typ, ln_w, ln_b, eps, drop_p, pad_id):
+        B, L = ids.shape
+        e = K.embed_gather(ids, word.detach(), pos.detach(), typ.detach(), pad_id)
+        x, mean, rstd, _ = K.layernorm_fwd(e, ln_w.detach(), ln_b.detach(), eps)
+        seed = None
+        if drop_p > 0:
+            seed = _next_seed()
+            x = K.dropout(x, drop_p, seed)
+        ctx.saved = (ids, e, mean, rstd, ln_w.detach(), drop_p, seed, pad_id, word.shape, pos.shape)
+        return x.view(B, L, -1)
+
+    @staticmethod
+    def backward(ctx, dx):
+        ids, e, mean, rstd, g, drop_p, seed, pad_id, wshape, pshape = ctx.saved
+        d2 = _to_bf16_2d(dx)
+        if drop_p > 0:
+            d2 = K.dropout(d2, drop_p, seed)
+        dg, db = torch.zeros_like(g), torch.zeros_like(g)
+        de = K.layernorm_bwd(d2, e, mean, rstd, g, dgamma=dg, dbeta=db)
+        dword = torch.zeros(wshape, device=de.device, dtype=F32)
+        dpos = torch.zeros(pshape, device=de.device, dtype=F32)
+        K.embed_scatter(ids, de, dword, dpos, pad_id)
+        dtyp = K.colsum(de).view(1, -1)
+        return None, dword, dpos, dtyp, dg, db, None, None, None
+
+
+ROBERTA_PLAIN = ("attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
+                 "attention.self.key.bias", "attention.self.value.weight", "attention.self.value.bias",
+                 "attention.output.dense.weight", "attention.output.dense.bias",
+                 "attention.output.LayerNorm.weight", "attention.output.LayerNorm.bias",
+                 "intermediate.dense.weight", "intermediate.dense.bias", "output.dense.weight", "output.dense.bias",
+                 "output.LayerNorm.weight", "output.LayerNorm.bias")
+ROBERTA_FUSED = ROBERTA_PLAIN + ("crossattention_t2i.self.query.weight", "crossattention_t2i.self.query.bias",
+                                 "crossattention_t2i.self.key.weight", "crossattention_t2i.self.key.bias",
+                                 "crossattention_t2i.self.value.weight", "crossattention_t2i.self.value.bias",
+                                 "crossattention_t2i.output.dense.weight", "crossattention_t2i.output.dense.bias",
+                                 "alpha_t2i")
+
+
+class RobertaLayerFn(torch.autograd.Function):
+    """forward(h [B,L,768], mask [B,L] f32 additive, image [B,T,Cimg] | None,
+               meta=(heads, last_norm, eps, hidden_drop, attn_drop), *params)"""
+
+    @staticmethod
+    def forward(ctx, h, mask, image, meta, *params):
+        nh, last_norm, eps, p_h, p_a = meta
+        B, L, C = h.shape
+        hd = C // nh
+        fused = image is not None
+        names = ROBERTA_FUSED if fused else ROBERTA_PLAIN
+        P = dict(zip(names, params))
+        p = {k: v.detach() for k, v in P.items()}
+        h2 = _to_bf16_2d(h)
+        sv = {}
+        scale = 1.0 / math.sqrt(hd)
+        km = None if mask is None else mask.contiguous()
+
+        wqkv, sv["wqkv_t"] = CACHE.weights((P["attention.self.query.weight"], P["attention.self.key.weight"],
+                                            P["attention.self.value.weight"]))
+        bqkv = CACHE.bias((P["attention.self.query.bias"], P["attention.self.key.bias"],
+                           P["attention.self.value.bias"]))
+        qkv = K.gemm(h2, wqkv, bias=bqkv)
+        sv["seed_a"] = _next_seed() if p_a > 0 else 0
+        ctxv, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], nh, hd, scale, groups=B, lq=L, lk=L,
+                               key_mask=km, drop_p=p_a, seed=sv["seed_a"])
+        wo, sv["wo_t"] = CACHE.weights((P["attention.output.dense.weight"],))
+        a = K.gemm(ctxv, wo, bias=p["attention.output.dense.bias"])
+        if p_h > 0:
+            sv["seed_o"] = _next_seed()
+            a = K.dropout(a, p_h, sv["seed_o"])
+        a2 = a
+        if fused:
+            img2 = _to_bf16_2d(image)
+            Tk = image.shape[1]
+            wq2, sv["wq2_t"] = CACHE.weights((P["crossattention_t2i.self.query.weight"],))
+            q2 = K.gemm(a, wq2, bias=p["crossattention_t2i.self.query.bias"])
+            wkv2, sv["wkv2_t"] = CACHE.weights((P["crossattention_t2i.self.key.weight"],
+                                                P["crossattention_t2i.self.value.weight"]))
+            bkv2 = CACHE.bias((P["crossattention_t2i.self.key.bias"], P["crossattention_t2i.self.value.bias"]))
+            kv2 = K.gemm(img2, wkv2, bias=bkv2)
+            sv["seed_a2"] = _next_seed() if p_a > 0 else 0
+            ctx2, lse2 = K.attn_fwd(q2, kv2[:, :C], kv2[:, C:], nh, hd, scale, groups=B, lq=L, lk=Tk,
+                                    drop_p=p_a, seed=sv["seed_a2"])
+            wo2, sv["wo2_t"] = CACHE.weights((P["crossattention_t2i.output.dense.weight"],))
+            c = K.gemm(ctx2, wo2, bias=p["crossattention_t2i.output.dense.bias"])
+            if p_h > 0:
+                sv["seed_o2"] = _next_seed()
+                c = K.dropout(c, p_h, sv["seed_o2"])
+            a2 = K.axpy(c, a, p["alpha_t2i"])
+            sv.update(img2=img2, Tk=Tk, q2=q2, kv2=kv2, ctx2=ctx2, lse2=lse2, c=c, image_shape=image.shape)
+        ln_a, sv["mean_a"], sv["rstd_a"], _ = K.layernorm_fwd(a2, p["attention.output.LayerNorm.weight"],
+                                                              p["attention.output.LayerNorm.bias"], eps, add=h2)
+        wi, sv["wi_t"] = CACHE.weights((P["intermediate.dense.weight"],))
+        hpre = torch.empty((B * L, wi.shape[0]), device=h.device, dtype=BF16)
+        inter = K.gemm(ln_a, wi, bias=p["intermediate.dense.bias"], act=K.ACT_GELU, preact=hpre)
+        wout, sv["wout_t"] = CACHE.weights((P["output.dense.weight"],))
+        f = K.gemm(inter, wout, bias=p["output.dense.bias"])
+        if p_h > 0:
+            sv["seed_f"] = _next_seed()
+            f = K.dropout(f, p_h, sv["seed_f"])
+        if last_norm:
+            out, sv["mean_o"], sv["rstd_o"], _ = K.layernorm_fwd(f, p["output.LayerNorm.weight"],
+                                                                 p["output.LayerNorm.bias"], eps, add=ln_a)
+        else:
+            out = K.axpy(f, ln_a)
+        sv.update(h2=h2, qkv=qkv, ctxv=ctxv, lse=lse, a=a, a2=a2, ln_a=ln_a, hpre=hpre, inter=inter, f=f, p=p, km=km,
+                  meta=meta, fused=fused, shape=(B, L, C))
+        ctx.sv = sv
+        return out.view(B, L, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.sv
+        p = sv["p"]
+        nh, last_norm, eps, p_h, p_a = sv["meta"]
+        B, L, C = sv["shape"]
+        hd = C // nh
+        scale = 1.0 / math.sqrt(hd)
+        fused = sv["fused"]
+        g = {}
+        d_out = _to_bf16_2d(dout)
+        if last_norm:
+            g["output.LayerNorm.weight"] = torch.zeros_like(p["output.LayerNorm.weight"])
+            g["output.LayerNorm.bias"] = torch.zeros_like(p["output.LayerNorm.bias"])
+            dsum = K.layernorm_bwd(d_out, sv["f"], sv["mean_o"], sv["rstd_o"], p["output.LayerNorm.weight"],
+                                   add=sv["ln_a"], dgamma=g["output.LayerNorm.weight"],
+                                   dbeta=g["output.LayerNorm.bias"])
+        else:
+            g["output.LayerNorm.weight"] = g["output.LayerNorm.bias"] = None
+            dsum = d_out
+        df = K.dropout(dsum, p_h, sv["seed_f"]) if p_h > 0 else dsum
+        g["output.dense.weight"] = _wgrad(df, sv["inter"])
+        g["output.dense.bias"] = K.colsum(df)
+        dhpre = K.gemm(df, sv["wout_t"], aux=sv["hpre"], act=K.ACT_GELU_GRAD)
+        g["intermediate.dense.weight"] = _wgrad(dhpre, sv["ln_a"])
+        g["intermediate.dense.bias"] = K.colsum(dhpre)
+        dln_a = K.gemm(dhpre, sv["wi_t"], residual=dsum)
+        g["attention.output.LayerNorm.weight"] = torch.zeros_like(p["attention.output.LayerNorm.weight"])
+        g["attention.output.LayerNorm.bias"] = torch.zeros_like(p["attention.output.LayerNorm.bias"])
+        ds1 = K.layernorm_bwd(dln_a, sv["a2"], sv["mean_a"], sv["rstd_a"], p["attention.output.LayerNorm.weight"],
+                              add=sv["h2"], dgamma=g["attention.output.LayerNorm.weight"],
+                              dbeta=g["attention.output.LayerNorm.bias"])
+        dimage = None
+        if fused:
+            alpha = p["alpha_t2i"]
+            g["alpha_t2i"] = K.dot(ds1, sv["c"])
+            gc = K.dropout(ds1, p_h, sv["seed_o2"]) if p_h > 0 else ds1
+            g["crossattention_t2i.output.dense.weight"] = _wgrad(gc, sv["ctx2"], scale=alpha)
+            g["crossattention_t2i.output.dense.bias"] = K.colsum(gc, scale=alpha)
+            dctx2 = K.gemm(gc, sv["wo2_t"], scale=alpha)
+            dq2 = torch.empty_like(sv["q2"])
+            dkv2 = torch.empty_like(sv["kv2"])
+            K.attn_bwd(dctx2, sv["q2"], sv["kv2"][:, :C], sv["kv2"][:, C:], sv["ctx2"], sv["lse2"], nh, hd, scale,
+                       dq2, dkv2[:, :C], dkv2[:, C:], groups=B, lq=L, lk=sv["Tk"], drop_p=p_a, seed=sv["seed_a2"])
+            dwkv2 = _wgrad(dkv2, sv["img2"])
+            dbkv2 = K.colsum(dkv2)
+            g["crossattention_t2i.self.key.weight"], g["crossattention_t2i.self.value.weight"] = dwkv2[:C], dwkv2[C:]
+            g["crossattention_t2i.self.key.bias"], g["crossattention_t2i.self.value.bias"] = dbkv2[:C], dbkv2[C:]
+            if ctx.needs_input_grad[2]:
+                dimage = K.gemm(dkv2, sv["wkv2_t"]).view(sv["image_shape"])
+            g["crossattention_t2i.self.query.weight"] = _wgrad(dq2, sv["a"])
+            g["crossattention_t2i.self.query.bias"] = K.colsum(dq2)
+            da = K.gemm(dq2, sv["wq2_t"], residual=ds1)
+        else:
+            da = ds1
+        if p_h > 0:
+            da = K.dropout(da, p_h, sv["seed_o"])
+        g["attention.output.dense.weight"] = _wgrad(da, sv["ctxv"])
+        g["attention.output.dense.bias"] = K.colsum(da)
+        dctx = K.gemm(da, sv["wo_t"])
+        qkv = sv["qkv"]
+        dqkv = torch.empty_like(qkv)
+        K.attn_bwd(dctx, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sv["ctxv"], sv["lse"], nh, hd, scale,
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], groups=B, lq=L, lk=L, key_mask=sv["km"],
+                   drop_p=p_a, seed=sv["seed_a"])
+        dwqkv = _wgrad(dqkv, sv["h2"])
+        dbqkv = K.colsum(dqkv)
+        for i, n in enumerate(("query", "key", "value")):
+            g["attention.self.%s.weight" % n] = dwqkv[i * C:(i + 1) * C]
+            g["attention.self.%s.bias" % n] = dbqkv[i * C:(i + 1) * C]
+        dh = K.gemm(dqkv, sv["wqkv_t"], residual=ds1)
+        ctx.sv = None
+        names = ROBERTA_FUSED if fused else ROBERTA_PLAIN
+        return (dh.view(B, L, C), None, dimage, None) + tuple(g[n] for n in names)

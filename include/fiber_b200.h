@@ -155,6 +155,10 @@ int fiber_dropout(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, i
 /* y[m,:] = x[m,:] * row_scale[m / rows_per_scale]   (timm DropPath, swin_transformer.py:390-391) */
 int fiber_scale_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m, int32_t n, const float* row_scale,
                      int32_t rows_per_scale, fiber_stream_t stream);
+/* out = add + (*alpha) * x  (alpha NULL = 1): the alpha_t2i gate of roberta.py:483 and the
+ * un-normalised residual of RobertaOutput with last_norm=False (roberta.py:420-423) */
+int fiber_axpy(const void* x, int64_t ldx, const void* add, int64_t ldadd, const float* alpha, void* out, int64_t ldo,
+               int64_t m, int32_t n, fiber_stream_t stream);
 int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t stream);
 /* fp32 master weight [n,k] -> bf16 copy [n,k] (ld_out) and/or transposed bf16 copy [k,n] (ldt_out) */
 int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void* w_out, int64_t ld_out, void* wt_out,

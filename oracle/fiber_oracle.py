@@ -120,7 +120,7 @@ def window_attention(x, sd, prefix, H, W, ws, shift, nh, text=None, text_mask=No
         s = (s.view(B, nW, nh, N, N) + m.to(x.device)[None, :, None]).view(B * nW, nh, N, N)
     o = _merge(torch.softmax(s, dim=-1) @ v)
     o = _lin(o, sd, prefix + ".proj")  # window order
-    out = torch.empty_like(x)
+    out = torch.empty((B, T, C), dtype=o.dtype, device=x.device)
     out[:, src.reshape(-1)] = o.view(B, nW * N, C)
     if text is not None:
         # i2t (:226-259): per-token query against the sample's own text keys; window layout is
