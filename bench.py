@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — FIBER-Base fwd+bwd throughput (image-text pairs/s) on B200, BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): coarse pre-training step ITM+ITC+MLM, 384 px, 40 tokens,
+B=64 pairs per GPU, bf16 activations / fp32 accumulation, synthetic data, random-init weights.
+One step = FIBERTransformerSS.training_step (4 fused + 1 image-only + 1 text-only backbone passes
++ heads) followed by backward; the optimizer step is not part of the metric; with N>1 the gradient
+all-reduce (DDP over NCCL) is inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_PAIR = 1636.23e9  # fwd+bwd, config 1 (FlopCounterMode over the reference)
+METRIC = "image-text pairs/sec/GPU FIBER-Base 384px fwd+bwd at 1/2/4/8 B200"
+
+
+def config(tasks, image_size=384, max_text_len=40):
+    """coarse_grained/fiber/config.py:21-92 defaults + task_pretrain_mlm_itm_itc (:95-110)."""
+    loss_names = {"itm": 0, "mlm": 0, "itc": 0, "vqa": 0, "nlvr2": 0, "caption_mle": 0, "caption_gold": 0,
+                  "caption_cider": 0}
+    loss_names.update({t: 1 for t in tasks})
+    return dict(loss_names=loss_names, image_size=image_size, vit="swin_base_patch4_window12_384_in22k",
+                input_image_embed_size=1024, input_text_embed_size=768, pretrained_vit=False, vqav2_label_size=3129,
+                max_text_len=max_text_len, tokenizer="roberta-base", vocab_size=50265, hidden_size=768, num_heads=12,
+                num_layers=12, mlp_ratio=4, drop_rate=0.1, num_fuse_block=6, itc_pooler=True, load_path="",
+                test_only=False, optim_type="adamw", learning_rate=1e-5, weight_decay=0.01, decay_power=1,
+                max_steps=100000, warmup_steps=10000, end_lr=0, lr_mult_head=5, lr_mult_cross_modal=5)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def to_device(batch, dev, non_blocking=True):
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [t.to(dev, non_blocking=non_blocking) for t in v]
+        elif torch.is_tensor(v):
+            out[k] = v.to(dev, non_blocking=non_blocking)
+        else:
+            out[k] = v
+    return out
+
+
+def pin(batch):
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [t.pin_memory() for t in v]
+        elif torch.is_tensor(v):
+            out[k] = v.pin_memory()
+        else:
+            out[k] = v
+    return out
+
+
+def batch_bytes(batch):
+    n = 0
+    for v in batch.values():
+        if isinstance(v, list) and v and torch.is_tensor(v[0]):
+            n += sum(t.numel() * t.element_size() for t in v)
+        elif torch.is_tensor(v):
+            n += v.numel() * v.element_size()
+    return n
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_seconds(B, image_size, L, steps, warmup, threads):
+    """fwd+bwd of the ITM+ITC+MLM step through oracle/fiber_oracle.py (fp32, CPU)."""
+    from oracle import fiber_oracle as O
+    from oracle import synth
+    torch.set_num_threads(threads)
+    cfg = config(["itm", "itc", "mlm"], image_size, L)
+    from fiber_b200.modules import FIBERTransformerSS
+    shapes = {k: (tuple(v.shape), v.dtype) for k, v in FIBERTransformerSS(cfg).state_dict().items()
+              if not k.startswith("rank_output")}
+    sd = {k: v.requires_grad_(True) for k, v in synth.synth_state_dict(shapes).items()}
+    batch = synth.synth_batch(B, image_size, L, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        itc = O.compute_itc(sd, cfg, batch, 0)
+        img_idx = torch.multinomial(itc["weights_t2i"] + 1e-9, 1).view(-1) if B > 1 else torch.zeros(B, dtype=torch.long)
+        txt_idx = torch.multinomial(itc["weights_i2t"] + 1e-9, 1).view(-1) if B > 1 else torch.zeros(B, dtype=torch.long)
+        itm = O.compute_itm_hardneg(sd, cfg, batch, batch["image"][0][img_idx], batch["text_ids"][txt_idx],
+                                    batch["text_masks"][txt_idx])
+        mlm = O.compute_mlm(sd, cfg, batch)
+        loss = itc["itc_loss"] + itm["itm_loss"] + mlm["mlm_loss"]
+        for v in sd.values():
+            v.grad = None
+        loss.backward()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.cpu_batch
+    sec = cpu_step_seconds(B, args.image_size, args.text_len, args.steps, min(args.warmup, 1), threads)
+    v = B / sec
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FIBER-Base coarse pretrain step ITM+ITC+MLM 384px/40tok fwd+bwd, oracle port on host "
+                               "cores (sample: B=%d pairs per step)" % B},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": "B=%d pairs/step, %d timed steps, fp32, torch %d threads" % (B, args.steps, threads)},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    from oracle import synth  # synthetic batch recipe only (data, not compute)
+    from fiber_b200 import lib, ops
+    from fiber_b200.modules import FIBERTransformerSS, fiber_utils
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    lib.check(lib.load().fiber_init(), "init")
+    B, R, L = args.batch, args.image_size, args.text_len
+    cfg = config(["itm", "itc", "mlm"], R, L)
+    torch.manual_seed(1234)
+    model = FIBERTransformerSS(cfg).to(dev)
+    with torch.no_grad():  # alpha gates at 0.5 so the cross-attention branches carry signal
+        for n, p in model.named_parameters():
+            if n.endswith(("alpha_i2t", "alpha_t2i")):
+                p.fill_(0.5)
+    model.train()
+    fiber_utils.set_task(model)
+    ops.set_dropout_seed(1234 + rank)
+    step_model = model
+    if world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                               gradient_as_bucket_view=True)
+    host = pin(synth.synth_batch(B, R, L, seed=1234 + rank))
+    h2d = batch_bytes(host)
+
+    # the heads on top of infer() (callers, plain torch fp32 modules) may use TF32 tensor cores
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+    def step(batch):
+        out = step_model(batch)
+        loss = sum(v for k, v in out.items() if "loss" in k)
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        return loss
+
+    def timed(n, from_host):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.launch_count()
+        e0.record()
+        res = None
+        for _ in range(n):
+            b = to_device(host, dev) if from_host else dev_batch
+            loss = step(b)
+            if from_host:
+                res = loss.item()  # device -> host read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms, lib.launch_count() - l0, res
+
+    dev_batch = to_device(host, dev)
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, _ = timed(args.steps, False)
+    clocks = sampler.stop()
+    ms_e2e, _, last_loss = timed(args.steps, True)
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    if rank != 0:
+        return
+    value = args.steps * B * world / (ms / 1e3)
+    e2e = args.steps * B * world / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = value / world * FLOPS_PER_PAIR / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "FIBER-Base coarse pretrain step ITM+ITC+MLM (BASELINE configs[1]) 384px/40tok fwd+bwd",
+                   "per_gpu_batch": B, "global_batch": B * world, "image_size": R, "text_len": L,
+                   "parallelism": "dp%d" % world, "l2": "per-step activations (>10 GB) exceed the 126 MB L2",
+                   "last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1)},
+        "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf, "traffic": None,
+                     "note": "whole step per GPU: pairs/s x 1636.23 GFLOP/pair vs %s bf16 sustained"
+                             % ("measured" if peaks else "fallback")},
+    }
+    if args.cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        sec = cpu_step_seconds(args.cpu_batch, R, L, 1, 0, threads)
+        line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": "B=%d pairs, 1 step of the same ITM+ITC+MLM 384px workload, fp32 oracle port"
+                                          % args.cpu_batch}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU")
+    ap.add_argument("--image-size", type=int, default=384)
+    ap.add_argument("--text-len", type=int, default=40)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@ def synth_tensor(name, shape, dtype=torch.float32, salt=0):
     if name == "temp":
         return torch.full(shape, 0.07, dtype=dtype)
     if leaf == "relative_position_bias_table":
-        return (torch.randn(shape, generator=g) * 0.5).to(dtype)
+        return (torch.randn(shape, generator=g) * 0.2).to(dtype)
     is_norm = any(k in name for k in ("norm", "LayerNorm", "vqa_classifier.1"))
     if is_norm and leaf == "weight":
         return (1.0 + 0.1 * torch.randn(shape, generator=g)).to(dtype)
@@ -37,10 +37,8 @@ def synth_tensor(name, shape, dtype=torch.float32, salt=0):
         q = torch.randn(shape, generator=g)
         return (q / q.norm(dim=0, keepdim=True)).to(dtype)
     if len(shape) >= 2:
-        fan_in = 1
-        for s in shape[1:]:
-            fan_in *= s
-        std = 0.02 if "embeddings" in name else min(0.05, 1.5 / fan_in ** 0.5)
+        # reference initialiser scale (trunc_normal / normal std 0.02); inputs ("in.*") get unit scale
+        std = 1.0 if name.startswith(("in.", "probe.")) else 0.02
         return (torch.randn(shape, generator=g) * std).to(dtype)
     return (0.02 * torch.randn(shape, generator=g)).to(dtype)
 

@@ -51,15 +51,15 @@ def grad_stats(module, prefix=""):
 
 
 def probe(name, shape):
-    return synth.synth_tensor("probe." + name, shape) * 20.0  # fixed random projection for scalar losses
+    return synth.synth_tensor("probe." + name, shape) * 1.0  # fixed random projection for scalar losses
 
 
 def gold_blocks():
     """Block-level fixtures at small widths (full outputs stored)."""
     out = {}
     B, H, ws, C, nh, L, Ct = 2, 14, 7, 64, 2, 6, 48
-    x = synth.synth_tensor("in.x", (B, H * H, C)) * 50
-    y = synth.synth_tensor("in.y", (B, L, Ct)) * 50
+    x = synth.synth_tensor("in.x", (B, H * H, C))
+    y = synth.synth_tensor("in.y", (B, L, Ct))
     ymask = torch.zeros(B, 1, 1, L)
     ymask[1, :, :, 4:] = -10000.0
     for tag, shift, fused in (("plain", 0, False), ("shift", 3, False), ("fused", 0, True), ("fused_shift", 3, True)):
@@ -92,7 +92,7 @@ def gold_blocks():
     from timm.models.layers import PatchEmbed
     pe = PatchEmbed(img_size=56, patch_size=4, in_chans=3, embed_dim=C, norm_layer=nn.LayerNorm)
     fill(pe, "vit_model.patch_embed.")
-    img = synth.synth_tensor("in.img", (B, 3, 56, 56)) * 50
+    img = synth.synth_tensor("in.img", (B, 3, 56, 56))
     o = pe(img)
     (o * probe("pe", o.shape)).sum().backward()
     out["patch_embed"] = {"out": o.detach(), "grads": grad_stats(pe, "vit_model.patch_embed.")}
@@ -109,12 +109,12 @@ def gold_blocks():
     ref_roberta.DIM_IMG = 64
     ref_roberta.NUM_FUSE_BLOCK = 6
     Lt = 10
-    h = synth.synth_tensor("in.h", (B, Lt, 64)) * 50
+    h = synth.synth_tensor("in.h", (B, Lt, 64))
     tm = torch.ones(B, Lt, dtype=torch.long)
     tm[1, 7:] = 0
     em = (1.0 - tm[:, None, None, :].float()) * -10000.0
-    img32 = synth.synth_tensor("in.img32", (B, 20, 32)) * 50
-    img64 = synth.synth_tensor("in.img64", (B, 9, 64)) * 50
+    img32 = synth.synth_tensor("in.img32", (B, 20, 32))
+    img64 = synth.synth_tensor("in.img64", (B, 9, 64))
     for tag, li, image, last_norm in (("plain", 2, None, True), ("fused", 7, img32, True), ("fused_nonorm", 11, img64, False)):
         layer = ref_roberta.RobertaLayer(cfg, layer_index=li)
         pre = "text_transformer.encoder.layer.%d." % li
