@@ -185,13 +185,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn, i
 }
 
 // ---- misc math / memory --------------------------------------------------------------------
+// erf(|x|) by Abramowitz & Stegun 7.1.28 (|error| <= 3e-7, one reciprocal, no branches):
+//   erf(x) = 1 - 1 / (1 + a1 x + ... + a6 x^6)^16,  x >= 0
+__device__ __forceinline__ float erf_pos(float ax) {
+  float t = fmaf(ax, 0.0000430638f, 0.0002765672f);
+  t = fmaf(ax, t, 0.0001520143f);
+  t = fmaf(ax, t, 0.0092705272f);
+  t = fmaf(ax, t, 0.0422820123f);
+  t = fmaf(ax, t, 0.0705230784f);
+  t = fmaf(ax, t, 1.0f);
+  t *= t; t *= t; t *= t; t *= t;
+  return 1.0f - __fdividef(1.0f, t);
+}
+// exact (erf-form) GELU, as timm's nn.GELU and HF ACT2FN["gelu"] compute it
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float e = copysignf(erf_pos(fabsf(x) * 0.70710678118654752440f), x);
+  return 0.5f * x * (1.0f + e);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float e = copysignf(erf_pos(fabsf(x) * 0.70710678118654752440f), x);
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  return 0.5f * (1.0f + e) + x * pdf;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -2,10 +2,10 @@
 //
 //   C[M,N] = epilogue( A[M,K] . B[N,K]^T )      bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA per SM, 6 warps:
+// One CTA per SM, 10 warps:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
-//   warps 2..5  epilogue       (tcgen05.ld TMEM -> regs -> swizzled smem transpose -> coalesced
+//   warps 2..9  epilogue       (tcgen05.ld TMEM -> regs -> swizzled smem transpose -> coalesced
 //                               fused bias / GELU / GELU' / gate / DropPath / residual -> global)
 // TMEM holds two BN-column fp32 accumulators so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Operands may be K-major (forward, dgrad) or MN-major (wgrad: dW = dY^T X, both
@@ -41,7 +41,7 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 
 template <int BN>
 struct GemmCfg {
@@ -49,7 +49,7 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t STAGING_BYTES = 4 * 32 * 32 * 4;  // 4 epilogue warps x 32x32 fp32
+  static constexpr uint32_t STAGING_BYTES = 8 * 32 * 32 * 4;  // 8 epilogue warps x 32x32 fp32
   static constexpr uint32_t SMEM_BYTES =
       1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -86,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 4);
+        mbar_init(&tempty_bar[a], 8);
       }
       mbar_fence_init();
     }
@@ -176,87 +176,141 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    float* st = staging + (warp - 2) * (32 * 32);
+    // ================= epilogue (warps 2..9) =================
+    // Two warps per TMEM lane quadrant, each owning half of the accumulator columns.  Per 32-column
+    // chunk: tcgen05.ld -> swizzled smem transpose -> all global loads of the chunk issued as one
+    // batch -> math -> coalesced stores (8-byte per lane, 64 B contiguous per row).
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;  // which half of the BN columns
+    float* st = staging + ew * (32 * 32);
     int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     const float scale = p.scale ? __ldg(p.scale) : 1.0f;
+    const float* __restrict__ bias = p.bias;
+    const bf16* __restrict__ residual = p.residual;
+    const bf16* __restrict__ aux = p.aux;
+    bf16* __restrict__ preact = p.preact;
+    const float* __restrict__ row_scale = p.row_scale;
+    const int ldc = static_cast<int>(p.ldc), ldr = static_cast<int>(p.ldr), ldaux = static_cast<int>(p.ldaux),
+              ldp = static_cast<int>(p.ldp);
+    const int act = p.act, out_mode = p.out_mode;
+    const int rsub = lane >> 3, cj = lane & 7;
+    constexpr int CHUNKS = BN / 64;  // 32-column chunks per warp
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       const int tile = unit % (p.tiles_m * p.tiles_n);
       const int m0 = (tile / p.tiles_n) * GEMM_BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase[acc]);
-      tc_fence_after();
       const int ncols = min(BN, p.N - n0);
+      const long long row0 = static_cast<long long>(m0) + q * 32;  // first row of this warp
+      const int rows_left = p.M - static_cast<int>(row0);           // rows of this warp inside M
+      // DropPath / per-sample scale: a warp's 32 rows span at most two samples (rows_per_scale >= 32)
+      float rs_lo = scale, rs_hi = scale;
+      int rs_split = 1 << 30;
+      if (row_scale) {
+        const int s0 = static_cast<int>(row0 / p.rows_per_scale);
+        rs_split = (s0 + 1) * p.rows_per_scale - static_cast<int>(row0);
+        rs_lo = scale * __ldg(row_scale + s0);
+        const long long last = row0 + 31 < p.M ? row0 + 31 : p.M - 1;
+        rs_hi = scale * __ldg(row_scale + static_cast<int>(last / p.rows_per_scale));
+      }
+      bf16* c16 = reinterpret_cast<bf16*>(p.c) + row0 * p.ldc + n0;
+      float* c32 = reinterpret_cast<float*>(p.c) + row0 * p.ldc + n0;
+      const bf16* res_t = residual ? residual + row0 * p.ldr + n0 : nullptr;
+      const bf16* aux_t = aux ? aux + row0 * p.ldaux + n0 : nullptr;
+      bf16* pre_t = preact ? preact + row0 * p.ldp + n0 : nullptr;
+
+      mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (c0 >= ncols) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
-        tmem_ld_wait();
-        // transpose through swizzled smem: thread = row -> lanes along columns
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c0 = (half * CHUNKS + i) * 32;
+        const bool last_chunk = (i == CHUNKS - 1) || (c0 + 32 >= ncols);
+        if (c0 < ncols) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
+          tmem_ld_wait();
+          if (last_chunk) {  // this warp's last TMEM read of the accumulator: hand it back early
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          reinterpret_cast<float4*>(st)[lane * 8 + (j ^ (lane & 7))] = v;
-        }
-        __syncwarp();
-        const int cj = lane & 7;
-        const int col = n0 + c0 + cj * 4;
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            reinterpret_cast<float4*>(st)[lane * 8 + (j ^ (lane & 7))] = v;
+          }
+          __syncwarp();
+          const int col = c0 + cj * 4;
+          const bool cvalid = col < ncols;
+          float4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const long long row = m0 + q * 32 + rr;
-          float4 v = reinterpret_cast<float4*>(st)[rr * 8 + (cj ^ (rr & 7))];
-          if (row < p.M && col < p.N) {
-            float x[4] = {v.x, v.y, v.z, v.w};
-            if (p.bias) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + col);
-              x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
-            }
-            if (p.preact) {
-              uint2 o = make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
-              *reinterpret_cast<uint2*>(p.preact + row * p.ldp + col) = o;
-            }
-            if (p.act == 1) {
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            v[it] = reinterpret_cast<const float4*>(st)[rr * 8 + (cj ^ (rr & 7))];
+          }
+          __syncwarp();  // staging may be overwritten by the next chunk from here on
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && cvalid) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
+          uint2 rres[8], raux[8];
+          if (res_t) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
-            } else if (p.act == 2) {
-              const uint2 a = *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col);
-              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y);
-              x[0] *= gelu_erf_grad(a0.x); x[1] *= gelu_erf_grad(a0.y);
-              x[2] *= gelu_erf_grad(a1.x); x[3] *= gelu_erf_grad(a1.y);
-            }
-            float s = scale;
-            if (p.row_scale) s *= __ldg(p.row_scale + row / p.rows_per_scale);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] *= s;
-            if (p.residual) {
-              const uint2 a = *reinterpret_cast<const uint2*>(p.residual + row * p.ldr + col);
-              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y);
-              x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
-            }
-            if (p.out_mode == 0) {
-              uint2 o = make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.c) + row * p.ldc + col) = o;
-            } else if (p.out_mode == 1) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + row * p.ldc + col) =
-                  make_float4(x[0], x[1], x[2], x[3]);
-            } else {
-              float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + col;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) atomicAdd(dst + e, x[e]);
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              rres[it] = (cvalid && rr < rows_left) ? *reinterpret_cast<const uint2*>(res_t + rr * ldr + col)
+                                                    : make_uint2(0u, 0u);
             }
           }
+          if (act == 2) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rsub;
+              raux[it] = (cvalid && rr < rows_left) ? *reinterpret_cast<const uint2*>(aux_t + rr * ldaux + col)
+                                                    : make_uint2(0u, 0u);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            if (cvalid && rr < rows_left) {
+              float x[4] = {v[it].x + b4.x, v[it].y + b4.y, v[it].z + b4.z, v[it].w + b4.w};
+              if (pre_t)
+                *reinterpret_cast<uint2*>(pre_t + rr * ldp + col) =
+                    make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+              if (act == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
+              } else if (act == 2) {
+                const float2 a0 = unpack_bf16(raux[it].x), a1 = unpack_bf16(raux[it].y);
+                x[0] *= gelu_erf_grad(a0.x); x[1] *= gelu_erf_grad(a0.y);
+                x[2] *= gelu_erf_grad(a1.x); x[3] *= gelu_erf_grad(a1.y);
+              }
+              const float sc = rr < rs_split ? rs_lo : rs_hi;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] *= sc;
+              if (res_t) {
+                const float2 a0 = unpack_bf16(rres[it].x), a1 = unpack_bf16(rres[it].y);
+                x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+              }
+              if (out_mode == 0) {
+                *reinterpret_cast<uint2*>(c16 + rr * ldc + col) =
+                    make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+              } else if (out_mode == 1) {
+                *reinterpret_cast<float4*>(c32 + rr * ldc + col) = make_float4(x[0], x[1], x[2], x[3]);
+              } else {
+                float* dst = c32 + rr * ldc + col;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) atomicAdd(dst + e, x[e]);
+              }
+            }
+          }
+        } else if (i == 0) {
+          // nothing to read for this warp (narrow last tile): still release the accumulator once
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        __syncwarp();
       }
-      // all TMEM reads of this accumulator are complete (tmem_ld_wait above): hand it back
-      tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc_phase[acc] ^= 1;
+      acc_phase ^= (1u << acc);
       acc ^= 1;
     }
   }
