@@ -1,0 +1,149 @@
+"""Host-side logic that needs no GPU: C-ABI surface, module tree / state_dict compatibility with
+the reference, optimizer grouping, index maps, ITC queue ring buffer, loud failure without CUDA."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import fiber_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _cfg(tasks, image_size=224, L=40):
+    import bench
+    return bench.config(tasks, image_size, L)
+
+
+def test_capi_exports_every_declared_symbol():
+    from fiber_b200 import lib
+    handle = lib.load()  # no GPU needed to load
+    syms = lib.declared_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(handle, s), "libfiber_b200.so does not export %s" % s
+    assert handle.fiber_version() >= 100
+
+
+def test_header_cites_reference_lines():
+    text = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
+    assert len(re.findall(r"(swin_transformer|roberta|fiber_module)\.py:\d+", text)) >= 8
+
+
+def test_ctypes_structs_match_header_field_order():
+    from fiber_b200 import lib
+    text = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
+    for cname, cls in (("fiber_gemm_args", lib.GemmArgs), ("fiber_attn_args", lib.AttnArgs), ("fiber_ln_args", lib.LnArgs)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.sub(r"[\*\s]", " ", part).split()[-1])
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+@pytest.mark.parametrize("fname,tasks,size", [("model_cfg0_224_itm_mlm.pt", ["itm", "mlm"], 224),
+                                              ("model_384_infer.pt", ["itm", "mlm", "itc"], 384),
+                                              ("model_224_vqa.pt", ["vqa"], 224)])
+def test_state_dict_matches_reference(fname, tasks, size):
+    from fiber_b200.modules import FIBERTransformerSS
+    gold = torch.load(os.path.join(GOLD, fname), weights_only=False)
+    ref = {k: v for k, v in gold["state_keys"].items() if not re.match(r"(train|val)_", k)}  # PL metric states
+    L = gold["L"]
+    ours = {k: tuple(v.shape) for k, v in FIBERTransformerSS(_cfg(tasks, size, L)).state_dict().items()}
+    assert sorted(ours) == sorted(ref)
+    assert all(ours[k] == tuple(ref[k]) for k in ref)
+
+
+@pytest.mark.parametrize("tag,tasks,size", [("cfg0", ["itm", "mlm"], 224), ("cfg1", ["itm", "mlm", "itc"], 384),
+                                            ("vqa", ["vqa"], 224)])
+def test_optimizer_groups_match_reference(tag, tasks, size):
+    from fiber_b200.modules import FIBERTransformerSS, fiber_utils
+    gold = torch.load(os.path.join(GOLD, "schedule.pt"), weights_only=False)[tag]
+    model = FIBERTransformerSS(dict(_cfg(tasks, size), learning_rate=1e-5))
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = fiber_utils.param_groups(model)
+    assert len(groups) == len(gold)
+    for g, r in zip(groups, gold):
+        assert len(g["params"]) == r["n"] and sum(p.numel() for p in g["params"]) == r["numel"]
+        assert abs(g["lr"] - r["lr"]) < 1e-12 and g["weight_decay"] == r["weight_decay"]
+        assert sorted(names[id(p)] for p in g["params"])[:3] == r["first"]
+    opt, sched = fiber_utils.set_schedule(model)
+    assert isinstance(opt[0], torch.optim.AdamW) and sched[0]["interval"] == "step"
+
+
+def test_module_buffers_match_oracle_index_maps():
+    from fiber_b200.modules import swin_transformer as S
+    blk = S.SwinTransformerBlock(64, (24, 24), 2, window_size=12, shift_size=6)
+    assert torch.equal(blk.attn_mask, O.shift_attn_mask(24, 24, 12, 6))
+    assert torch.equal(blk.attn.relative_position_index, O.relative_position_index(12))
+    one = S.SwinTransformerBlock(64, (12, 12), 2, window_size=12, shift_size=6)
+    assert one.shift_size == 0 and one.attn_mask is None  # swin_transformer.py:304-307
+
+
+def test_structure_follows_reference_rules():
+    from fiber_b200.modules import FIBERTransformerSS
+    m = FIBERTransformerSS(_cfg(["itm", "mlm"], 384))
+    st2 = m.vit_model.layers[2].blocks
+    assert [b.attn.has_i2t for b in st2] == [False] * 14 + [True] * 4
+    assert [b.shift_size for b in st2[14:]] == [0, 6, 0, 6]
+    assert all(b.attn.has_i2t and b.shift_size == 0 for b in m.vit_model.layers[3].blocks)
+    enc = m.text_transformer.encoder.layer
+    assert [hasattr(l, "crossattention_t2i") for l in enc] == [False] * 6 + [True] * 6
+    assert enc[6].crossattention_t2i.self.key.weight.shape == (768, 512)
+    assert enc[10].crossattention_t2i.self.key.weight.shape == (768, 1024)
+    # rank_output aliases row 1 of the ITM classifier (fiber_module.py:112-114)
+    assert m.rank_output.weight.data_ptr() == m.itm_score.fc.weight[1:].data_ptr()
+    dpr = [b.drop_path.drop_prob if hasattr(b.drop_path, "drop_prob") else 0.0
+           for layer in m.vit_model.layers for b in layer.blocks]
+    assert dpr[0] == 0.0 and abs(dpr[-1] - 0.1) < 1e-6 and dpr == sorted(dpr)
+
+
+def test_extended_mask_and_position_ids_semantics():
+    from fiber_b200.modules.roberta import RobertaConfig, RobertaModel
+    cfg = RobertaConfig(num_hidden_layers=1, vocab_size=50)
+    rm = RobertaModel(cfg, add_pooling_layer=False)
+    mask = torch.tensor([[1, 1, 0], [1, 0, 0]])
+    ext = rm.get_extended_attention_mask(mask, mask.shape, mask.device)
+    assert ext.shape == (2, 1, 1, 3) and torch.equal(ext, O.extended_mask(mask))
+    assert float(ext.min()) == -10000.0 and float(ext.max()) == 0.0
+
+
+def test_itc_queue_ring_buffer_wraps():
+    from fiber_b200.modules import FIBERTransformerSS
+    m = FIBERTransformerSS(_cfg(["itc"], 32))
+    m.queue_size = 10
+    for name in ("image_queue", "text_queue"):
+        setattr(m, name, torch.zeros(768, 10))
+    m.image_input_queue = torch.zeros(10, 3, 32, 32)
+    m.text_input_queue = torch.zeros(10, 40, dtype=torch.long)
+    m.text_input_mask_queue = torch.zeros(10, 40, dtype=torch.long)
+    for step in range(3):
+        n = 4
+        f = torch.full((n, 768), float(step + 1))
+        m._dequeue_and_enqueue(f, -f, torch.full((n, 3, 32, 32), float(step + 1)),
+                               torch.full((n, 40), step + 1), torch.ones(n, 40, dtype=torch.long))
+    assert int(m.queue_ptr) == 2 and int(m.queue_total) == 12
+    assert m.image_queue[0].tolist() == [3, 3, 1, 1, 2, 2, 2, 2, 3, 3]
+    assert m.text_input_queue[:, 0].tolist() == [3, 3, 1, 1, 2, 2, 2, 2, 3, 3]
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly instead of computing on the CPU."""
+    from fiber_b200.modules import swin_transformer as S
+    blk = S.SwinTransformerBlock(64, (14, 14), 2, window_size=7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(torch.randn(1, 196, 64, dtype=torch.bfloat16))
+
+
+def test_product_code_never_imports_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "fiber_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "oracle" not in open(os.path.join(d, f)).read(), os.path.join(d, f)

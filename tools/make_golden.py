@@ -188,3 +188,25 @@ if __name__ == "__main__":
                    infer_modes=("fused", "image_only", "text_only"))
     if "vqa" in which:    # VQA head path at 224 px / 50 tok (576 px is covered by the window-324 block test)
         gold_model("224_vqa", 224, ["vqa"], 2, 50, infer_modes=())
+
+
+def gold_schedule():
+    """Parameter-group sizes of the reference's fiber_utils.set_schedule (name-substring rules)."""
+    import types
+    from fiber.modules import fiber_utils as ref_utils
+    out = {}
+    for tag, tasks, size in (("cfg0", ["itm", "mlm"], 224), ("cfg1", ["itm", "mlm", "itc"], 384), ("vqa", ["vqa"], 224)):
+        cfg = ref_shims.default_config(tasks=tasks, image_size=size)
+        model = FIBERTransformerSS(cfg)
+        model.trainer = types.SimpleNamespace(max_steps=1000)
+        opt = ref_utils.set_schedule(model)[0][0]
+        names = {id(p): n for n, p in model.named_parameters()}
+        out[tag] = [{"lr": g.get("initial_lr", g["lr"]), "weight_decay": g["weight_decay"], "n": len(g["params"]),
+                     "numel": sum(p.numel() for p in g["params"]),
+                     "first": sorted(names[id(p)] for p in g["params"])[:3]} for g in opt.param_groups]
+    torch.save(out, os.path.join(GOLD, "schedule.pt"))
+    print("schedule.pt", {k: [g["n"] for g in v] for k, v in out.items()})
+
+
+if __name__ == "__main__" and "schedule" in sys.argv[1:]:
+    gold_schedule()
