@@ -35,7 +35,7 @@ int num_sms() {
 
 int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream);
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream);
-int attn_bwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream);
+int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream);
 
 static AttnParams to_params(const fiber_attn_args* a) {
   AttnParams p;
@@ -131,7 +131,7 @@ int fiber_attn_fwd(const fiber_attn_args* a, fiber_stream_t stream) {
 }
 int fiber_attn_bwd(const fiber_attn_args* a, fiber_stream_t stream) {
   if (!a) { fiber::set_last_error("null args"); return -1; }
-  return fiber::attn_bwd_dispatch(fiber::to_params(a), a->head_dim, reinterpret_cast<cudaStream_t>(stream));
+  return fiber::attn_bwd_dispatch(fiber::to_params(a), a->head_dim, a->d_scratch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fiber_layernorm_fwd(const fiber_ln_args* a, fiber_stream_t s) {

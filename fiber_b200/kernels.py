@@ -138,6 +138,10 @@ def attn_bwd(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, dbias_tab
     a.lddo, a.lddq, a.lddk, a.lddv = d_o.stride(-2), dq.stride(-2), dk.stride(-2), dv.stride(-2)
     if dbias_table is not None:
         _req(dbias_table, F32, "dbias_table"); a.dbias_table = dbias_table.data_ptr()
+    scratch = None
+    if kw.get("window") is not None:
+        scratch = torch.empty((q.shape[0], heads), device=q.device, dtype=F32)
+        a.d_scratch = scratch.data_ptr()
     _lib.check(_lib.load().fiber_attn_bwd(C.byref(a), _stream()), "attn_bwd")
 
 

@@ -46,6 +46,7 @@ class AttnArgs(C.Structure):
         ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("lddo", C.c_int64), ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
         ("dbias_table", C.c_void_p),
+        ("d_scratch", C.c_void_p),
     ]
 
 

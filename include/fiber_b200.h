@@ -100,6 +100,7 @@ typedef struct fiber_attn_args {
   void* dv;
   int64_t lddo, lddq, lddk, lddv;
   float* dbias_table;
+  float* d_scratch; /* window backward: fp32 [rows, heads] workspace for rowsum(dO*O); NULL = slow path */
 } fiber_attn_args;
 
 int fiber_attn_fwd(const fiber_attn_args* args, fiber_stream_t stream);
