@@ -68,74 +68,129 @@ __device__ __forceinline__ void store8(bf16* ptr, const float (&x)[8]) {
   *reinterpret_cast<uint4*>(ptr) = u;
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnParams p) {
-  const int lane = threadIdx.x & 31;
+// Lane mapping: LPR lanes cooperate on one row (LPR = 16 for C <= 128 so both half-warps work, else
+// 32); each lane owns VPL vectors of 8 columns; ROWS row-groups are in flight per warp iteration so
+// several 16-byte loads per lane are outstanding.  Statistics in one pass (sum, sum of squares) in fp32.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL, int LPR, int ROWS>
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) ln_fwd_kernel(const LnParams p) {
+  constexpr int RPW = 32 / LPR;  // rows per warp per group
+  const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float invC = 1.0f / p.C;
-  for (long long row = warp_global; row < p.rows; row += nwarps) {
-    float x[VPL][8];
-    float sum = 0.f;
+  constexpr bool CACHE_GB = VPL <= 2;  // keep gamma/beta in registers only when that is cheap
+  float g[CACHE_GB ? VPL : 1][8], b[CACHE_GB ? VPL : 1][8];
+  if (CACHE_GB) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
-      if (col < p.C) {
-        load8(p.in1 + ln_src_offset(p, row, col), x[v]);
-        if (p.in2) {
-          float y[8];
-          load8(p.in2 + row * p.ld2 + col, y);
+      const int col = (sl + LPR * v) * 8;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) x[v][e] += y[e];
-          if (p.sum_out) store8(p.sum_out + row * p.lds + col, x[v]);
+      for (int e = 0; e < 8; ++e) {
+        g[v][e] = col < p.C ? __ldg(p.gamma + col + e) : 0.f;
+        b[v][e] = col < p.C ? __ldg(p.beta + col + e) : 0.f;
+      }
+    }
+  }
+  for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
+    float x[ROWS][VPL][8];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (sl + LPR * v) * 8;
+        if (row < p.rows && col < p.C) {
+          load8(p.in1 + ln_src_offset(p, row, col), x[r][v]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[r][v][e] = 0.f;
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sum += x[v][e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[v][e] = 0.f;
       }
     }
-    const float mean = warp_sum(sum) * invC;
-    float var = 0.f;
+    if (p.in2) {
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
-      if (col < p.C) {
+      for (int r = 0; r < ROWS; ++r) {
+        const long long row = row0 + r * RPW + sr;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = x[v][e] - mean; var += d * d; }
+        for (int v = 0; v < VPL; ++v) {
+          const int col = (sl + LPR * v) * 8;
+          if (row < p.rows && col < p.C) {
+            float y[8];
+            load8(p.in2 + row * p.ld2 + col, y);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[r][v][e] += y[e];
+            if (p.sum_out) store8(p.sum_out + row * p.lds + col, x[r][v]);
+          }
+        }
       }
     }
-    const float rstd = rsqrtf(warp_sum(var) * invC + p.eps);
+    float s1[ROWS], s2[ROWS];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
-      if (col < p.C) {
-        float y[8];
-        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + col);
-        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + col + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(p.beta + col);
-        const float4 b1 = *reinterpret_cast<const float4*>(p.beta + col + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int r = 0; r < ROWS; ++r) {
+      s1[r] = s2[r] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (x[v][e] - mean) * rstd * g[e] + b[e];
-        store8(p.out + row * p.ldo + col, y);
-      }
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s1[r] += x[r][v][e];
+          s2[r] = fmaf(x[r][v][e], x[r][v][e], s2[r]);
+        }
     }
-    if (lane == 0) {
-      if (p.mean) p.mean[row] = mean;
-      if (p.rstd) p.rstd[row] = rstd;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      s1[r] = group_sum<LPR>(s1[r]);
+      s2[r] = group_sum<LPR>(s2[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+      const float mean = s1[r] * invC;
+      const float rstd = rsqrtf(fmaxf(s2[r] * invC - mean * mean, 0.f) + p.eps);
+      if (row < p.rows) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int col = (sl + LPR * v) * 8;
+          if (col < p.C) {
+            float y[8];
+            if (CACHE_GB) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = fmaf((x[r][v][e] - mean) * rstd, g[v][e], b[v][e]);
+            } else {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + col + 4));
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = fmaf((x[r][v][e] - mean) * rstd, gg[e], bb[e]);
+            }
+            store8(p.out + row * p.ldo + col, y);
+          }
+        }
+        if (sl == 0) {
+          if (p.mean) p.mean[row] = mean;
+          if (p.rstd) p.rstd[row] = rstd;
+        }
+      }
     }
   }
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnParams p) {
+template <int VPL, int LPR, int ROWS>
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 2 : 1) ln_bwd_kernel(const LnParams p) {
+  constexpr int RPW = 32 / LPR;
   extern __shared__ float s_acc[];  // [2][C]: dgamma, dbeta block partials
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float invC = 1.0f / p.C;
@@ -145,63 +200,104 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) dg[v][e] = db[v][e] = 0.f;
 
-  for (long long row = warp_global; row < p.rows; row += nwarps) {
-    const float mean = p.mean[row], rstd = p.rstd[row];
-    float xh[VPL][8], gy[VPL][8];
-    float c1 = 0.f, c2 = 0.f;
+  for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
+    float xh[ROWS][VPL][8], gy[ROWS][VPL][8];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
-      if (col < p.C) {
-        load8(p.in1 + ln_src_offset(p, row, col), xh[v]);
-        if (p.in2) {
-          float y[8];
-          load8(p.in2 + row * p.ld2 + col, y);
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) xh[v][e] += y[e];
-        }
-        float dy[8];
-        load8(p.dy + row * p.lddy + col, dy);
-        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + col);
-        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + col + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (sl + LPR * v) * 8;
+        if (row < p.rows && col < p.C) {
+          load8(p.in1 + ln_src_offset(p, row, col), xh[r][v]);
+          load8(p.dy + row * p.lddy + col, gy[r][v]);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xh[v][e] = (xh[v][e] - mean) * rstd;
-          gy[v][e] = dy[e] * g[e];
-          c1 += gy[v][e];
-          c2 += gy[v][e] * xh[v][e];
-          dg[v][e] += dy[e] * xh[v][e];
-          db[v][e] += dy[e];
+          for (int e = 0; e < 8; ++e) xh[r][v][e] = gy[r][v][e] = 0.f;
         }
       }
     }
-    c1 = warp_sum(c1) * invC;
-    c2 = warp_sum(c2) * invC;
+    if (p.in2) {
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
-      if (col < p.C) {
-        float dx[8];
+      for (int r = 0; r < ROWS; ++r) {
+        const long long row = row0 + r * RPW + sr;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dx[e] = rstd * (gy[v][e] - c1 - xh[v][e] * c2);
-        if (p.dres) {
-          float r[8];
-          load8(p.dres + (p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddres + (col % p.Cin)
-                                  : row * p.lddres + col), r);
+        for (int v = 0; v < VPL; ++v) {
+          const int col = (sl + LPR * v) * 8;
+          if (row < p.rows && col < p.C) {
+            float y[8];
+            load8(p.in2 + row * p.ld2 + col, y);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dx[e] += r[e];
+            for (int e = 0; e < 8; ++e) xh[r][v][e] += y[e];
+          }
         }
-        const long long off = p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddx + (col % p.Cin)
-                                      : row * p.lddx + col;
-        store8(p.dx + off, dx);
+      }
+    }
+    float c1[ROWS], c2[ROWS], rs[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+      const bool rv = row < p.rows;
+      const float mean = rv ? p.mean[row] : 0.f;
+      rs[r] = rv ? p.rstd[row] : 0.f;
+      c1[r] = c2[r] = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (sl + LPR * v) * 8;
+        if (col < p.C) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4));
+          const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dy = gy[r][v][e];
+            const float xhat = (xh[r][v][e] - mean) * rs[r];
+            xh[r][v][e] = xhat;
+            gy[r][v][e] = dy * gam[e];
+            c1[r] += gy[r][v][e];
+            c2[r] = fmaf(gy[r][v][e], xhat, c2[r]);
+            dg[v][e] = fmaf(dy, xhat, dg[v][e]);
+            db[v][e] += dy;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      c1[r] = group_sum<LPR>(c1[r]);
+      c2[r] = group_sum<LPR>(c2[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+      if (row < p.rows) {
+        const float k1 = c1[r] * invC, k2 = c2[r] * invC;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int col = (sl + LPR * v) * 8;
+          if (col < p.C) {
+            float dx[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dx[e] = rs[r] * (gy[r][v][e] - k1 - xh[r][v][e] * k2);
+            if (p.dres) {
+              float rr[8];
+              load8(p.dres + (p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddres + (col % p.Cin)
+                                      : row * p.lddres + col), rr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dx[e] += rr[e];
+            }
+            const long long off = p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddx + (col % p.Cin)
+                                          : row * p.lddx + col;
+            store8(p.dx + off, dx);
+          }
+        }
       }
     }
   }
   if (p.dgamma) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const int col = (lane + 32 * v) * 8;
+      const int col = (sl + LPR * v) * 8;
       if (col < p.C) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -218,21 +314,20 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnParams p) {
   }
 }
 
-static int ln_grid(long long rows) {
-  const long long blocks = (rows + 7) / 8;  // 8 warps per block
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+static int ln_grid(long long rows, int rows_per_warp, int blocks_per_sm) {
+  const long long blocks = (rows + 8 * rows_per_warp - 1) / (8 * rows_per_warp);  // 8 warps per block
+  const long long cap = static_cast<long long>(num_sms()) * blocks_per_sm;
   return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
-template <int VPL>
+template <int VPL, int LPR, int ROWS>
 static int ln_launch(const LnParams& p, bool bwd, cudaStream_t stream) {
+  const int rpw = ROWS * (32 / LPR);
   if (!bwd) {
-    ln_fwd_kernel<VPL><<<ln_grid(p.rows), 256, 0, stream>>>(p);
+    ln_fwd_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 6), 256, 0, stream>>>(p);
   } else {
-    int grid = ln_grid(p.rows);
-    const int cap = num_sms() * 2;  // fewer blocks => fewer global atomics for dgamma/dbeta
-    if (grid > cap) grid = cap;
-    ln_bwd_kernel<VPL><<<grid, 256, 2 * p.C * sizeof(float), stream>>>(p);
+    // few resident blocks => few global atomics for dgamma/dbeta
+    ln_bwd_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 2), 256, 2 * p.C * sizeof(float), stream>>>(p);
   }
   FIBER_CUDA(cudaGetLastError());
   count_launch();
@@ -246,11 +341,12 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
     FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
                 "bad PatchMerging LayerNorm geometry");
   }
-  if (p.C <= 256) return ln_launch<1>(p, bwd, stream);
-  if (p.C <= 512) return ln_launch<2>(p, bwd, stream);
-  if (p.C <= 768) return ln_launch<3>(p, bwd, stream);
-  if (p.C <= 1024) return ln_launch<4>(p, bwd, stream);
-  return ln_launch<8>(p, bwd, stream);
+  if (p.C <= 128) return ln_launch<1, 16, 2>(p, bwd, stream);
+  if (p.C <= 256) return ln_launch<1, 32, 2>(p, bwd, stream);
+  if (p.C <= 512) return ln_launch<2, 32, 2>(p, bwd, stream);
+  if (p.C <= 768) return ln_launch<3, 32, 1>(p, bwd, stream);
+  if (p.C <= 1024) return ln_launch<4, 32, 1>(p, bwd, stream);
+  return ln_launch<8, 32, 1>(p, bwd, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
