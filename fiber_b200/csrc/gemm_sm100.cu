@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/fiber_b200.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace fiber {
@@ -37,6 +38,7 @@ struct GemmParams {
   int rows_per_scale;
   int act;
   int out_mode;
+  int tma_store;  // epilogue variant: thread=row math -> swizzled smem box -> TMA store (no residual/aux)
 };
 
 constexpr int GEMM_BM = 128;
@@ -58,6 +60,7 @@ struct GemmCfg {
 template <int BN, int MN_MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                     const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -222,6 +225,106 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
       tc_fence_after();
+      if (p.tma_store) {
+        // ---- thread = accumulator row: bias / GELU / scales on registers, bf16 pack, 16-byte stores into
+        //      this warp's 32x64 128B-swizzled box, one TMA store per box (and per output tensor) ----
+        uint8_t* box = reinterpret_cast<uint8_t*>(st);  // 4 KB, 1024-byte aligned
+        const float sc = lane < rs_split ? rs_lo : rs_hi;
+        constexpr int BOXES = BN / 128;  // 64-column boxes per warp
+        const int passes = preact ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+          const bool write_pre = preact && pass == 0;
+#pragma unroll 1
+          for (int bx = 0; bx < BOXES; ++bx) {
+            const int cb = (half * BOXES + bx) * 64;  // first column of the box inside the tile
+            if (cb < ncols) {
+              if (lane == 0) tma_store_wait_read();  // previous store has finished reading the box
+              __syncwarp();
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = cb + cc * 32;
+                // residual / GELU'-operand rows are read straight in the accumulator layout (one row per
+                // thread, 64 contiguous bytes per 32-column chunk), issued before the TMEM load completes
+                uint4 rv[4], av[4];
+                const bool row_ok = lane < rows_left;
+                if (res_t && !write_pre) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    rv[j] = (row_ok && c0 + j * 8 < ncols)
+                                ? *reinterpret_cast<const uint4*>(res_t + static_cast<long long>(lane) * ldr + c0 + j * 8)
+                                : make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (act == 2) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    av[j] = (row_ok && c0 + j * 8 < ncols)
+                                ? *reinterpret_cast<const uint4*>(aux_t + static_cast<long long>(lane) * ldaux + c0 + j * 8)
+                                : make_uint4(0u, 0u, 0u, 0u);
+                }
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {  // 16-byte chunk = 8 columns
+                  float x[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[j * 8 + e]);
+                  if (bias) {
+                    const int col = n0 + c0 + j * 8;
+                    if (col < p.N) {
+                      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                    }
+                  }
+                  if (!write_pre) {
+                    if (act == 1) {
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
+                    } else if (act == 2) {
+                      const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[j]);
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float2 f = unpack_bf16(au[e]);
+                        x[2 * e] *= gelu_erf_grad(f.x);
+                        x[2 * e + 1] *= gelu_erf_grad(f.y);
+                      }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] *= sc;
+                    if (res_t) {
+                      const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[j]);
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float2 f = unpack_bf16(ru[e]);
+                        x[2 * e] += f.x;
+                        x[2 * e + 1] += f.y;
+                      }
+                    }
+                  }
+                  uint4 o;
+                  o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+                  o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+                  const int chunk = cc * 4 + j;
+                  *reinterpret_cast<uint4*>(box + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+                }
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(write_pre ? &tmP : &tmC, box, n0 + cb, m0 + q * 32);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc_phase ^= (1u << acc);
+        acc ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int i = 0; i < CHUNKS; ++i) {
         const int c0 = (half * CHUNKS + i) * 32;
@@ -313,6 +416,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc_phase ^= (1u << acc);
       acc ^= 1;
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -365,8 +469,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
 }
 
 template <int BN, int MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BN, MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -374,7 +478,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                                     GemmCfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, p);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -429,12 +533,31 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
     if (make_tmap_bf16_2d(&ta, a->a, a->m, a->k, a->lda, 64, GEMM_BK)) return -1;
     if (make_tmap_bf16_2d(&tb, a->b, a->n, a->k, a->ldb, 64, GEMM_BK)) return -1;
   }
+  // TMA-store epilogue (thread = accumulator row) whenever the output is bf16 with TMA-compatible pitch
+  // and the fused operands are 16-byte addressable; fp32 / atomic outputs use the transposing epilogue
+  CUtensorMap tc = ta, tp = ta;
+  p.tma_store = 0;
+  static const int tma_mode = [] {  // FIBER_TMA_STORE=0 never, 1 only without residual/aux, 2 (default) always
+    const char* e = getenv("FIBER_TMA_STORE");
+    return e ? atoi(e) : 2;
+  }();
+  if (tma_mode > 0 && (tma_mode > 1 || (a->residual == nullptr && a->act != 2)) &&
+      a->out_mode == 0 && (a->ldc * 2) % 16 == 0 &&
+      (a->residual == nullptr || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)) &&
+      (a->act != 2 || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)) &&
+      (reinterpret_cast<uintptr_t>(a->c) & 15) == 0 &&
+      (a->preact == nullptr || ((a->ldp * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) &&
+      (a->row_scale == nullptr || p.rows_per_scale >= 32) && a->n % 8 == 0) {
+    if (make_tmap_bf16_2d(&tc, a->c, a->n, a->m, a->ldc, 64, 32)) return -1;
+    if (a->preact && make_tmap_bf16_2d(&tp, a->preact, a->n, a->m, a->ldp, 64, 32)) return -1;
+    p.tma_store = 1;
+  }
   const int units = tiles * p.splits;
   const int grid = units < sms ? units : sms;
   if (BN == 256) {
-    return mn ? launch_gemm<256, 1>(ta, tb, p, grid, stream) : launch_gemm<256, 0>(ta, tb, p, grid, stream);
+    return mn ? launch_gemm<256, 1>(ta, tb, tc, tp, p, grid, stream) : launch_gemm<256, 0>(ta, tb, tc, tp, p, grid, stream);
   }
-  return mn ? launch_gemm<128, 1>(ta, tb, p, grid, stream) : launch_gemm<128, 0>(ta, tb, p, grid, stream);
+  return mn ? launch_gemm<128, 1>(ta, tb, tc, tp, p, grid, stream) : launch_gemm<128, 0>(ta, tb, tc, tp, p, grid, stream);
 }
 
 }  // namespace fiber

@@ -67,3 +67,23 @@ def test_gemm_epilogue(cuda_dev):
     torch.nn.functional.gelu(x).sum().backward()
     ref2 = (a.float() @ b.float().t()) * x.grad
     torch.testing.assert_close(out2.float(), ref2, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 512, 128), (333, 264, 200), (4096, 128, 256), (130, 72, 64)])
+def test_gemm_tma_store_epilogue(cuda_dev, m, n, k):
+    """No residual / aux => thread=row epilogue with TMA stores (bias, GELU, preact, gate, DropPath)."""
+    from fiber_b200 import kernels as K
+    a = _mk((m, k), cuda_dev, 11)
+    b = _mk((n, k), cuda_dev, 12, k ** -0.5)
+    bias = torch.randn(n, device=cuda_dev)
+    scale = torch.tensor([0.75], device=cuda_dev)
+    rps = 50
+    row_scale = torch.rand((m + rps - 1) // rps, device=cuda_dev) + 0.5
+    pre = torch.zeros((m, n), device=cuda_dev, dtype=torch.bfloat16)
+    out = K.gemm(a, b, bias=bias, preact=pre, scale=scale, row_scale=row_scale, rows_per_scale=rps, act=K.ACT_GELU)
+    h = a.float() @ b.float().t() + bias
+    ref = torch.nn.functional.gelu(h) * 0.75 * row_scale.repeat_interleave(rps)[:m, None]
+    torch.testing.assert_close(pre.float(), h, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
+    out2 = K.gemm(a, b, bias=bias)
+    torch.testing.assert_close(out2.float(), h, rtol=RTOL, atol=ATOL)
