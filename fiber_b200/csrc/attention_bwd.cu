@@ -428,9 +428,8 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
   float* sD = sLse + 2 * BW_QROWS;                                  // [2][144]
   float* sTbl = sD + 2 * BW_QROWS;
   float* sdTbl = sTbl + ATT_MAXTBL;
-  uint8_t* sTh = reinterpret_cast<uint8_t*>(sdTbl + ATT_MAXTBL);
-  uint8_t* sTw = sTh + BW_QROWS;
-  uint8_t* sRid = sTw + BW_QROWS;  // [2][144]
+  int16_t* sB = reinterpret_cast<int16_t*>(sdTbl + ATT_MAXTBL);  // (j/ws)*(2ws-1) + j%ws
+  uint8_t* sRid = reinterpret_cast<uint8_t*>(sB + BW_QROWS);     // [2][144]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x;
@@ -450,10 +449,7 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
     sTbl[t] = p.bias_table[t * p.nH + h];
     sdTbl[t] = 0.f;
   }
-  for (int i = tid; i < BW_QROWS; i += blockDim.x) {
-    sTh[i] = i < N ? i / ws : 0;
-    sTw[i] = i < N ? i % ws : 0;
-  }
+  for (int i = tid; i < BW_QROWS; i += blockDim.x) sB[i] = i < N ? (i / ws) * tw2 + i % ws : 0;
 
   auto prefetch = [&](int g, int buf) {
     bf16* tb = tiles + buf * 4 * WB_TILE;
@@ -513,8 +509,10 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
       const int rl0 = warp * 16 + r_lo;
       const float lse0 = lse_s[rl0], lse1 = lse_s[rl0 + 8];
       const float D0 = d_s[rl0], D1 = d_s[rl0 + 8];
-      const int th0 = sTh[rl0], th1 = sTh[rl0 + 8], tw0 = sTw[rl0], tw1 = sTw[rl0 + 8];
+      const int aq0 = sB[rl0] + (ws - 1) * (tw2 + 1), aq1 = sB[rl0 + 8] + (ws - 1) * (tw2 + 1);
       const int rid0 = rid_s[rl0], rid1 = rid_s[rl0 + 8];
+      const int wcur = g % wg.nW;
+      const bool has_mask = p.shift > 0 && (wcur / wg.nWw == p.H / ws - 1 || wcur % wg.nWw == wg.nWw - 1);
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
 #pragma unroll
@@ -545,16 +543,15 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
           for (int nt = 0; nt < 6; ++nt) {
             const int j0 = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;  // keys j0, j0+1
             const int jj0 = j0 < N ? j0 : 0, jj1 = j0 + 1 < N ? j0 + 1 : 0;
-            const int thj0 = sTh[jj0], thj1 = sTh[jj1], twj0 = sTw[jj0], twj1 = sTw[jj1];
-            const int ridj0 = rid_s[jj0], ridj1 = rid_s[jj1];
+            const int bj0 = sB[jj0], bj1 = sB[jj1];
+            const int ridj0 = has_mask ? rid_s[jj0] : 0, ridj1 = has_mask ? rid_s[jj1] : 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const bool hi = e >> 1, odd = e & 1;
               const int j = j0 + odd;
-              const int thq = hi ? th1 : th0, twq = hi ? tw1 : tw0, ridq = hi ? rid1 : rid0;
-              const int thj = odd ? thj1 : thj0, twj = odd ? twj1 : twj0, ridj = odd ? ridj1 : ridj0;
-              float v = s[nt][e] * p.scale + sTbl[(thq - thj + ws - 1) * tw2 + twq - twj + ws - 1];
-              if (p.shift > 0 && ridq != ridj) v += -100.0f;
+              const int ridq = hi ? rid1 : rid0, ridj = odd ? ridj1 : ridj0;
+              float v = s[nt][e] * p.scale + sTbl[(hi ? aq1 : aq0) - (odd ? bj1 : bj0)];
+              if (has_mask && ridq != ridj) v += -100.0f;
               const float pr = (j < N) ? __expf(v - (hi ? lse1 : lse0)) : 0.f;
               const float ds = pr * (dp[nt][e] - (hi ? D1 : D0));
               s[nt][e] = pr;
@@ -659,9 +656,7 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
       const int j = t * 8 + (lane & 3) * 2 + (e & 1);
       const int qi = warp * 16 + r_lo + (e >> 1) * 8;
       if (qi < N && j < N)
-        atomicAdd(&sdTbl[(static_cast<int>(sTh[qi]) - static_cast<int>(sTh[j]) + ws - 1) * tw2 +
-                         static_cast<int>(sTw[qi]) - static_cast<int>(sTw[j]) + ws - 1],
-                  dbacc[t][e]);
+        atomicAdd(&sdTbl[sB[qi] + (ws - 1) * (tw2 + 1) - sB[j]], dbacc[t][e]);
     }
   }
   __syncthreads();

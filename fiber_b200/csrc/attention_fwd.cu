@@ -22,9 +22,9 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
   float* sMask = reinterpret_cast<float*>(sV + ATT_SKEYS * PITCH);  // [ATT_SKEYS]
   float* sTbl = sMask + ATT_SKEYS;                                  // window only
   int* sRow = reinterpret_cast<int*>(sTbl + ATT_MAXTBL);
-  uint8_t* sTh = reinterpret_cast<uint8_t*>(sRow + ATT_MAXTOK);
-  uint8_t* sTw = sTh + ATT_MAXTOK;
-  uint8_t* sRid = sTw + ATT_MAXTOK;
+  // bias index = A_q - sB[j] with A_q = (qi/ws)*(2ws-1) + qi%ws + (ws-1)*2ws, sB[j] = (j/ws)*(2ws-1) + j%ws
+  int16_t* sB = reinterpret_cast<int16_t*>(sRow + ATT_MAXTOK);
+  uint8_t* sRid = reinterpret_cast<uint8_t*>(sB + ATT_MAXTOK);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * QROWS, h = blockIdx.y, g = blockIdx.z;
@@ -32,19 +32,22 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
   const int Lq = p.Lq, Lk = p.Lk;
   long long qbase = static_cast<long long>(g) * Lq, kbase = static_cast<long long>(g) * Lk;
   const int ws = p.ws, tw2 = 2 * ws - 1;
+  bool has_mask = false;  // only windows in the last window row / column contain masked pairs
 
   if (window) {
     const int nWw = p.W / ws, nW = (p.H / ws) * nWw;
     const int b = g / nW, w = g % nW, wh = w / nWw, ww = w % nWw;
+    has_mask = p.shift > 0 && (wh == p.H / ws - 1 || ww == nWw - 1);
     for (int i = tid; i < ATT_MAXTOK; i += blockDim.x) {
-      int row = 0, th = 0, tw = 0, rid = 0;
+      int row = 0, bidx = 0, rid = 0;
       if (i < Lq) {
-        th = i / ws; tw = i % ws;
+        const int th = i / ws, tw = i % ws;
         const int hp = wh * ws + th, wp = ww * ws + tw;
         row = b * p.H * p.W + ((hp + p.shift) % p.H) * p.W + (wp + p.shift) % p.W;
         rid = 3 * ((hp >= p.H - ws) + (hp >= p.H - p.shift)) + (wp >= p.W - ws) + (wp >= p.W - p.shift);
+        bidx = th * tw2 + tw;
       }
-      sRow[i] = row; sTh[i] = th; sTw[i] = tw; sRid[i] = rid;
+      sRow[i] = row; sB[i] = static_cast<int16_t>(bidx); sRid[i] = rid;
     }
     for (int t = tid; t < tw2 * tw2; t += blockDim.x) sTbl[t] = p.bias_table[t * p.nH + h];
     __syncthreads();
@@ -112,22 +115,40 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
       }
       // ---- scale + bias + mask, online softmax ----
       float mx[2] = {-1e30f, -1e30f};
+      int aq[2] = {0, 0}, ridq[2] = {0, 0};
+      if (window) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int qi = qi0 + r * 8;
+          const int qq = qi < Lq ? qi : 0;
+          aq[r] = sB[qq] + (ws - 1) * (tw2 + 1);
+          ridq[r] = sRid[qq];
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 6; ++nt) {
+        const int jl0 = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;
+        int bj[2] = {0, 0}, ridj[2] = {0, 0};
+        float mk[2] = {0.f, 0.f};
+        if (window) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int jj = kc0 + jl0 + c < Lk ? kc0 + jl0 + c : 0;
+            bj[c] = sB[jj];
+            if (has_mask) ridj[c] = sRid[jj];
+          }
+        } else {
+          mk[0] = sMask[jl0]; mk[1] = sMask[jl0 + 1];
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int jl = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2 + (e & 1);  // key within smem chunk
-          const int j = kc0 + jl;
-          const int qi = qi0 + (e >> 1) * 8;
+          const int j = kc0 + jl0 + (e & 1);
           float v = s[nt][e] * p.scale;
           if (window) {
-            const int qq = qi < Lq ? qi : 0;
-            const int jj = j < Lk ? j : 0;
-            v += sTbl[(static_cast<int>(sTh[qq]) - static_cast<int>(sTh[jj]) + ws - 1) * tw2 +
-                      static_cast<int>(sTw[qq]) - static_cast<int>(sTw[jj]) + ws - 1];
-            if (p.shift > 0 && sRid[qq] != sRid[jj]) v += -100.0f;
+            v += sTbl[aq[e >> 1] - bj[e & 1]];
+            if (has_mask && ridq[e >> 1] != ridj[e & 1]) v += -100.0f;
           } else {
-            v += sMask[jl];
+            v += mk[e & 1];
           }
           if (j >= Lk) v = -1e30f;
           s[nt][e] = v;
@@ -222,7 +243,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int QROWS = 16 * NWARPS;
   constexpr int PITCH = HD + 8;
   const size_t smem = (QROWS + 2 * ATT_SKEYS) * PITCH * 2 + ATT_SKEYS * 4 + ATT_MAXTBL * 4 +
-                      ATT_MAXTOK * 4 + 3 * ATT_MAXTOK + 16;
+                      ATT_MAXTOK * 4 + 3 * ATT_MAXTOK + 16;  // sRow + sB (int16) + sRid
   auto kern = attn_fwd_kernel<HD, NWARPS>;
   static bool attr_set = false;
   if (!attr_set) {
