@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
   uint8_t* sTh = reinterpret_cast<uint8_t*>(sRow + ATT_MAXTOK);
   uint8_t* sTw = sTh + ATT_MAXTOK;
   uint8_t* sRid = sTw + ATT_MAXTOK;
+  // fp32 dQ accumulator [nqc*144][HD], only when both the query and the key loop have several chunks
+  float* sDQ = reinterpret_cast<float*>(smem + (((sRid + ATT_MAXTOK) - smem + 15) & ~static_cast<ptrdiff_t>(15)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
   const int nqc = (Lq + BW_QROWS - 1) / BW_QROWS;
   const float keep_inv = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
   const int r_lo = lane >> 2;
+  const bool acc_dq_smem = nqc > 1 && nkc > 1;
+  const bool db_regs = Lq <= BW_QROWS;  // fixed (i,j) ownership only with a single query/key chunk
 
   float dbacc[WINDOW ? 18 : 1][4];
   if (WINDOW) {
@@ -166,6 +170,13 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
 #pragma unroll
             for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
           }
+          if (acc_dq_smem && kc > 0) {  // continue the running sum of this query tile (thread-private slots)
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) {
+              const float* a0 = sDQ + (q0 + warp * 16 + r_lo) * HD + i * 8 + (lane & 3) * 2;
+              dq[i][0] = a0[0]; dq[i][1] = a0[1]; dq[i][2] = a0[8 * HD]; dq[i][3] = a0[8 * HD + 1];
+            }
+          }
 #pragma unroll
           for (int sub = 0; sub < ATT_SKEYS / ATT_KCHUNK; ++sub) {
             if (sub * ATT_KCHUNK < nk_pad) {
@@ -220,7 +231,14 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
                   const float ds = pr * (dpv - ((e >> 1) ? D1 : D0));
                   s[nt][e] = pd;
                   dp[nt][e] = ds;
-                  if (WINDOW) dbacc[sub * 6 + nt][e] += ds;
+                  if (WINDOW) {
+                    if (db_regs) {
+                      dbacc[sub * 6 + nt][e] += ds;
+                    } else if (qi < Lq && j < Lk) {
+                      atomicAdd(&sdTbl[(static_cast<int>(sTh[qi]) - static_cast<int>(sTh[j]) + ws - 1) * tw2 +
+                                       static_cast<int>(sTw[qi]) - static_cast<int>(sTw[j]) + ws - 1], ds);
+                    }
+                  }
                 }
               }
               // P, dS -> smem (bf16) for phase B; dQ += dS K from registers
@@ -280,8 +298,16 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
             }
           }
         }
-        // ---- dQ store (per query chunk when the key loop has one chunk, else after the last) ----
-        if (nqc > 1 || kc == nkc - 1) {
+        // ---- dQ: running sums in smem while more key chunks follow; store after the last ----
+        if (acc_dq_smem && kc < nkc - 1) {
+          if (warp < n_qtiles) {
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) {
+              float* a0 = sDQ + (q0 + warp * 16 + r_lo) * HD + i * 8 + (lane & 3) * 2;
+              a0[0] = dq[i][0]; a0[1] = dq[i][1]; a0[8 * HD] = dq[i][2]; a0[8 * HD + 1] = dq[i][3];
+            }
+          }
+        } else if (nqc > 1 || kc == nkc - 1) {
           __syncthreads();  // phase B finished reading sQ
           if (warp < n_qtiles) {
 #pragma unroll
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
     // flush the register-resident d(bias) sums: smem atomics, then one global atomic per entry
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 18; ++t) {
+    for (int t = 0; t < (db_regs ? 18 : 0); ++t) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = t * 8 + (lane & 3) * 2 + (e & 1);
@@ -694,14 +720,17 @@ static int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
 template <int HD, bool WINDOW>
 static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int PITCH = HD + 8;
-  const size_t smem = (2 * BW_QROWS + 2 * ATT_SKEYS) * PITCH * 2 + 2 * BW_QROWS * BW_SP * 2 +
+  const int nqc = (p.Lq + BW_QROWS - 1) / BW_QROWS, nkc = (p.Lk + ATT_SKEYS - 1) / ATT_SKEYS;
+  const size_t base = (2 * BW_QROWS + 2 * ATT_SKEYS) * PITCH * 2 + 2 * BW_QROWS * BW_SP * 2 +
                       (2 * BW_QROWS + ATT_SKEYS) * 4 + 2 * ATT_MAXTBL * 4 + ATT_MAXTOK * 4 +
-                      3 * ATT_MAXTOK + 16;
+                      3 * ATT_MAXTOK + 32;
+  const size_t smem = base + ((nqc > 1 && nkc > 1) ? static_cast<size_t>(nqc) * BW_QROWS * HD * 4 : 0);
+  FIBER_CHECK(smem <= 227 * 1024, "attention backward: Lq=%d with Lk=%d needs %zu bytes of shared memory", p.Lq, p.Lk, smem);
   auto kern = attn_bwd_kernel<HD, WINDOW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   const int n_groups = WINDOW ? p.G * (p.H / p.ws) * (p.W / p.ws) : p.G;
   int gy = n_groups;
@@ -719,9 +748,6 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
   FIBER_CHECK(p.d_o && p.dq && p.dk && p.dv && p.lse && p.o, "attention backward needs o, lse, d_o, dq, dk, dv");
-  FIBER_CHECK(p.Lq <= BW_QROWS || p.Lk <= ATT_SKEYS,
-              "attention backward: Lq > 144 together with Lk > 144 is not supported yet (Lq=%d, Lk=%d)",
-              p.Lq, p.Lk);
   if (p.mode == 1) {
     FIBER_CHECK(hd == 32, "window attention uses head_dim 32");
     FIBER_CHECK(p.dbias_table != nullptr, "window backward needs dbias_table");

@@ -46,7 +46,13 @@ def _check_param_grads(module, prefix, sd, tol=GRAD_TOL):
         assert p.grad is not None, "missing grad for " + n
         a, b = p.grad.float(), go.float()
         err = (a - b).abs().max().item()
-        t = 0.1 if "alpha" in n else tol
+        t = tol
+        if "alpha" in n:
+            # scalar gate gradient = dot product of two bf16 tensors over rows*C elements with heavy
+            # cancellation: its rounding noise scales with the operands (block scale), not with the result
+            assert err <= 0.1 * b.abs().max().item() + 5e-3 * scale, \
+                "d%s: err %g vs ref %g (block scale %g)" % (n, err, b.abs().max().item(), scale)
+            continue
         if n.endswith("self.key.bias"):  # exactly zero in exact arithmetic; bf16 colsum noise on our side
             assert a.abs().max().item() <= 1e-3 * scale, "d%s: %g (block scale %g)" % (n, a.abs().max().item(), scale)
             continue
@@ -60,6 +66,8 @@ def _check_param_grads(module, prefix, sd, tol=GRAD_TOL):
     (2, 24, 12, 512, 16, 6, True),      # FIBER stage 2 @384
     (3, 12, 12, 1024, 32, 0, True),     # FIBER stage 3 @384
     (1, 96, 12, 128, 4, 6, False),      # FIBER stage 0 @384
+    (1, 36, 18, 512, 16, 9, True),      # FIBER stage 2 @576 (VQA config: 324-token windows, L=50 handled below)
+    (2, 18, 18, 1024, 32, 0, True),     # FIBER stage 3 @576
 ])
 def test_swin_block(cuda_dev, B, H, ws, C, nh, shift, fused):
     from fiber_b200.modules import swin_transformer as S
