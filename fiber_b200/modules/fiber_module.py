@@ -154,6 +154,7 @@ class FIBERTransformerSS(LightningModule):
             return {"text_feats": text_embeds, "image_feats": None, "cls_feats": cls, "text_labels": text_labels,
                     "text_ids": text_ids, "text_masks": text_masks, "image": None}
 
+        vit.draw_droppath(img.shape[0], img.device)
         image_embeds = vit.pos_drop(vit.patch_embed(img))
         if image_only:  # fiber_module.py:278-308
             for layer in vit.layers:

@@ -162,8 +162,12 @@ class SwinTransformerBlock(nn.Module):
             assert y.shape[0] == B, "B_ is not a multiplier of B_text in window attention"
         s1 = s2 = None
         if isinstance(self.drop_path, DropPath):
-            s1 = self.drop_path.sample_scale(B, x.device)
-            s2 = self.drop_path.sample_scale(B, x.device)
+            pre = self.__dict__.pop("_dp_scales", None)  # drawn in bulk by SwinTransformer.draw_droppath
+            if pre is not None and pre[0].shape[0] == B and self.training:
+                s1, s2 = pre
+            else:
+                s1 = self.drop_path.sample_scale(B, x.device)
+                s2 = self.drop_path.sample_scale(B, x.device)
         mask2d = None
         if fused and y_mask is not None:
             mask2d = y_mask.reshape(B, -1).float()
@@ -244,7 +248,20 @@ class SwinTransformer(nn.Module):
         self.avgpool = nn.AdaptiveAvgPool1d(1)
         self.apply(_init_vit_weights)
 
+    def draw_droppath(self, batch, device):
+        """Draw the two independent per-sample DropPath scales of every block of one pass in a single
+        batched op (same distribution as timm's DropPath: floor(keep + U) / keep per sample)."""
+        blocks = [b for layer in self.layers for b in layer.blocks if isinstance(b.drop_path, DropPath)
+                  and b.drop_path.drop_prob > 0.0]
+        if not self.training or not blocks:
+            return
+        keep = torch.tensor([1.0 - b.drop_path.drop_prob for b in blocks for _ in range(2)], device=device)
+        scales = torch.floor(keep[:, None] + torch.rand(len(keep), batch, device=device)) / keep[:, None]
+        for i, b in enumerate(blocks):
+            b.__dict__["_dp_scales"] = (scales[2 * i], scales[2 * i + 1])
+
     def forward_features(self, x, y=None, y_mask=None):
+        self.draw_droppath(x.shape[0], x.device)
         x = self.patch_embed(x)
         x = self.pos_drop(x)
         for layer in self.layers:

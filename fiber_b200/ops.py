@@ -102,9 +102,32 @@ class _WeightCache:
 CACHE = _WeightCache()
 
 
-def _wgrad(dy, x, scale=None):
+class _GradArena(dict):
+    """One zero-filled fp32 buffer per backward call; gradients are named views of it (a single
+    memset instead of one fill kernel per gradient tensor)."""
+
+    def __init__(self, shapes, device):
+        super().__init__()
+        sizes = {}
+        for n, shp in shapes.items():
+            numel = 1
+            for d in shp:
+                numel *= d
+            sizes[n] = (numel, ((numel + 3) // 4) * 4)  # keep every view 16-byte aligned
+        flat = torch.zeros(sum(v[1] for v in sizes.values()), device=device, dtype=F32)
+        off = 0
+        for n, shp in shapes.items():
+            self[n] = flat[off:off + sizes[n][0]].view(shp)
+            off += sizes[n][1]
+
+
+def _wgrad(dy, x, scale=None, out=None):
     """dW[N,K] = dy[rows,N]^T x[rows,K]  (fp32, split-K atomics on a zeroed buffer)."""
-    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale)
+    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale, out=out)
+
+
+def _colsum(x, out=None, **kw):
+    return K.colsum(x, out=out, **kw)
 
 
 def _as2d(x):
@@ -285,19 +308,18 @@ class SwinBlockFn(torch.autograd.Function):
         hd = C // nh
         scale = hd ** -0.5
         fused = sv["fused"]
-        g = {}
+        names = SWIN_FUSED if fused else SWIN_PLAIN
+        g = _GradArena({n: tuple(p[n].shape) for n in names}, dout.device)
         d_out = _to_bf16_2d(dout)
 
         # ---- MLP branch: out = x1 + s * fc2(gelu(fc1(LN2(x1)))) ----
         dz = K.scale_rows(d_out, sv["s_mlp"], T) if sv["s_mlp"] is not None else d_out
-        g["mlp.fc2.weight"] = _wgrad(dz, sv["a"])
-        g["mlp.fc2.bias"] = K.colsum(dz)
+        _wgrad(dz, sv["a"], out=g["mlp.fc2.weight"])
+        K.colsum(dz, out=g["mlp.fc2.bias"])
         dh = K.gemm(dz, sv["w2_t"], aux=sv["h"], act=K.ACT_GELU_GRAD)
-        g["mlp.fc1.weight"] = _wgrad(dh, sv["ln2"])
-        g["mlp.fc1.bias"] = K.colsum(dh)
+        _wgrad(dh, sv["ln2"], out=g["mlp.fc1.weight"])
+        K.colsum(dh, out=g["mlp.fc1.bias"])
         dln2 = K.gemm(dh, sv["w1_t"])
-        g["norm2.weight"] = torch.zeros_like(p["norm2.weight"])
-        g["norm2.bias"] = torch.zeros_like(p["norm2.bias"])
         dx1 = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
                               dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
         # ---- attention branch: x1 = x + s * (z [+ alpha * y]) ----
@@ -305,46 +327,40 @@ class SwinBlockFn(torch.autograd.Function):
         dtext = None
         if fused:
             alpha = p["attn.alpha_i2t"]
-            g["attn.alpha_i2t"] = K.dot(dZ, sv["y"])
-            g["attn.proj_i2t.weight"] = _wgrad(dZ, sv["ao2"], scale=alpha)
-            g["attn.proj_i2t.bias"] = K.colsum(dZ, scale=alpha)
+            K.dot(dZ, sv["y"], out=g["attn.alpha_i2t"])
+            _wgrad(dZ, sv["ao2"], scale=alpha, out=g["attn.proj_i2t.weight"])
+            K.colsum(dZ, scale=alpha, out=g["attn.proj_i2t.bias"])
             dao2 = K.gemm(dZ, sv["wp2_t"], scale=alpha)
             dq2 = torch.empty_like(sv["q2"])
             dkvt = torch.empty_like(sv["kvt"])
             K.attn_bwd(dao2, sv["q2"], sv["kvt"][:, :C], sv["kvt"][:, C:], sv["ao2"], sv["lse2"], nh, hd, scale,
                        dq2, dkvt[:, :C], dkvt[:, C:], groups=B, lq=T, lk=sv["L"], key_mask=sv["km"])
-            g["attn.qkv_text_i2t.weight"] = _wgrad(dkvt, sv["t2"])
-            g["attn.qkv_text_i2t.bias"] = K.colsum(dkvt)
+            _wgrad(dkvt, sv["t2"], out=g["attn.qkv_text_i2t.weight"])
+            K.colsum(dkvt, out=g["attn.qkv_text_i2t.bias"])
             if ctx.needs_input_grad[1]:
                 dtext = K.gemm(dkvt, sv["wkvt_t"]).view(sv["text_shape"])
-            g["attn.qkv_i2t.weight"] = _wgrad(dq2, sv["lnz"])
-            g["attn.qkv_i2t.bias"] = K.colsum(dq2)
+            _wgrad(dq2, sv["lnz"], out=g["attn.qkv_i2t.weight"])
+            K.colsum(dq2, out=g["attn.qkv_i2t.bias"])
             dlnz = K.gemm(dq2, sv["wq2_t"])
-            g["attn.norm_i2t_i.weight"] = torch.zeros_like(p["attn.norm_i2t_i.weight"])
-            g["attn.norm_i2t_i.bias"] = torch.zeros_like(p["attn.norm_i2t_i.bias"])
             dzz = K.layernorm_bwd(dlnz, sv["z"], sv["meanz"], sv["rstdz"], p["attn.norm_i2t_i.weight"], dres=dZ,
                                   dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"])
         else:
             dzz = dZ
-        g["attn.proj.weight"] = _wgrad(dzz, sv["ao"])
-        g["attn.proj.bias"] = K.colsum(dzz)
+        _wgrad(dzz, sv["ao"], out=g["attn.proj.weight"])
+        K.colsum(dzz, out=g["attn.proj.bias"])
         dao = K.gemm(dzz, sv["wproj_t"])
         dqkv = torch.empty_like(sv["qkv"])
-        g["attn.relative_position_bias_table"] = torch.zeros_like(p["attn.relative_position_bias_table"])
         qkv = sv["qkv"]
         K.attn_bwd(dao, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sv["ao"], sv["lse"], nh, hd, scale,
                    dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
                    dbias_table=g["attn.relative_position_bias_table"], window=(B, H, W, ws, shift),
                    bias_table=p["attn.relative_position_bias_table"])
-        g["attn.qkv.weight"] = _wgrad(dqkv, sv["ln1"])
-        g["attn.qkv.bias"] = K.colsum(dqkv)
+        _wgrad(dqkv, sv["ln1"], out=g["attn.qkv.weight"])
+        K.colsum(dqkv, out=g["attn.qkv.bias"])
         dln1 = K.gemm(dqkv, sv["wqkv_t"])
-        g["norm1.weight"] = torch.zeros_like(p["norm1.weight"])
-        g["norm1.bias"] = torch.zeros_like(p["norm1.bias"])
         dx = K.layernorm_bwd(dln1, sv["x2"], sv["mean1"], sv["rstd1"], p["norm1.weight"], dres=dx1,
                              dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
         ctx.sv = None
-        names = SWIN_FUSED if fused else SWIN_PLAIN
         return (dx.view(B, T, C), dtext, None, None, None, None) + tuple(g[n] for n in names)
 
 
@@ -472,11 +488,16 @@ class RobertaLayerFn(torch.autograd.Function):
         hd = C // nh
         scale = 1.0 / math.sqrt(hd)
         fused = sv["fused"]
-        g = {}
+        names = ROBERTA_FUSED if fused else ROBERTA_PLAIN
+        shapes = {n: tuple(p[n].shape) for n in names if "self." not in n}
+        shapes["wqkv"], shapes["bqkv"] = (3 * C, C), (3 * C,)
+        if fused:
+            shapes["wkv2"], shapes["bkv2"] = (2 * C, sv["img2"].shape[1]), (2 * C,)
+            shapes["crossattention_t2i.self.query.weight"] = (C, C)
+            shapes["crossattention_t2i.self.query.bias"] = (C,)
+        g = _GradArena(shapes, dout.device)
         d_out = _to_bf16_2d(dout)
         if last_norm:
-            g["output.LayerNorm.weight"] = torch.zeros_like(p["output.LayerNorm.weight"])
-            g["output.LayerNorm.bias"] = torch.zeros_like(p["output.LayerNorm.bias"])
             dsum = K.layernorm_bwd(d_out, sv["f"], sv["mean_o"], sv["rstd_o"], p["output.LayerNorm.weight"],
                                    add=sv["ln_a"], dgamma=g["output.LayerNorm.weight"],
                                    dbeta=g["output.LayerNorm.bias"])
@@ -484,56 +505,53 @@ class RobertaLayerFn(torch.autograd.Function):
             g["output.LayerNorm.weight"] = g["output.LayerNorm.bias"] = None
             dsum = d_out
         df = K.dropout(dsum, p_h, sv["seed_f"]) if p_h > 0 else dsum
-        g["output.dense.weight"] = _wgrad(df, sv["inter"])
-        g["output.dense.bias"] = K.colsum(df)
+        _wgrad(df, sv["inter"], out=g["output.dense.weight"])
+        K.colsum(df, out=g["output.dense.bias"])
         dhpre = K.gemm(df, sv["wout_t"], aux=sv["hpre"], act=K.ACT_GELU_GRAD)
-        g["intermediate.dense.weight"] = _wgrad(dhpre, sv["ln_a"])
-        g["intermediate.dense.bias"] = K.colsum(dhpre)
+        _wgrad(dhpre, sv["ln_a"], out=g["intermediate.dense.weight"])
+        K.colsum(dhpre, out=g["intermediate.dense.bias"])
         dln_a = K.gemm(dhpre, sv["wi_t"], residual=dsum)
-        g["attention.output.LayerNorm.weight"] = torch.zeros_like(p["attention.output.LayerNorm.weight"])
-        g["attention.output.LayerNorm.bias"] = torch.zeros_like(p["attention.output.LayerNorm.bias"])
         ds1 = K.layernorm_bwd(dln_a, sv["a2"], sv["mean_a"], sv["rstd_a"], p["attention.output.LayerNorm.weight"],
                               add=sv["h2"], dgamma=g["attention.output.LayerNorm.weight"],
                               dbeta=g["attention.output.LayerNorm.bias"])
         dimage = None
         if fused:
             alpha = p["alpha_t2i"]
-            g["alpha_t2i"] = K.dot(ds1, sv["c"])
+            K.dot(ds1, sv["c"], out=g["alpha_t2i"])
             gc = K.dropout(ds1, p_h, sv["seed_o2"]) if p_h > 0 else ds1
-            g["crossattention_t2i.output.dense.weight"] = _wgrad(gc, sv["ctx2"], scale=alpha)
-            g["crossattention_t2i.output.dense.bias"] = K.colsum(gc, scale=alpha)
+            _wgrad(gc, sv["ctx2"], scale=alpha, out=g["crossattention_t2i.output.dense.weight"])
+            K.colsum(gc, scale=alpha, out=g["crossattention_t2i.output.dense.bias"])
             dctx2 = K.gemm(gc, sv["wo2_t"], scale=alpha)
             dq2 = torch.empty_like(sv["q2"])
             dkv2 = torch.empty_like(sv["kv2"])
             K.attn_bwd(dctx2, sv["q2"], sv["kv2"][:, :C], sv["kv2"][:, C:], sv["ctx2"], sv["lse2"], nh, hd, scale,
                        dq2, dkv2[:, :C], dkv2[:, C:], groups=B, lq=L, lk=sv["Tk"], drop_p=p_a, seed=sv["seed_a2"])
-            dwkv2 = _wgrad(dkv2, sv["img2"])
-            dbkv2 = K.colsum(dkv2)
+            dwkv2 = _wgrad(dkv2, sv["img2"], out=g["wkv2"])
+            dbkv2 = K.colsum(dkv2, out=g["bkv2"])
             g["crossattention_t2i.self.key.weight"], g["crossattention_t2i.self.value.weight"] = dwkv2[:C], dwkv2[C:]
             g["crossattention_t2i.self.key.bias"], g["crossattention_t2i.self.value.bias"] = dbkv2[:C], dbkv2[C:]
             if ctx.needs_input_grad[2]:
                 dimage = K.gemm(dkv2, sv["wkv2_t"]).view(sv["image_shape"])
-            g["crossattention_t2i.self.query.weight"] = _wgrad(dq2, sv["a"])
-            g["crossattention_t2i.self.query.bias"] = K.colsum(dq2)
+            _wgrad(dq2, sv["a"], out=g["crossattention_t2i.self.query.weight"])
+            K.colsum(dq2, out=g["crossattention_t2i.self.query.bias"])
             da = K.gemm(dq2, sv["wq2_t"], residual=ds1)
         else:
             da = ds1
         if p_h > 0:
             da = K.dropout(da, p_h, sv["seed_o"])
-        g["attention.output.dense.weight"] = _wgrad(da, sv["ctxv"])
-        g["attention.output.dense.bias"] = K.colsum(da)
+        _wgrad(da, sv["ctxv"], out=g["attention.output.dense.weight"])
+        K.colsum(da, out=g["attention.output.dense.bias"])
         dctx = K.gemm(da, sv["wo_t"])
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
         K.attn_bwd(dctx, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sv["ctxv"], sv["lse"], nh, hd, scale,
                    dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], groups=B, lq=L, lk=L, key_mask=sv["km"],
                    drop_p=p_a, seed=sv["seed_a"])
-        dwqkv = _wgrad(dqkv, sv["h2"])
-        dbqkv = K.colsum(dqkv)
+        dwqkv = _wgrad(dqkv, sv["h2"], out=g["wqkv"])
+        dbqkv = K.colsum(dqkv, out=g["bqkv"])
         for i, n in enumerate(("query", "key", "value")):
             g["attention.self.%s.weight" % n] = dwqkv[i * C:(i + 1) * C]
             g["attention.self.%s.bias" % n] = dbqkv[i * C:(i + 1) * C]
         dh = K.gemm(dqkv, sv["wqkv_t"], residual=ds1)
         ctx.sv = None
-        names = ROBERTA_FUSED if fused else ROBERTA_PLAIN
         return (dh.view(B, L, C), None, dimage, None) + tuple(g[n] for n in names)
