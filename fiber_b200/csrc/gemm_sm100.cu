@@ -2,11 +2,12 @@
 //
 //   C[M,N] = epilogue( A[M,K] . B[N,K]^T )      bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA per SM, 10 warps:
+// One CTA per SM, 18 warps:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers)
-//   warps 2..9  epilogue       (tcgen05.ld TMEM -> regs -> swizzled smem transpose -> coalesced
-//                               fused bias / GELU / GELU' / gate / DropPath / residual -> global)
+//   warps 2..17 epilogue       (thread = accumulator row: tcgen05.ld TMEM -> registers -> fused bias /
+//                               GELU / GELU' / gate / DropPath / residual -> bf16 pack -> 64B-swizzled
+//                               smem box -> TMA store; fp32 / atomic outputs store from registers)
 // TMEM holds two BN-column fp32 accumulators so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Operands may be K-major (forward, dgrad) or MN-major (wgrad: dW = dY^T X, both
 // operands read straight from their row-major activations, no transposes materialised).
@@ -43,7 +44,7 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_THREADS = 576;  // TMA warp, MMA warp, 16 epilogue warps
 
 template <int BN>
 struct GemmCfg {
@@ -51,7 +52,7 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t STAGING_BYTES = 8 * 32 * 32 * 4;  // 8 epilogue warps x 32x32 fp32
+  static constexpr uint32_t STAGING_BYTES = 16 * 2048;  // 16 epilogue warps x (32 rows x 64 B) TMA-store box
   static constexpr uint32_t SMEM_BYTES =
       1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -89,7 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 8);
+        mbar_init(&tempty_bar[a], 16);
       }
       mbar_fence_init();
     }
@@ -179,14 +180,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
     }
   } else {
-    // ================= epilogue (warps 2..9) =================
-    // Two warps per TMEM lane quadrant, each owning half of the accumulator columns.  Per 32-column
-    // chunk: tcgen05.ld -> swizzled smem transpose -> all global loads of the chunk issued as one
-    // batch -> math -> coalesced stores (8-byte per lane, 64 B contiguous per row).
+    // ================= epilogue (warps 2..17) =================
+    // Four warps per TMEM lane quadrant, each owning a quarter of the accumulator columns.  Thread =
+    // accumulator row: per 32-column chunk one tcgen05.ld, all fused math on registers (bias, erf-GELU,
+    // GELU' * aux, gate, DropPath, residual; residual / aux rows are read directly, 64 contiguous bytes
+    // per thread), bf16 pack, 16-byte stores into this warp's 32x32 64B-swizzled box, one TMA store per
+    // box and output tensor.  fp32 / atomic outputs (wgrad, tiny fp32 tails) store straight from registers.
     const int ew = warp - 2;
-    const int q = warp & 3;    // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;  // which half of the BN columns
-    float* st = staging + ew * (32 * 32);
+    const int q = warp & 3;     // TMEM lane quadrant this warp may access
+    const int cgrp = ew >> 2;   // which quarter of the BN columns
+    constexpr int CPW = BN / 128;  // 32-column chunks per warp
+    uint8_t* box = reinterpret_cast<uint8_t*>(staging) + ew * 2048;  // 32 rows x 64 B
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     const float scale = p.scale ? __ldg(p.scale) : 1.0f;
@@ -195,228 +199,125 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bf16* __restrict__ aux = p.aux;
     bf16* __restrict__ preact = p.preact;
     const float* __restrict__ row_scale = p.row_scale;
-    const int ldc = static_cast<int>(p.ldc), ldr = static_cast<int>(p.ldr), ldaux = static_cast<int>(p.ldaux),
-              ldp = static_cast<int>(p.ldp);
-    const int act = p.act, out_mode = p.out_mode;
-    const int rsub = lane >> 3, cj = lane & 7;
-    constexpr int CHUNKS = BN / 64;  // 32-column chunks per warp
+    const int act = p.act, out_mode = p.out_mode, use_tma = p.tma_store;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       const int tile = unit % (p.tiles_m * p.tiles_n);
       const int m0 = (tile / p.tiles_n) * GEMM_BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int ncols = min(BN, p.N - n0);
-      const long long row0 = static_cast<long long>(m0) + q * 32;  // first row of this warp
-      const int rows_left = p.M - static_cast<int>(row0);           // rows of this warp inside M
-      // DropPath / per-sample scale: a warp's 32 rows span at most two samples (rows_per_scale >= 32)
-      float rs_lo = scale, rs_hi = scale;
-      int rs_split = 1 << 30;
-      if (row_scale) {
-        const int s0 = static_cast<int>(row0 / p.rows_per_scale);
-        rs_split = (s0 + 1) * p.rows_per_scale - static_cast<int>(row0);
-        rs_lo = scale * __ldg(row_scale + s0);
-        const long long last = row0 + 31 < p.M ? row0 + 31 : p.M - 1;
-        rs_hi = scale * __ldg(row_scale + static_cast<int>(last / p.rows_per_scale));
-      }
-      bf16* c16 = reinterpret_cast<bf16*>(p.c) + row0 * p.ldc + n0;
-      float* c32 = reinterpret_cast<float*>(p.c) + row0 * p.ldc + n0;
-      const bf16* res_t = residual ? residual + row0 * p.ldr + n0 : nullptr;
-      const bf16* aux_t = aux ? aux + row0 * p.ldaux + n0 : nullptr;
-      bf16* pre_t = preact ? preact + row0 * p.ldp + n0 : nullptr;
+      const long long row = static_cast<long long>(m0) + q * 32 + lane;  // this thread's output row
+      const bool row_ok = row < p.M;
+      float sc = scale;  // gate alpha x DropPath scale of this row's sample
+      if (row_scale && row_ok) sc *= __ldg(row_scale + static_cast<int>(row / p.rows_per_scale));
+      const bf16* res_r = residual ? residual + row * p.ldr + n0 : nullptr;
+      const bf16* aux_r = aux ? aux + row * p.ldaux + n0 : nullptr;
 
       mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
       tc_fence_after();
-      if (p.tma_store) {
-        // ---- thread = accumulator row: bias / GELU / scales on registers, bf16 pack, 16-byte stores into
-        //      this warp's 32x64 128B-swizzled box, one TMA store per box (and per output tensor) ----
-        uint8_t* box = reinterpret_cast<uint8_t*>(st);  // 4 KB, 1024-byte aligned
-        const float sc = lane < rs_split ? rs_lo : rs_hi;
-        constexpr int BOXES = BN / 128;  // 64-column boxes per warp
-        const int passes = preact ? 2 : 1;
-        for (int pass = 0; pass < passes; ++pass) {
-          const bool write_pre = preact && pass == 0;
+      const int passes = preact ? 2 : 1;
+      for (int pass = 0; pass < passes; ++pass) {
+        const bool write_pre = preact && pass == 0;
 #pragma unroll 1
-          for (int bx = 0; bx < BOXES; ++bx) {
-            const int cb = (half * BOXES + bx) * 64;  // first column of the box inside the tile
-            if (cb < ncols) {
-              if (lane == 0) tma_store_wait_read();  // previous store has finished reading the box
-              __syncwarp();
+        for (int i = 0; i < CPW; ++i) {
+          const int c0 = (cgrp * CPW + i) * 32;
+          if (c0 >= ncols) break;
+          uint4 rv[4], av[4];
+          if (res_r && !write_pre) {
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = cb + cc * 32;
-                // residual / GELU'-operand rows are read straight in the accumulator layout (one row per
-                // thread, 64 contiguous bytes per 32-column chunk), issued before the TMEM load completes
-                uint4 rv[4], av[4];
-                const bool row_ok = lane < rows_left;
-                if (res_t && !write_pre) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    rv[j] = (row_ok && c0 + j * 8 < ncols)
-                                ? *reinterpret_cast<const uint4*>(res_t + static_cast<long long>(lane) * ldr + c0 + j * 8)
-                                : make_uint4(0u, 0u, 0u, 0u);
-                }
-                if (act == 2) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    av[j] = (row_ok && c0 + j * 8 < ncols)
-                                ? *reinterpret_cast<const uint4*>(aux_t + static_cast<long long>(lane) * ldaux + c0 + j * 8)
-                                : make_uint4(0u, 0u, 0u, 0u);
-                }
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {  // 16-byte chunk = 8 columns
-                  float x[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[j * 8 + e]);
-                  if (bias) {
-                    const int col = n0 + c0 + j * 8;
-                    if (col < p.N) {
-                      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-                      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                    }
-                  }
-                  if (!write_pre) {
-                    if (act == 1) {
-#pragma unroll
-                      for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
-                    } else if (act == 2) {
-                      const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[j]);
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const float2 f = unpack_bf16(au[e]);
-                        x[2 * e] *= gelu_erf_grad(f.x);
-                        x[2 * e + 1] *= gelu_erf_grad(f.y);
-                      }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] *= sc;
-                    if (res_t) {
-                      const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[j]);
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const float2 f = unpack_bf16(ru[e]);
-                        x[2 * e] += f.x;
-                        x[2 * e + 1] += f.y;
-                      }
-                    }
-                  }
-                  uint4 o;
-                  o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
-                  o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
-                  const int chunk = cc * 4 + j;
-                  *reinterpret_cast<uint4*>(box + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
-                }
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(write_pre ? &tmP : &tmC, box, n0 + cb, m0 + q * 32);
-                tma_store_commit();
-              }
-            }
+            for (int j = 0; j < 4; ++j)
+              rv[j] = (row_ok && c0 + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(res_r + c0 + j * 8)
+                                                     : make_uint4(0u, 0u, 0u, 0u);
           }
-        }
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        acc_phase ^= (1u << acc);
-        acc ^= 1;
-        continue;
-      }
-#pragma unroll 1
-      for (int i = 0; i < CHUNKS; ++i) {
-        const int c0 = (half * CHUNKS + i) * 32;
-        const bool last_chunk = (i == CHUNKS - 1) || (c0 + 32 >= ncols);
-        if (c0 < ncols) {
+          if (act == 2 && !write_pre) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              av[j] = (row_ok && c0 + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(aux_r + c0 + j * 8)
+                                                     : make_uint4(0u, 0u, 0u, 0u);
+          }
           uint32_t r[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
           tmem_ld_wait();
-          if (last_chunk) {  // this warp's last TMEM read of the accumulator: hand it back early
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (use_tma) {
+            if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
+            __syncwarp();
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            reinterpret_cast<float4*>(st)[lane * 8 + (j ^ (lane & 7))] = v;
-          }
-          __syncwarp();
-          const int col = c0 + cj * 4;
-          const bool cvalid = col < ncols;
-          float4 v[8];
+          for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte bf16 chunk
+            float x[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            v[it] = reinterpret_cast<const float4*>(st)[rr * 8 + (cj ^ (rr & 7))];
-          }
-          __syncwarp();  // staging may be overwritten by the next chunk from here on
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias && cvalid) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
-          uint2 rres[8], raux[8];
-          if (res_t) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              rres[it] = (cvalid && rr < rows_left) ? *reinterpret_cast<const uint2*>(res_t + rr * ldr + col)
-                                                    : make_uint2(0u, 0u);
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[j * 8 + e]);
+            const int col = c0 + j * 8;  // column inside the tile
+            const bool col_ok = col < ncols;
+            if (bias && col_ok) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
             }
-          }
-          if (act == 2) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rsub;
-              raux[it] = (cvalid && rr < rows_left) ? *reinterpret_cast<const uint2*>(aux_t + rr * ldaux + col)
-                                                    : make_uint2(0u, 0u);
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            if (cvalid && rr < rows_left) {
-              float x[4] = {v[it].x + b4.x, v[it].y + b4.y, v[it].z + b4.z, v[it].w + b4.w};
-              if (pre_t)
-                *reinterpret_cast<uint2*>(pre_t + rr * ldp + col) =
-                    make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
+            if (!write_pre) {
               if (act == 1) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = gelu_erf(x[e]);
+                for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
               } else if (act == 2) {
-                const float2 a0 = unpack_bf16(raux[it].x), a1 = unpack_bf16(raux[it].y);
-                x[0] *= gelu_erf_grad(a0.x); x[1] *= gelu_erf_grad(a0.y);
-                x[2] *= gelu_erf_grad(a1.x); x[3] *= gelu_erf_grad(a1.y);
-              }
-              const float sc = rr < rs_split ? rs_lo : rs_hi;
+                const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[j]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] *= sc;
-              if (res_t) {
-                const float2 a0 = unpack_bf16(rres[it].x), a1 = unpack_bf16(rres[it].y);
-                x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16(au[e]);
+                  x[2 * e] *= gelu_erf_grad(f.x);
+                  x[2 * e + 1] *= gelu_erf_grad(f.y);
+                }
               }
-              if (out_mode == 0) {
-                *reinterpret_cast<uint2*>(c16 + rr * ldc + col) =
-                    make_uint2(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]));
-              } else if (out_mode == 1) {
-                *reinterpret_cast<float4*>(c32 + rr * ldc + col) = make_float4(x[0], x[1], x[2], x[3]);
-              } else {
-                float* dst = c32 + rr * ldc + col;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) atomicAdd(dst + e, x[e]);
+              for (int e = 0; e < 8; ++e) x[e] *= sc;
+              if (res_r) {
+                const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16(ru[e]);
+                  x[2 * e] += f.x;
+                  x[2 * e + 1] += f.y;
+                }
+              }
+            }
+            if (out_mode == 0 || write_pre) {
+              uint4 o;
+              o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+              o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+              if (use_tma) {
+                *reinterpret_cast<uint4*>(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+              } else if (row_ok && col_ok) {  // pitch not TMA-addressable: direct 16-byte row stores
+                bf16* dst = write_pre ? preact + row * p.ldp + n0 + col
+                                      : reinterpret_cast<bf16*>(p.c) + row * p.ldc + n0 + col;
+                *reinterpret_cast<uint4*>(dst) = o;
+              }
+            } else if (row_ok && col_ok) {
+              float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + n0 + col;
+              if (out_mode == 1) {
+                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              } else {  // split-K wgrad: 16-byte vector reductions (red.global.add.v4.f32)
+                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(x[0], x[1], x[2], x[3]));
+                atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(x[4], x[5], x[6], x[7]));
               }
             }
           }
-        } else if (i == 0) {
-          // nothing to read for this warp (narrow last tile): still release the accumulator once
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (use_tma) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(write_pre ? &tmP : &tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
         }
       }
+      // every TMEM read of this accumulator by this warp has completed (tmem_ld_wait): hand it back
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc_phase ^= (1u << acc);
       acc ^= 1;
     }
-    if (p.tma_store && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
+    if (use_tma && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -451,7 +352,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map: dim0 = contiguous dimension (inner), dim1 = rows; 128B swizzle.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
-                      uint64_t row_pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+                      uint64_t row_pitch_elems, uint32_t box_inner, uint32_t box_outer,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   FIBER_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   FIBER_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16B aligned");
@@ -462,7 +364,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FIBER_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return 0;
@@ -488,7 +390,6 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a != nullptr, "null args");
   FIBER_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "bad GEMM shape %d x %d x %d", a->m, a->n, a->k);
   FIBER_CHECK(a->a_major == a->b_major, "mixed operand majors are not supported");
-  FIBER_CHECK(a->n % 4 == 0, "N must be a multiple of 4 (got %d)", a->n);
   FIBER_CHECK(a->out_mode >= 0 && a->out_mode <= 2, "bad out_mode");
   FIBER_CHECK(a->act != 2 || a->aux != nullptr, "act=2 (GELU grad) needs aux");
   const int mn = a->a_major;
@@ -537,19 +438,22 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   // and the fused operands are 16-byte addressable; fp32 / atomic outputs use the transposing epilogue
   CUtensorMap tc = ta, tp = ta;
   p.tma_store = 0;
-  static const int tma_mode = [] {  // FIBER_TMA_STORE=0 never, 1 only without residual/aux, 2 (default) always
+  static const int tma_mode = [] {  // FIBER_TMA_STORE=0: direct row stores instead of TMA stores (debug)
     const char* e = getenv("FIBER_TMA_STORE");
     return e ? atoi(e) : 2;
   }();
-  if (tma_mode > 0 && (tma_mode > 1 || (a->residual == nullptr && a->act != 2)) &&
-      a->out_mode == 0 && (a->ldc * 2) % 16 == 0 &&
-      (a->residual == nullptr || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0)) &&
-      (a->act != 2 || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)) &&
-      (reinterpret_cast<uintptr_t>(a->c) & 15) == 0 &&
-      (a->preact == nullptr || ((a->ldp * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0)) &&
-      (a->row_scale == nullptr || p.rows_per_scale >= 32) && a->n % 8 == 0) {
-    if (make_tmap_bf16_2d(&tc, a->c, a->n, a->m, a->ldc, 64, 32)) return -1;
-    if (a->preact && make_tmap_bf16_2d(&tp, a->preact, a->n, a->m, a->ldp, 64, 32)) return -1;
+  FIBER_CHECK(a->n % 8 == 0, "N must be a multiple of 8 (got %d)", a->n);
+  FIBER_CHECK(a->residual == nullptr || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0),
+              "residual rows must be 16-byte aligned");
+  FIBER_CHECK(a->act != 2 || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0),
+              "aux rows must be 16-byte aligned");
+  FIBER_CHECK((a->ldc * (a->out_mode == 0 ? 2 : 4)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->c) & 15) == 0,
+              "output rows must be 16-byte aligned");
+  FIBER_CHECK(a->preact == nullptr || ((a->ldp * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->preact) & 15) == 0),
+              "preact rows must be 16-byte aligned");
+  if (tma_mode > 0 && a->out_mode == 0) {
+    if (make_tmap_bf16_2d(&tc, a->c, a->n, a->m, a->ldc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+    if (a->preact && make_tmap_bf16_2d(&tp, a->preact, a->n, a->m, a->ldp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
     p.tma_store = 1;
   }
   const int units = tiles * p.splits;

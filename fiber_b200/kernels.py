@@ -15,6 +15,10 @@ F32 = torch.float32
 ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 
+# Optional in-situ profiling (bench.py): when a list is installed here every GEMM launch is bracketed
+# by CUDA events on the launching stream and (class key, flops, algorithmic bytes, start, stop) recorded.
+GEMM_PROFILE = None
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -86,7 +90,19 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
     args.act = act
     args.out_mode = out_mode
     args.splits = splits
+    if GEMM_PROFILE is None:
+        _lib.check(_lib.load().fiber_gemm(C.byref(args), _stream()), "gemm")
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.check(_lib.load().fiber_gemm(C.byref(args), _stream()), "gemm")
+    e1.record()
+    esz = 2 if out.dtype == BF16 else 4
+    nbytes = 2 * (m * k + n * k) + esz * m * n + 2 * m * n * sum(t is not None for t in (residual, aux, preact))
+    epi = "+".join(x for x, on in (("bias", bias is not None), ("gelu", act == ACT_GELU), ("gelu_grad", act == ACT_GELU_GRAD),
+                                   ("preact", preact is not None), ("res", residual is not None),
+                                   ("wgrad", mn_major)) if on) or "plain"
+    GEMM_PROFILE.append(((m, n, k, epi), 2.0 * m * n * k, nbytes, e0, e1))
     return out
 
 
