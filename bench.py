@@ -216,8 +216,12 @@ def run_ours(args):
     ops.set_dropout_seed(1234 + rank)
     step_model = model
     if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
-                                                               gradient_as_bucket_view=True)
+        # the set of grad-less parameters is fixed per task mix => static graph
+        ddp_kw = dict(static_graph=True) if os.environ.get("FIBER_DDP_STATIC", "1") == "1" else \
+            dict(find_unused_parameters=True)
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                               bucket_cap_mb=int(os.environ.get("FIBER_DDP_BUCKET_MB", "100")),
+                                                               **ddp_kw)
     host = pin(synth.synth_batch(B, R, L, seed=1234 + rank))
     h2d = batch_bytes(host)
 
@@ -264,7 +268,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_e2e, _, last_loss = timed(args.steps, True)
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
-    gemm_stats = profile_gemms(step, dev_batch) if rank == 0 else None
+    gemm_stats = profile_gemms(step, dev_batch)  # every rank runs it: the step contains DDP collectives
 
     if rank != 0:
         return
