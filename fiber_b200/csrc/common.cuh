@@ -195,27 +195,45 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn, i
 }
 
 // ---- misc math / memory --------------------------------------------------------------------
-// erf(|x|) by Abramowitz & Stegun 7.1.28 (|error| <= 3e-7, one reciprocal, no branches):
-//   erf(x) = 1 - 1 / (1 + a1 x + ... + a6 x^6)^16,  x >= 0
-__device__ __forceinline__ float erf_pos(float ax) {
-  float t = fmaf(ax, 0.0000430638f, 0.0002765672f);
-  t = fmaf(ax, t, 0.0001520143f);
-  t = fmaf(ax, t, 0.0092705272f);
-  t = fmaf(ax, t, 0.0422820123f);
-  t = fmaf(ax, t, 0.0705230784f);
+// Exact (erf-form) GELU as timm's nn.GELU and HF ACT2FN["gelu"] compute it, with
+// erf(u) = 1 - 1 / (1 + a1 u + ... + a6 u^6)^16, u >= 0   (Abramowitz & Stegun 7.1.28, |error| <= 3e-7).
+// u = |x| / sqrt(2) is folded into the coefficients; one MUFU reciprocal, no branches.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// returns r = 1 - erf(|x| / sqrt 2) = erfc(|x| / sqrt 2)  in (0, 1]
+__device__ __forceinline__ float erfc_abs_scaled(float ax) {
+  constexpr float c1 = 0.0705230784f * 0.70710678118654752f;
+  constexpr float c2 = 0.0422820123f * 0.5f;
+  constexpr float c3 = 0.0092705272f * 0.35355339059327376f;
+  constexpr float c4 = 0.0001520143f * 0.25f;
+  constexpr float c5 = 0.0002765672f * 0.17677669529663688f;
+  constexpr float c6 = 0.0000430638f * 0.125f;
+  float t = fmaf(ax, c6, c5);
+  t = fmaf(ax, t, c4);
+  t = fmaf(ax, t, c3);
+  t = fmaf(ax, t, c2);
+  t = fmaf(ax, t, c1);
   t = fmaf(ax, t, 1.0f);
   t *= t; t *= t; t *= t; t *= t;
-  return 1.0f - __fdividef(1.0f, t);
+  return rcp_approx(t);
 }
-// exact (erf-form) GELU, as timm's nn.GELU and HF ACT2FN["gelu"] compute it
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = 0.5 (x + |x| (1 - r))
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float e = copysignf(erf_pos(fabsf(x) * 0.70710678118654752440f), x);
-  return 0.5f * x * (1.0f + e);
+  const float ax = fabsf(x);
+  const float r = erfc_abs_scaled(ax);
+  const float m = fmaf(-ax, r, ax);
+  return fmaf(0.5f, x, 0.5f * m);
 }
+// gelu'(x) = Phi(x) + x phi(x),  Phi(x) = 0.5 + 0.5 sign(x) (1 - r),  phi(x) = exp(-x^2 / 2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float e = copysignf(erf_pos(fabsf(x) * 0.70710678118654752440f), x);
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return 0.5f * (1.0f + e) + x * pdf;
+  const float ax = fabsf(x);
+  const float r = erfc_abs_scaled(ax);
+  const float cdf = fmaf(0.5f, copysignf(1.0f - r, x), 0.5f);
+  const float pdf = 0.39894228040143267794f * exp2f(x * x * -0.72134752044448170368f);
+  return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
