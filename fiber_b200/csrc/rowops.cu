@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "../../include/fiber_b200.h"
 
+#include <cstdlib>
+
 namespace fiber {
 
 void count_launch(int n = 1);
@@ -341,9 +343,10 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
     FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
                 "bad PatchMerging LayerNorm geometry");
   }
+  // unroll depths picked from tools/bench_ln.py on B200
   if (p.C <= 128) return ln_launch<1, 16, 2>(p, bwd, stream);
-  if (p.C <= 256) return ln_launch<1, 32, 2>(p, bwd, stream);
-  if (p.C <= 512) return ln_launch<2, 32, 2>(p, bwd, stream);
+  if (p.C <= 256) return bwd ? ln_launch<1, 32, 4>(p, true, stream) : ln_launch<1, 32, 2>(p, false, stream);
+  if (p.C <= 512) return ln_launch<2, 32, 1>(p, bwd, stream);
   if (p.C <= 768) return ln_launch<3, 32, 1>(p, bwd, stream);
   if (p.C <= 1024) return ln_launch<4, 32, 1>(p, bwd, stream);
   return ln_launch<8, 32, 1>(p, bwd, stream);
