@@ -5,6 +5,8 @@ Same constructor argument (the sacred `_config` dict), sub-module names, state_d
 ITM / ITC / MLM / VQA objectives sit on top unchanged; the fused backbone underneath runs on the
 sm_100a kernels of this package (no eager or CPU fallback: calling it without the CUDA library or
 with CPU tensors raises)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -101,6 +103,7 @@ class FIBERTransformerSS(LightningModule):
             self.vqa_classifier.apply(objectives.init_weights)
         fiber_utils.set_metrics(self)
         self.current_tasks = list()
+        self.merge_mlm_itm_pass = os.environ.get("FIBER_MERGE_PASSES", "1") != "0"
         if config["load_path"] != "" and config["test_only"]:
             self._load(config["load_path"])
 
@@ -203,13 +206,20 @@ class FIBERTransformerSS(LightningModule):
         if len(self.current_tasks) == 0:
             ret.update(self.infer(batch))
             return ret
-        if "mlm" in self.current_tasks:
+        tasks = self.current_tasks
+        # MLM and hard-negative ITM share the fused backbone on independent samples: one 4B pass
+        # instead of a B pass and a 3B pass (same losses; FIBER_MERGE_PASSES=0 restores the
+        # reference's call-by-call order of fiber_module.py:437-451)
+        merge = self.merge_mlm_itm_pass and all(t in tasks for t in ("mlm", "itc", "itm"))
+        if "mlm" in tasks and not merge:
             ret.update(objectives.compute_mlm(self, batch))
-        if "itc" in self.current_tasks:
+        if "itc" in tasks:
             ret_itc, image_neg, text_neg, text_mask_neg = objectives.compute_itc(self, batch)
             ret.update(ret_itc)
-        if "itm" in self.current_tasks:
-            if "itc" in self.current_tasks:
+        if merge:
+            ret.update(objectives.compute_mlm_itm_hardneg_merged(self, batch, image_neg, text_neg, text_mask_neg))
+        elif "itm" in tasks:
+            if "itc" in tasks:
                 ret.update(objectives.compute_itm_hardneg(self, batch, image_neg, text_neg, text_mask_neg))
             else:
                 ret.update(objectives.compute_itm(self, batch))

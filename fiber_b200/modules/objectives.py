@@ -77,6 +77,36 @@ def compute_itm_hardneg(pl_module, batch, image_neg, text_neg, text_mask_neg):
     return _itm_tail(pl_module, infer, itm_labels)
 
 
+def compute_mlm_itm_hardneg_merged(pl_module, batch, image_neg, text_neg, text_mask_neg):
+    """compute_mlm + compute_itm_hardneg through ONE backbone pass of 4B samples.
+
+    The reference runs infer() on the B masked-text pairs (objectives.py:18) and, separately, on the
+    3B ITM pairs (:85-97).  Samples are independent through the whole backbone, so concatenating the
+    two batches gives the same features; on the GPU it means a third fewer (and larger) kernel launches
+    and one gradient accumulation less per parameter.  Returns the union of both functions' dicts."""
+    B = len(batch["text"])
+    img = batch["image"][0]
+    merged = {k: v for k, v in batch.items()}
+    merged["image"] = [torch.cat([img, img, img, image_neg], dim=0)]
+    merged["text_ids"] = torch.cat([batch["text_ids_mlm"], batch["text_ids"], text_neg, batch["text_ids"]], dim=0)
+    merged["text_masks"] = torch.cat([batch["text_masks"], batch["text_masks"], text_mask_neg, batch["text_masks"]], dim=0)
+    merged["text_labels"] = torch.cat([batch["text_labels_mlm"]] + [batch["text_labels"]] * 3, dim=0)
+    infer = pl_module.infer(merged, mask_text=False, mask_image=False)
+    # ---- MLM on the first B samples (objectives.py:19-41) ----
+    mlm_logits = pl_module.mlm_score(infer["text_feats"][:B])
+    mlm_labels = batch["text_labels_mlm"]
+    mlm_loss = F.cross_entropy(mlm_logits.view(-1, pl_module.hparams.config["vocab_size"]).float(),
+                               mlm_labels.view(-1), ignore_index=-100)
+    ret = {"mlm_loss": mlm_loss, "mlm_logits": mlm_logits, "mlm_labels": mlm_labels, "mlm_ids": batch["text_ids_mlm"]}
+    phase = _phase(pl_module)
+    pl_module.log(f"mlm/{phase}/loss", getattr(pl_module, f"{phase}_mlm_loss")(mlm_loss))
+    pl_module.log(f"mlm/{phase}/accuracy", getattr(pl_module, f"{phase}_mlm_accuracy")(mlm_logits, mlm_labels))
+    # ---- ITM on the remaining 3B samples (objectives.py:99-116) ----
+    itm_labels = torch.cat([torch.ones(B), torch.zeros(2 * B)]).to(pl_module.device)
+    ret.update(_itm_tail(pl_module, {"cls_feats": infer["cls_feats"][B:]}, itm_labels))
+    return ret
+
+
 def compute_itc(pl_module, batch):
     with torch.no_grad():
         pl_module.temp.clamp_(0.001, 1.0)

@@ -156,3 +156,22 @@ def test_training_step_with_dropout_runs(cuda_dev, m224):
     n_grad = sum(1 for p in model.parameters() if p.grad is not None)
     assert n_grad > 600
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_merged_mlm_itm_pass_equals_separate_passes(cuda_dev):
+    """The 4B-sample merged MLM+ITM pass gives the losses of the reference's separate passes."""
+    from fiber_b200.modules import fiber_utils
+    model, cfg, sd = _build(["itm", "mlm", "itc"], 224, 40, cuda_dev)
+    model.eval()  # deterministic: no dropout / DropPath; ITC queue is not updated in eval mode
+    fiber_utils.set_task(model)
+    batch = _to(synth.synth_batch(4, 224, 40, seed=99), cuda_dev)
+    outs = []
+    for merged in (True, False):
+        model.merge_mlm_itm_pass = merged
+        torch.manual_seed(5)  # same hard-negative draws
+        with torch.no_grad():
+            outs.append(model(batch))
+    a, b = outs
+    for k in ("mlm_loss", "itm_loss", "itc_loss"):
+        assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(1.0, abs(float(b[k]))), k
+    assert torch.equal(a["mlm_logits"], b["mlm_logits"]) and torch.equal(a["itm_logits"], b["itm_logits"])
