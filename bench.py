@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_PAIR = 1636.23e9  # fwd+bwd, config 1 (FlopCounterMode over the reference)
 METRIC = "image-text pairs/sec/GPU FIBER-Base 384px fwd+bwd at 1/2/4/8 B200"
+WORKLOAD = "FIBER-Base coarse pretrain step ITM+ITC+MLM (BASELINE configs[1]) 384px/40tok fwd+bwd"
 
 
 def config(tasks, image_size=384, max_text_len=40):
@@ -75,6 +76,27 @@ class ClockSampler:
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def make_batch(B, image_size, L, seed=1234, vocab=50265):
+    """Synthetic batch with the schema of the reference's collate (datasets/base_dataset.py:172-245),
+    SURVEY.md §8(d): N(0,1) images; <s> ... </s> token ids with every other row padded; 15 % <mask>."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    batch = {"image": [torch.randn(B, 3, image_size, image_size, generator=g)]}
+    ids = torch.randint(3, vocab - 1, (B, L), generator=g)
+    masks = torch.ones(B, L, dtype=torch.long)
+    lens = torch.randint(8, L + 1, (B,), generator=g)
+    for b in range(B):
+        n = int(lens[b]) if b % 2 == 1 else L
+        ids[b, 0], ids[b, n - 1] = 0, 2
+        ids[b, n:] = 1
+        masks[b, n:] = 0
+    pick = (torch.rand(B, L, generator=g) < 0.15) & (ids > 2)
+    pick[:, 1] = True
+    batch.update(text_ids=ids, text_masks=masks, text_labels=torch.full((B, L), -100),
+                 text_ids_mlm=torch.where(pick, torch.full_like(ids, vocab - 1), ids),
+                 text_labels_mlm=torch.where(pick, ids, torch.full_like(ids, -100)), text=["synthetic caption"] * B)
+    return batch
 
 
 def to_device(batch, dev, non_blocking=True):
@@ -148,15 +170,17 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = args.cpu_batch
+    B = args.cpu_batch if args.steps <= 10 else 1  # bounded sample: keep K steps within a few minutes
     sec = cpu_step_seconds(B, args.image_size, args.text_len, args.steps, min(args.warmup, 1), threads)
     v = B / sec
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FIBER-Base coarse pretrain step ITM+ITC+MLM 384px/40tok fwd+bwd, oracle port on host "
-                               "cores (sample: B=%d pairs per step)" % B},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": 64, "image_size": args.image_size, "text_len": args.text_len,
+                   "reference_arm": "the reference's algorithm (oracle port; the reference package itself needs "
+                                    "pytorch_lightning/timm/sacred and cannot run on the GPU box) on all host cores, "
+                                    "bounded sample of B=%d pairs per step" % B},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": "B=%d pairs/step, %d timed steps, fp32, torch %d threads" % (B, args.steps, threads)},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -191,7 +215,6 @@ def profile_gemms(step, batch):
 
 
 def run_ours(args):
-    from oracle import synth  # synthetic batch recipe only (data, not compute)
     from fiber_b200 import lib, ops
     from fiber_b200.modules import FIBERTransformerSS, fiber_utils
 
@@ -222,7 +245,7 @@ def run_ours(args):
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                                bucket_cap_mb=int(os.environ.get("FIBER_DDP_BUCKET_MB", "100")),
                                                                **ddp_kw)
-    host = pin(synth.synth_batch(B, R, L, seed=1234 + rank))
+    host = pin(make_batch(B, R, L, seed=1234 + rank))
     h2d = batch_bytes(host)
 
     # the heads on top of infer() (callers, plain torch fp32 modules) may use TF32 tensor cores
@@ -287,8 +310,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "FIBER-Base coarse pretrain step ITM+ITC+MLM (BASELINE configs[1]) 384px/40tok fwd+bwd",
-                   "per_gpu_batch": B, "global_batch": B * world, "image_size": R, "text_len": L,
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image_size": R, "text_len": L,
                    "parallelism": "dp%d" % world, "l2": "per-step activations (>10 GB) exceed the 126 MB L2",
                    "last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1)},
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
