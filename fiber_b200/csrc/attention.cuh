@@ -64,6 +64,13 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr,
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+// exp(x) as one FMUL + one MUFU.EX2 (no denormal range fix-up: results below 2^-126 flush to zero,
+// which is what a softmax probability that small rounds to in bf16 anyway).
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 // Counter-based keep decision for attention-probability dropout (same in forward and backward).
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
   unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;

@@ -10,6 +10,7 @@
 // (shared-memory atomics -> one global atomic per table entry per CTA).
 #include "attention.cuh"
 #include "../../include/fiber_b200.h"
+#include <cstdlib>
 
 namespace fiber {
 
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
                   } else {
                     v += sMask[jl];
                   }
-                  float pr = (j < Lk) ? __expf(v - ((e >> 1) ? lse1 : lse0)) : 0.f;
+                  float pr = (j < Lk) ? fast_exp(v - ((e >> 1) ? lse1 : lse0)) : 0.f;
                   float dpv = dp[nt][e];
                   float pd = pr;  // P after dropout (feeds dV)
                   if (p.drop_p > 0.f) {
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const A
               const int ridq = hi ? rid1 : rid0, ridj = odd ? ridj1 : ridj0;
               float v = s[nt][e] * p.scale + sTbl[(hi ? aq1 : aq0) - (odd ? bj1 : bj0)];
               if (has_mask && ridq != ridj) v += -100.0f;
-              const float pr = (j < N) ? __expf(v - (hi ? lse1 : lse0)) : 0.f;
+              const float pr = (j < N) ? fast_exp(v - (hi ? lse1 : lse0)) : 0.f;
               const float ds = pr * (dp[nt][e] - (hi ? D1 : D0));
               s[nt][e] = pr;
               dp[nt][e] = ds;
@@ -745,13 +746,22 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
+bool win_attn_supported(const AttnParams& p, int hd);
+int launch_win_bwd2(const AttnParams& p, float* D, cudaStream_t stream);
+// A/B switch for the round-1 measurements only: FIBER_WINATTN_V1=1 selects the first-generation kernels.
+bool win_attn_use_v1() {
+  static const bool v1 = [] { const char* e = getenv("FIBER_WINATTN_V1"); return e && e[0] == '1'; }();
+  return v1;
+}
+
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
   FIBER_CHECK(p.d_o && p.dq && p.dk && p.dv && p.lse && p.o, "attention backward needs o, lse, d_o, dq, dk, dv");
   if (p.mode == 1) {
     FIBER_CHECK(hd == 32, "window attention uses head_dim 32");
     FIBER_CHECK(p.dbias_table != nullptr, "window backward needs dbias_table");
-    if (p.Lq <= BW_QROWS && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
+    if (win_attn_supported(p, hd) && d_scratch != nullptr)
+      return win_attn_use_v1() ? launch_win_bwd(p, d_scratch, stream) : launch_win_bwd2(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
   }
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);

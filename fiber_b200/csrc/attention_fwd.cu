@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float m_new = fmaxf(m_run[r], mx[r]);
-        corr[r] = __expf(m_run[r] - m_new);
+        corr[r] = fast_exp(m_run[r] - m_new);
         m_run[r] = m_new;
         l_run[r] *= corr[r];
       }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
       for (int nt = 0; nt < 6; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float pv = __expf(s[nt][e] - m_run[e >> 1]);
+          float pv = fast_exp(s[nt][e] - m_run[e >> 1]);
           l_run[e >> 1] += pv;
           if (p.drop_p > 0.f) {
             const int j = kc0 + sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2 + (e & 1);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(WF_NWARPS * 32, 2) win_attn_fwd_kernel(const A
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float m_new = fmaxf(m_run[r], mx[r]);
-        corr[r] = __expf(m_run[r] - m_new);
+        corr[r] = fast_exp(m_run[r] - m_new);
         m_run[r] = m_new;
         l_run[r] *= corr[r];
       }
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(WF_NWARPS * 32, 2) win_attn_fwd_kernel(const A
       for (int nt = 0; nt < 6; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = __expf(s[nt][e] - m_run[e >> 1]);
+          const float pv = fast_exp(s[nt][e] - m_run[e >> 1]);
           l_run[e >> 1] += pv;
           s[nt][e] = pv;
         }
@@ -490,9 +490,13 @@ int attn_check(const AttnParams& p, int hd) {
   return 0;
 }
 
+bool win_attn_supported(const AttnParams& p, int hd);
+int launch_win_fwd2(const AttnParams& p, cudaStream_t stream);
+bool win_attn_use_v1();
+
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
-  if (p.mode == 1 && hd == 32 && p.Lq <= WF_ROWS && p.drop_p == 0.f) return launch_win_fwd(p, stream);
+  if (win_attn_supported(p, hd)) return win_attn_use_v1() ? launch_win_fwd(p, stream) : launch_win_fwd2(p, stream);
   if (hd == 32) {
     if (p.Lq <= 48) return launch_fwd<32, 3>(p, stream);
     if (p.Lq <= 64) return launch_fwd<32, 4>(p, stream);

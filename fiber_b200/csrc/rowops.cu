@@ -355,33 +355,58 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // column sum (bias gradients):  out[n] (+)= scale * sum_m rs[m / rps] * x[m, n]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* x, long long ld, long long M, int N, float* out,
-                                                     const float* scale, const float* row_scale, int rps,
-                                                     long long rows_per_block) {
-  __shared__ float s_part[8][256];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = (blockIdx.x * 32 + tx) * 8;
+// One block covers `cw` 16-byte vector columns (all of a row when N <= 2048) and 256 / cw rows per pass, so
+// every thread issues coalesced 16-byte loads whatever N is; four independent loads are in flight per thread.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ld, long long M, int N,
+                                                     float* out, const float* scale, const float* row_scale, int rps,
+                                                     long long rows_per_block, int cw) {
+  __shared__ float s_part[2048];
+  const int rpp = 256 / cw;                  // rows per pass
+  const int slot = threadIdx.x / cw, lc = threadIdx.x - slot * cw;
+  const int vcol = blockIdx.x * cw + lc;     // vector column of this thread
+  const bool active = slot < rpp && vcol * 8 < N;
   const long long r0 = blockIdx.y * rows_per_block;
   const long long r1 = min(r0 + rows_per_block, M);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (col < N) {
-    for (long long r = r0 + ty; r < r1; r += 8) {
-      float v[8];
-      load8(x + r * ld + col, v);
-      const float s = row_scale ? row_scale[r / rps] : 1.0f;
+  if (active) {
+    const bf16* xp = x + vcol * 8;
+    long long r = r0 + slot;
+    for (; r + 3LL * rpp < r1; r += 4LL * rpp) {
+      float v[4][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += v[e] * s;
+      for (int u = 0; u < 4; ++u) load8(xp + (r + static_cast<long long>(u) * rpp) * ld, v[u]);
+      if (row_scale) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float sc = row_scale[(r + static_cast<long long>(u) * rpp) / rps];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[u][e], sc, acc[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += (v[0][e] + v[1][e]) + (v[2][e] + v[3][e]);
+      }
+    }
+    for (; r < r1; r += rpp) {
+      float v[8];
+      load8(xp + r * ld, v);
+      const float sc = row_scale ? row_scale[r / rps] : 1.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], sc, acc[e]);
     }
   }
+  if (slot < rpp) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) s_part[ty][tx * 8 + e] = acc[e];
+    for (int e = 0; e < 8; ++e) s_part[slot * cw * 8 + lc * 8 + e] = acc[e];
+  }
   __syncthreads();
-  const int c = threadIdx.x;  // 256 columns of this block
-  float t = 0.f;
-#pragma unroll
-  for (int y = 0; y < 8; ++y) t += s_part[y][c];
-  const int gc = blockIdx.x * 256 + c;
-  if (gc < N) atomicAdd(out + gc, t * (scale ? *scale : 1.0f));
+  const float sc = scale ? *scale : 1.0f;
+  for (int c = threadIdx.x; c < cw * 8; c += 256) {
+    float t = 0.f;
+    for (int y = 0; y < rpp; ++y) t += s_part[y * cw * 8 + c];
+    const int gc = blockIdx.x * cw * 8 + c;
+    if (gc < N) atomicAdd(out + gc, t * sc);
+  }
 }
 
 // dot(a, b) -> *out += sum a[i]*b[i]   (2-D, row-major with independent leading dimensions)
@@ -595,13 +620,17 @@ static int ew_grid(long long work_items) {
 int colsum_dispatch(const bf16* x, long long ld, long long M, int N, float* out, const float* scale,
                     const float* row_scale, int rps, cudaStream_t stream) {
   FIBER_CHECK(N % 8 == 0 && M > 0, "colsum: N must be a multiple of 8");
-  const int gx = (N + 255) / 256;
-  long long gy = (2LL * num_sms() + gx - 1) / gx;
-  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+  const int nv = N / 8;
+  const int gx = (nv + 255) / 256;
+  const int cw = (nv + gx - 1) / gx;  // vector columns per block (<= 256)
+  const int rpp = 256 / cw;
+  long long gy = (4LL * num_sms() + gx - 1) / gx;
+  const long long min_rows = 8LL * rpp;  // at least two unrolled passes per block
+  if (gy > (M + min_rows - 1) / min_rows) gy = (M + min_rows - 1) / min_rows;
   if (gy < 1) gy = 1;
   const long long rpb = (M + gy - 1) / gy;
   colsum_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, stream>>>(x, ld, M, N, out, scale, row_scale,
-                                                                        rps > 0 ? rps : 1, rpb);
+                                                                        rps > 0 ? rps : 1, rpb, cw);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

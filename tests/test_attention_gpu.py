@@ -22,7 +22,8 @@ def _close(a, b, tol, name):
 
 
 @pytest.mark.parametrize("B,H,ws,shift,nh", [(2, 24, 12, 0, 2), (2, 24, 12, 6, 2), (3, 14, 7, 3, 4), (1, 12, 12, 0, 3),
-                                             (2, 96, 12, 6, 4), (1, 36, 18, 9, 2), (2, 18, 18, 0, 3)])
+                                             (2, 96, 12, 6, 4), (1, 36, 18, 9, 2), (2, 18, 18, 0, 3),
+                                             (8, 48, 12, 6, 8), (4, 28, 7, 0, 4), (2, 48, 12, 5, 2)])
 def test_window_attention_fwd_bwd(cuda_dev, B, H, ws, shift, nh):
     from fiber_b200 import kernels as K
     hd = 32
