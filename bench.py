@@ -207,7 +207,13 @@ def profile_gemms(step, batch):
         d[0] += 1; d[1] += fl; d[2] += nb; d[3] += e0.elapsed_time(e1)
     tot_ms = sum(d[3] for d in by.values())
     tot_fl = sum(d[1] for d in by.values())
-    top = sorted(by.items(), key=lambda kv: -kv[1][3])[:12]
+    ranked = sorted(by.items(), key=lambda kv: -kv[1][3])
+    dump = os.environ.get("FIBER_BENCH_DUMP")  # full per-shape table (tools / profiles), not part of the JSON line
+    if dump:
+        with open(dump, "w") as f:
+            for k, d in ranked:
+                f.write("%-44s n=%4d ms=%8.3f tflops=%7.1f gbs=%6.0f\n" % (str(k), d[0], d[3], d[1] / d[3] / 1e9, d[2] / d[3] / 1e6))
+    top = ranked[:12]
     return {"launches": len(rec), "ms": tot_ms, "tflops": tot_fl / tot_ms / 1e9,
             "gbs": sum(d[2] for d in by.values()) / tot_ms / 1e6,
             "top": [{"mnk_epi": list(k), "n": d[0], "ms": round(d[3], 3), "tflops": round(d[1] / d[3] / 1e9, 1),

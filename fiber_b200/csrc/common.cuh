@@ -169,6 +169,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -198,6 +209,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn, i
 // Exact (erf-form) GELU as timm's nn.GELU and HF ACT2FN["gelu"] compute it, with
 // erf(u) = 1 - 1 / (1 + a1 u + ... + a6 u^6)^16, u >= 0   (Abramowitz & Stegun 7.1.28, |error| <= 3e-7).
 // u = |x| / sqrt(2) is folded into the coefficients; one MUFU reciprocal, no branches.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -232,8 +248,117 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float ax = fabsf(x);
   const float r = erfc_abs_scaled(ax);
   const float cdf = fmaf(0.5f, copysignf(1.0f - r, x), 0.5f);
-  const float pdf = 0.39894228040143267794f * exp2f(x * x * -0.72134752044448170368f);
+  const float pdf = 0.39894228040143267794f * ex2_approx(x * x * -0.72134752044448170368f);
   return fmaf(x, pdf, cdf);
+}
+// ---- packed fp32x2 math (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+#define FIBER_PK2C(c) ::fiber::pk2((c), (c))
+// erfc(|x| / sqrt 2) on FOUR packed pairs in lockstep (same polynomial as erfc_abs_scaled).  The source is
+// written "vertically" — one Horner step across all four pairs before the next — so the dependent
+// FFMA2 / FMUL2 / MUFU chains of the pairs interleave instead of serialising on their latencies.
+__device__ __forceinline__ void erfc_abs_scaled2x4(const uint64_t (&ax)[4], uint64_t (&r)[4]) {
+  constexpr float c1 = 0.0705230784f * 0.70710678118654752f;
+  constexpr float c2 = 0.0422820123f * 0.5f;
+  constexpr float c3 = 0.0092705272f * 0.35355339059327376f;
+  constexpr float c4 = 0.0001520143f * 0.25f;
+  constexpr float c5 = 0.0002765672f * 0.17677669529663688f;
+  constexpr float c6 = 0.0000430638f * 0.125f;
+  uint64_t t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], FIBER_PK2C(c6), FIBER_PK2C(c5));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], t[i], FIBER_PK2C(c4));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], t[i], FIBER_PK2C(c3));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], t[i], FIBER_PK2C(c2));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], t[i], FIBER_PK2C(c1));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = fma2(ax[i], t[i], FIBER_PK2C(1.0f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = mul2(t[i], t[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t0, t1;
+    upk2(t[i], t0, t1);
+    r[i] = pk2(rcp_approx(t0), rcp_approx(t1));
+  }
+}
+// gelu on four packed pairs: 0.5 x + |x| (0.5 - 0.5 r)
+__device__ __forceinline__ void gelu_erf2x4(uint64_t (&x)[4]) {
+  uint64_t ax[4], r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0, x1;
+    upk2(x[i], x0, x1);
+    ax[i] = pk2(fabsf(x0), fabsf(x1));
+  }
+  erfc_abs_scaled2x4(ax, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma2(r[i], FIBER_PK2C(-0.5f), FIBER_PK2C(0.5f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = mul2(ax[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = fma2(x[i], FIBER_PK2C(0.5f), r[i]);
+}
+// g[i] *= gelu'(x[i]) on four packed pairs
+__device__ __forceinline__ void gelu_erf_grad_mul2x4(uint64_t (&g)[4], const uint64_t (&x)[4]) {
+  uint64_t ax[4], r[4], sh[4], e[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0, x1;
+    upk2(x[i], x0, x1);
+    ax[i] = pk2(fabsf(x0), fabsf(x1));
+    sh[i] = pk2(copysignf(0.5f, x0), copysignf(0.5f, x1));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(x[i], x[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(e[i], FIBER_PK2C(-0.72134752044448170368f));
+  erfc_abs_scaled2x4(ax, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float e0, e1;
+    upk2(e[i], e0, e1);
+    e[i] = pk2(ex2_approx(e0), ex2_approx(e1));  // exp(-x^2 / 2)
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma2(r[i], FIBER_PK2C(-1.0f), FIBER_PK2C(1.0f));   // 1 - r
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma2(sh[i], r[i], FIBER_PK2C(0.5f));               // Phi(x)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ax[i] = mul2(x[i], FIBER_PK2C(0.39894228040143267794f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma2(ax[i], e[i], r[i]);                           // Phi + x phi
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = mul2(g[i], r[i]);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

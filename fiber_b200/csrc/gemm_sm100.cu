@@ -58,6 +58,82 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
+// One 32-row x 32-column chunk of the TMA-store epilogue with every epilogue option fixed at compile time
+// (the generic runtime-flag loop below spends half of its issue slots on branches and predicates).
+// Preconditions (checked by the caller, warp-uniform): all 32 rows and all 32 columns are in range.
+//   ACT 0 none / 1 erf-GELU / 2 multiply by GELU'(aux);  BIAS: + bias[col];  SCALE: * sc;  RES: + residual
+template <int ACT, bool BIAS, bool SCALE, bool RES>
+__device__ __forceinline__ void epi_chunk_full(uint32_t taddr, uint8_t* box_row, int swz,
+                                               const float* __restrict__ bias_c, const bf16* __restrict__ res_c,
+                                               const bf16* __restrict__ aux_c, float sc) {
+  uint4 rv[4], av[4];
+  if (RES) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(res_c + j * 8);
+  }
+  if (ACT == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const uint4*>(aux_c + j * 8);
+  }
+  const uint64_t sc2 = pk2(sc, sc);
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t r[16];
+    tmem_ld16(taddr + hf * 16, r);
+    float4 bv[4];
+    if (BIAS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bias_c + hf * 16 + j * 4));
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint64_t xp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        xp[e] = pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+      if (BIAS) {
+        xp[0] = add2(xp[0], pk2(bv[2 * j].x, bv[2 * j].y)); xp[1] = add2(xp[1], pk2(bv[2 * j].z, bv[2 * j].w));
+        xp[2] = add2(xp[2], pk2(bv[2 * j + 1].x, bv[2 * j + 1].y));
+        xp[3] = add2(xp[3], pk2(bv[2 * j + 1].z, bv[2 * j + 1].w));
+      }
+      if (ACT == 1) gelu_erf2x4(xp);
+      if (ACT == 2) {
+        const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[hf * 2 + j]);
+        uint64_t hx[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(au[e]);
+          hx[e] = pk2(f.x, f.y);
+        }
+        gelu_erf_grad_mul2x4(xp, hx);
+      }
+      if (RES) {
+        const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[hf * 2 + j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(ru[e]);
+          xp[e] = SCALE ? fma2(xp[e], sc2, pk2(f.x, f.y)) : add2(xp[e], pk2(f.x, f.y));
+        }
+      } else if (SCALE) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xp[e] = mul2(xp[e], sc2);
+      }
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) upk2(xp[e], x[2 * e], x[2 * e + 1]);
+      uint4 o;
+      o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+      o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+      *reinterpret_cast<uint4*>(box_row + (((hf * 2 + j) ^ swz) << 4)) = o;
+    }
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 template <int BN, int MN_MAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -212,6 +288,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bf16* res_r = residual ? residual + row * p.ldr + n0 : nullptr;
       const bf16* aux_r = aux ? aux + row * p.ldaux + n0 : nullptr;
 
+      // operands the epilogue reads from HBM (64 B per chunk and thread): start them towards L2 while the
+      // MMAs of this tile are still running
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+          const int c0 = (cgrp * CPW + i) * 32;
+          if (c0 < ncols) {
+            if (res_r) prefetch_l2(res_r + c0);
+            if (aux_r) prefetch_l2(aux_r + c0);
+          }
+        }
+      }
+      // warp-uniform fast-path key of this tile: every row in range, bf16 output through the TMA-store box
+      const bool tile_fast = use_tma && (m0 + GEMM_BM <= p.M);
+      const bool scaled = p.scale != nullptr || row_scale != nullptr;
+
       mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
       tc_fence_after();
       const int passes = preact ? 2 : 1;
@@ -221,83 +313,130 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < CPW; ++i) {
           const int c0 = (cgrp * CPW + i) * 32;
           if (c0 >= ncols) break;
-          uint4 rv[4], av[4];
-          if (res_r && !write_pre) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              rv[j] = (row_ok && c0 + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(res_r + c0 + j * 8)
-                                                     : make_uint4(0u, 0u, 0u, 0u);
-          }
-          if (act == 2 && !write_pre) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              av[j] = (row_ok && c0 + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(aux_r + c0 + j * 8)
-                                                     : make_uint4(0u, 0u, 0u, 0u);
-          }
-          uint32_t r[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0, r);
-          tmem_ld_wait();
           if (use_tma) {
             if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
             __syncwarp();
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte bf16 chunk
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(r[j * 8 + e]);
-            const int col = c0 + j * 8;  // column inside the tile
-            const bool col_ok = col < ncols;
-            if (bias && col_ok) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+          if (tile_fast && c0 + 32 <= ncols) {
+            // compile-time specialised chunk bodies for the epilogues the FIBER path uses; anything else
+            // (and every ragged edge) takes the generic runtime-flag body below
+            const int eff_act = write_pre ? 0 : act;
+            const bool eff_res = res_r != nullptr && !write_pre;
+            const bool eff_scale = scaled && !write_pre;
+            const int key = eff_act | (bias ? 4 : 0) | (eff_scale ? 8 : 0) | (eff_res ? 16 : 0);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+            uint8_t* box_row = box + lane * 64;
+            const int swz = (lane >> 1) & 3;
+            const float* bias_c = bias + n0 + c0;
+            const bf16* res_c = res_r + c0;
+            const bf16* aux_c = aux_r + c0;
+            bool done = true;
+            switch (key) {
+              case 0:           epi_chunk_full<0, false, false, false>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 4:           epi_chunk_full<0, true, false, false>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 1 | 4:       epi_chunk_full<1, true, false, false>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 2:           epi_chunk_full<2, false, false, false>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 16:          epi_chunk_full<0, false, false, true>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 4 | 16:      epi_chunk_full<0, true, false, true>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 4 | 8 | 16:  epi_chunk_full<0, true, true, true>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              case 8:           epi_chunk_full<0, false, true, false>(taddr, box_row, swz, bias_c, res_c, aux_c, sc); break;
+              default: done = false; break;
             }
-            if (!write_pre) {
-              if (act == 1) {
+            if (done) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(write_pre ? &tmP : &tmC, box, n0 + c0, m0 + q * 32);
+                tma_store_commit();
+              }
+              continue;
+            }
+          }
+          // two 16-column halves per 32-column box: short live ranges leave registers for interleaving the
+          // GELU dependency chains of four packed pairs
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
-              } else if (act == 2) {
-                const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[j]);
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ch = c0 + hf * 16;
+            uint4 rv[2], av[2];
+            if (res_r && !write_pre) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16(au[e]);
-                  x[2 * e] *= gelu_erf_grad(f.x);
-                  x[2 * e + 1] *= gelu_erf_grad(f.y);
+              for (int j = 0; j < 2; ++j)
+                rv[j] = (row_ok && ch + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(res_r + ch + j * 8)
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (act == 2 && !write_pre) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                av[j] = (row_ok && ch + j * 8 < ncols) ? *reinterpret_cast<const uint4*>(aux_r + ch + j * 8)
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+            }
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + ch, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {  // 8 columns = one 16-byte bf16 chunk; math on packed fp32 pairs
+              uint64_t xp[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                xp[e] = pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+              const int col = ch + j * 8;  // column inside the tile
+              const bool col_ok = col < ncols;
+              if (bias && col_ok) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + col + 4));
+                xp[0] = add2(xp[0], pk2(b0.x, b0.y)); xp[1] = add2(xp[1], pk2(b0.z, b0.w));
+                xp[2] = add2(xp[2], pk2(b1.x, b1.y)); xp[3] = add2(xp[3], pk2(b1.z, b1.w));
+              }
+              if (!write_pre) {
+                if (act == 1) {
+                  gelu_erf2x4(xp);
+                } else if (act == 2) {
+                  const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[j]);
+                  uint64_t hx[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16(au[e]);
+                    hx[e] = pk2(f.x, f.y);
+                  }
+                  gelu_erf_grad_mul2x4(xp, hx);
+                }
+                const uint64_t sc2 = pk2(sc, sc);
+                if (res_r) {
+                  const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16(ru[e]);
+                    xp[e] = fma2(xp[e], sc2, pk2(f.x, f.y));
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) xp[e] = mul2(xp[e], sc2);
                 }
               }
+              float x[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] *= sc;
-              if (res_r) {
-                const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[j]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16(ru[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
+              for (int e = 0; e < 4; ++e) upk2(xp[e], x[2 * e], x[2 * e + 1]);
+              const int jb = hf * 2 + j;  // 16-byte chunk inside the 64-byte box row
+              if (out_mode == 0 || write_pre) {
+                uint4 o;
+                o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+                o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+                if (use_tma) {
+                  *reinterpret_cast<uint4*>(box + lane * 64 + ((jb ^ ((lane >> 1) & 3)) << 4)) = o;
+                } else if (row_ok && col_ok) {  // pitch not TMA-addressable: direct 16-byte row stores
+                  bf16* dst = write_pre ? preact + row * p.ldp + n0 + col
+                                        : reinterpret_cast<bf16*>(p.c) + row * p.ldc + n0 + col;
+                  *reinterpret_cast<uint4*>(dst) = o;
                 }
-              }
-            }
-            if (out_mode == 0 || write_pre) {
-              uint4 o;
-              o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
-              o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
-              if (use_tma) {
-                *reinterpret_cast<uint4*>(box + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
-              } else if (row_ok && col_ok) {  // pitch not TMA-addressable: direct 16-byte row stores
-                bf16* dst = write_pre ? preact + row * p.ldp + n0 + col
-                                      : reinterpret_cast<bf16*>(p.c) + row * p.ldc + n0 + col;
-                *reinterpret_cast<uint4*>(dst) = o;
-              }
-            } else if (row_ok && col_ok) {
-              float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + n0 + col;
-              if (out_mode == 1) {
-                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
-              } else {  // split-K wgrad: 16-byte vector reductions (red.global.add.v4.f32)
-                atomicAdd(reinterpret_cast<float4*>(dst), make_float4(x[0], x[1], x[2], x[3]));
-                atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(x[4], x[5], x[6], x[7]));
+              } else if (row_ok && col_ok) {
+                float* dst = reinterpret_cast<float*>(p.c) + row * p.ldc + n0 + col;
+                if (out_mode == 1) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                } else {  // split-K wgrad: 16-byte vector reductions (red.global.add.v4.f32)
+                  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(x[0], x[1], x[2], x[3]));
+                  atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(x[4], x[5], x[6], x[7]));
+                }
               }
             }
           }

@@ -87,3 +87,48 @@ def test_gemm_tma_store_epilogue(cuda_dev, m, n, k):
     torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
     out2 = K.gemm(a, b, bias=bias)
     torch.testing.assert_close(out2.float(), h, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("combo", ["plain", "bias", "bias_gelu_pre", "gelu_grad", "res", "bias_res", "bias_scale_res",
+                                   "scale", "bias_pre_scale_res"])
+def test_gemm_specialised_epilogues(cuda_dev, combo):
+    """Tile-aligned shapes take the compile-time specialised epilogue chunks (gemm_sm100.cu epi_chunk_full)."""
+    from fiber_b200 import kernels as K
+    m, n, k = 512, 768, 192
+    a = _mk((m, k), cuda_dev, 21)
+    b = _mk((n, k), cuda_dev, 22, k ** -0.5)
+    bias = torch.randn(n, device=cuda_dev)
+    res = _mk((m, n), cuda_dev, 23)
+    aux = _mk((m, n), cuda_dev, 24)
+    alpha = torch.tensor([0.6], device=cuda_dev)
+    rs = torch.rand(m // 64, device=cuda_dev) + 0.5
+    acc = a.float() @ b.float().t()
+    rsf = rs.repeat_interleave(64)[:, None]
+    pre = torch.zeros((m, n), device=cuda_dev, dtype=torch.bfloat16)
+    if combo == "plain":
+        out, ref = K.gemm(a, b), acc
+    elif combo == "bias":
+        out, ref = K.gemm(a, b, bias=bias), acc + bias
+    elif combo == "bias_gelu_pre":
+        out = K.gemm(a, b, bias=bias, act=K.ACT_GELU, preact=pre)
+        ref = torch.nn.functional.gelu(acc + bias)
+        torch.testing.assert_close(pre.float(), acc + bias, rtol=RTOL, atol=ATOL)
+    elif combo == "gelu_grad":
+        out = K.gemm(a, b, aux=aux, act=K.ACT_GELU_GRAD)
+        x = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(x).sum().backward()
+        ref = acc * x.grad
+    elif combo == "res":
+        out, ref = K.gemm(a, b, residual=res), acc + res.float()
+    elif combo == "bias_res":
+        out, ref = K.gemm(a, b, bias=bias, residual=res), acc + bias + res.float()
+    elif combo == "bias_scale_res":
+        out = K.gemm(a, b, bias=bias, residual=res, row_scale=rs, rows_per_scale=64)
+        ref = (acc + bias) * rsf + res.float()
+    elif combo == "scale":
+        out, ref = K.gemm(a, b, scale=alpha), acc * 0.6
+    else:
+        out = K.gemm(a, b, bias=bias, preact=pre, scale=alpha, residual=res, row_scale=rs, rows_per_scale=64)
+        ref = (acc + bias) * 0.6 * rsf + res.float()
+        torch.testing.assert_close(pre.float(), acc + bias, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
