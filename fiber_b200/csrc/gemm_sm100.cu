@@ -40,6 +40,7 @@ struct GemmParams {
   int act;
   int out_mode;
   int tma_store;  // epilogue variant: thread=row math -> swizzled smem box -> TMA store (no residual/aux)
+  float* colsum;  // MN-major only: colsum[m] += scale * sum_k A[k, m] (extra N=16 MMA against a tile of ones)
 };
 
 constexpr int GEMM_BM = 128;
@@ -174,6 +175,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  // Bias-gradient column sums (wgrad): a tile of bf16 ones in the (otherwise unused) TMA-store staging area is
+  // the B operand of one extra 128 x 16 MMA per k-step; its accumulator sits behind the single main accumulator.
+  const bool do_cs = MN_MAJOR == 1 && p.colsum != nullptr;
+  if (do_cs) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(staging);
+    for (int i = threadIdx.x; i < 8192 / 4; i += GEMM_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
+  const int nacc = do_cs ? 1 : 2;  // accumulators in flight (the column-sum columns take the second one's place)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -216,6 +226,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, MN_MAJOR, MN_MAJOR);
+    constexpr uint32_t idesc_cs = umma_idesc_bf16(GEMM_BM, 16, MN_MAJOR, MN_MAJOR);
+    const uint32_t ones_addr = smem_u32(staging);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -224,6 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int split = unit / (p.tiles_m * p.tiles_n);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      const bool cs_unit = do_cs && ((unit % (p.tiles_m * p.tiles_n)) % p.tiles_n == 0);  // first n-tile of its row
       // wait until the epilogue has drained this accumulator
       mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1);
       tc_fence_after();
@@ -245,6 +258,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               bdesc = umma_desc_sw128(sb + k * 2048, 8192, 1024);
             }
             umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (MN_MAJOR == 1 && cs_unit)
+              umma_f16_ss(tmem_base + BN, adesc, umma_desc_sw128(ones_addr + k * 2048, 8192, 1024), idesc_cs,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
@@ -253,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       acc_phase[acc] ^= 1;
-      acc ^= 1;
+      acc = nacc == 2 ? acc ^ 1 : 0;
     }
   } else {
     // ================= epilogue (warps 2..17) =================
@@ -450,11 +466,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (do_cs && n0 == 0 && cgrp == 0) {  // the 16 column-sum columns are identical: take the first
+        uint32_t cs[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN, cs);
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(p.colsum + row, __uint_as_float(cs[0]) * scale);
+      }
       // every TMEM read of this accumulator by this warp has completed (tmem_ld_wait): hand it back
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc_phase ^= (1u << acc);
-      acc ^= 1;
+      acc = nacc == 2 ? acc ^ 1 : 0;
     }
     if (use_tma && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
   }
@@ -545,11 +567,18 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   if (a->out_mode != 2) {
     splits = 1;
   } else if (splits <= 0) {
-    // enough work units to fill the machine, at least 4 k-blocks each
-    splits = (2 * sms + tiles - 1) / tiles;
+    // Work units = tiles x splits are dealt round-robin to one CTA per SM and all have the same depth, so the
+    // launch takes ceil(units / SMs) waves of ceil(kb / splits) k-blocks (+ ~6 k-blocks of epilogue / atomics
+    // per wave): pick the split count with the shortest makespan, at least 4 k-blocks per unit.
     const int max_splits = (p.kb_total + 3) / 4;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    long long best_cost = -1;
+    splits = 1;
+    for (int s = 1; s <= max_splits && s <= 8 * sms; ++s) {
+      const long long waves = (static_cast<long long>(tiles) * s + sms - 1) / sms;
+      const long long depth = (p.kb_total + s - 1) / s;
+      const long long cost = waves * (depth + 6);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = s; }
+    }
   }
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -562,6 +591,9 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   p.scale = a->scale; p.row_scale = a->row_scale;
   p.rows_per_scale = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
   p.act = a->act; p.out_mode = a->out_mode;
+  p.colsum = a->colsum;
+  FIBER_CHECK(a->colsum == nullptr || (a->a_major == 1 && a->out_mode != 0 && a->row_scale == nullptr),
+              "colsum needs MN-major operands, an fp32 output and no row_scale");
 
   CUtensorMap ta, tb;
   if (mn == 0) {

@@ -43,11 +43,12 @@ def _rowmajor_2d(t, name):
 
 def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=None, scale=None,
          row_scale=None, rows_per_scale=1, act=ACT_NONE, out=None, out_dtype=BF16,
-         accumulate=False, splits=0):
+         accumulate=False, splits=0, colsum=None):
     """out[M,N] = epilogue(A . B^T).
 
     mn_major=False: a is [M,K], b is [N,K]  (forward / dgrad with a transposed weight copy)
-    mn_major=True : a is [K,M], b is [K,N]  (wgrad: a = dY [rows,N_out], b = X [rows,K_in])
+    mn_major=True : a is [K,M], b is [K,N]  (wgrad: a = dY [rows,N_out], b = X [rows,K_in]);
+                    colsum (fp32 [M]) additionally accumulates scale * sum_k a[k, :] (the bias gradient)
     """
     _req(a, BF16, "a"); _req(b, BF16, "b")
     lda = _rowmajor_2d(a, "a"); ldb = _rowmajor_2d(b, "b")
@@ -90,6 +91,11 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
     args.act = act
     args.out_mode = out_mode
     args.splits = splits
+    if colsum is not None:
+        _req(colsum, F32, "colsum")
+        if not mn_major or colsum.numel() != m or not colsum.is_contiguous():
+            raise RuntimeError("fiber_b200.gemm: colsum needs mn_major=True and a contiguous fp32 [M] tensor")
+        args.colsum = colsum.data_ptr()
     if GEMM_PROFILE is None:
         _lib.check(_lib.load().fiber_gemm(C.byref(args), _stream()), "gemm")
         return out

@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("scale", C.c_void_p),
         ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
         ("act", C.c_int32), ("out_mode", C.c_int32), ("splits", C.c_int32),
+        ("colsum", C.c_void_p),
     ]
 
 

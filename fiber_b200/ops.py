@@ -121,9 +121,10 @@ class _GradArena(dict):
             off += sizes[n][1]
 
 
-def _wgrad(dy, x, scale=None, out=None):
-    """dW[N,K] = dy[rows,N]^T x[rows,K]  (fp32, split-K atomics on a zeroed buffer)."""
-    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale, out=out)
+def _wgrad(dy, x, scale=None, out=None, db=None):
+    """dW[N,K] = dy[rows,N]^T x[rows,K]  (fp32, split-K atomics on a zeroed buffer); db[N] += colsum(dy)
+    comes out of the same kernel (one extra 128x16 MMA per k-step against a tile of ones)."""
+    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale, out=out, colsum=db)
 
 
 def _colsum(x, out=None, **kw):
@@ -160,8 +161,8 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, wt, has_bias, xshape, xdtype = ctx.saved
         dy2 = _to_bf16_2d(dy)
-        dw = _wgrad(dy2, x2)
-        db = K.colsum(dy2) if has_bias else None
+        db = torch.zeros(dy2.shape[1], device=dy2.device, dtype=F32) if has_bias else None
+        dw = _wgrad(dy2, x2, db=db)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dy2, wt, out_dtype=F32 if xdtype == F32 else BF16).view(xshape)
@@ -314,11 +315,9 @@ class SwinBlockFn(torch.autograd.Function):
 
         # ---- MLP branch: out = x1 + s * fc2(gelu(fc1(LN2(x1)))) ----
         dz = K.scale_rows(d_out, sv["s_mlp"], T) if sv["s_mlp"] is not None else d_out
-        _wgrad(dz, sv["a"], out=g["mlp.fc2.weight"])
-        K.colsum(dz, out=g["mlp.fc2.bias"])
+        _wgrad(dz, sv["a"], out=g["mlp.fc2.weight"], db=g["mlp.fc2.bias"])
         dh = K.gemm(dz, sv["w2_t"], aux=sv["h"], act=K.ACT_GELU_GRAD)
-        _wgrad(dh, sv["ln2"], out=g["mlp.fc1.weight"])
-        K.colsum(dh, out=g["mlp.fc1.bias"])
+        _wgrad(dh, sv["ln2"], out=g["mlp.fc1.weight"], db=g["mlp.fc1.bias"])
         dln2 = K.gemm(dh, sv["w1_t"])
         dx1 = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
                               dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
@@ -328,26 +327,22 @@ class SwinBlockFn(torch.autograd.Function):
         if fused:
             alpha = p["attn.alpha_i2t"]
             K.dot(dZ, sv["y"], out=g["attn.alpha_i2t"])
-            _wgrad(dZ, sv["ao2"], scale=alpha, out=g["attn.proj_i2t.weight"])
-            K.colsum(dZ, scale=alpha, out=g["attn.proj_i2t.bias"])
+            _wgrad(dZ, sv["ao2"], scale=alpha, out=g["attn.proj_i2t.weight"], db=g["attn.proj_i2t.bias"])
             dao2 = K.gemm(dZ, sv["wp2_t"], scale=alpha)
             dq2 = torch.empty_like(sv["q2"])
             dkvt = torch.empty_like(sv["kvt"])
             K.attn_bwd(dao2, sv["q2"], sv["kvt"][:, :C], sv["kvt"][:, C:], sv["ao2"], sv["lse2"], nh, hd, scale,
                        dq2, dkvt[:, :C], dkvt[:, C:], groups=B, lq=T, lk=sv["L"], key_mask=sv["km"])
-            _wgrad(dkvt, sv["t2"], out=g["attn.qkv_text_i2t.weight"])
-            K.colsum(dkvt, out=g["attn.qkv_text_i2t.bias"])
+            _wgrad(dkvt, sv["t2"], out=g["attn.qkv_text_i2t.weight"], db=g["attn.qkv_text_i2t.bias"])
             if ctx.needs_input_grad[1]:
                 dtext = K.gemm(dkvt, sv["wkvt_t"]).view(sv["text_shape"])
-            _wgrad(dq2, sv["lnz"], out=g["attn.qkv_i2t.weight"])
-            K.colsum(dq2, out=g["attn.qkv_i2t.bias"])
+            _wgrad(dq2, sv["lnz"], out=g["attn.qkv_i2t.weight"], db=g["attn.qkv_i2t.bias"])
             dlnz = K.gemm(dq2, sv["wq2_t"])
             dzz = K.layernorm_bwd(dlnz, sv["z"], sv["meanz"], sv["rstdz"], p["attn.norm_i2t_i.weight"], dres=dZ,
                                   dgamma=g["attn.norm_i2t_i.weight"], dbeta=g["attn.norm_i2t_i.bias"])
         else:
             dzz = dZ
-        _wgrad(dzz, sv["ao"], out=g["attn.proj.weight"])
-        K.colsum(dzz, out=g["attn.proj.bias"])
+        _wgrad(dzz, sv["ao"], out=g["attn.proj.weight"], db=g["attn.proj.bias"])
         dao = K.gemm(dzz, sv["wproj_t"])
         dqkv = torch.empty_like(sv["qkv"])
         qkv = sv["qkv"]
@@ -355,8 +350,7 @@ class SwinBlockFn(torch.autograd.Function):
                    dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:],
                    dbias_table=g["attn.relative_position_bias_table"], window=(B, H, W, ws, shift),
                    bias_table=p["attn.relative_position_bias_table"])
-        _wgrad(dqkv, sv["ln1"], out=g["attn.qkv.weight"])
-        K.colsum(dqkv, out=g["attn.qkv.bias"])
+        _wgrad(dqkv, sv["ln1"], out=g["attn.qkv.weight"], db=g["attn.qkv.bias"])
         dln1 = K.gemm(dqkv, sv["wqkv_t"])
         dx = K.layernorm_bwd(dln1, sv["x2"], sv["mean1"], sv["rstd1"], p["norm1.weight"], dres=dx1,
                              dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
@@ -505,11 +499,9 @@ class RobertaLayerFn(torch.autograd.Function):
             g["output.LayerNorm.weight"] = g["output.LayerNorm.bias"] = None
             dsum = d_out
         df = K.dropout(dsum, p_h, sv["seed_f"]) if p_h > 0 else dsum
-        _wgrad(df, sv["inter"], out=g["output.dense.weight"])
-        K.colsum(df, out=g["output.dense.bias"])
+        _wgrad(df, sv["inter"], out=g["output.dense.weight"], db=g["output.dense.bias"])
         dhpre = K.gemm(df, sv["wout_t"], aux=sv["hpre"], act=K.ACT_GELU_GRAD)
-        _wgrad(dhpre, sv["ln_a"], out=g["intermediate.dense.weight"])
-        K.colsum(dhpre, out=g["intermediate.dense.bias"])
+        _wgrad(dhpre, sv["ln_a"], out=g["intermediate.dense.weight"], db=g["intermediate.dense.bias"])
         dln_a = K.gemm(dhpre, sv["wi_t"], residual=dsum)
         ds1 = K.layernorm_bwd(dln_a, sv["a2"], sv["mean_a"], sv["rstd_a"], p["attention.output.LayerNorm.weight"],
                               add=sv["h2"], dgamma=g["attention.output.LayerNorm.weight"],
@@ -519,36 +511,35 @@ class RobertaLayerFn(torch.autograd.Function):
             alpha = p["alpha_t2i"]
             K.dot(ds1, sv["c"], out=g["alpha_t2i"])
             gc = K.dropout(ds1, p_h, sv["seed_o2"]) if p_h > 0 else ds1
-            _wgrad(gc, sv["ctx2"], scale=alpha, out=g["crossattention_t2i.output.dense.weight"])
-            K.colsum(gc, scale=alpha, out=g["crossattention_t2i.output.dense.bias"])
+            _wgrad(gc, sv["ctx2"], scale=alpha, out=g["crossattention_t2i.output.dense.weight"],
+                   db=g["crossattention_t2i.output.dense.bias"])
             dctx2 = K.gemm(gc, sv["wo2_t"], scale=alpha)
             dq2 = torch.empty_like(sv["q2"])
             dkv2 = torch.empty_like(sv["kv2"])
             K.attn_bwd(dctx2, sv["q2"], sv["kv2"][:, :C], sv["kv2"][:, C:], sv["ctx2"], sv["lse2"], nh, hd, scale,
                        dq2, dkv2[:, :C], dkv2[:, C:], groups=B, lq=L, lk=sv["Tk"], drop_p=p_a, seed=sv["seed_a2"])
-            dwkv2 = _wgrad(dkv2, sv["img2"], out=g["wkv2"])
-            dbkv2 = K.colsum(dkv2, out=g["bkv2"])
+            dwkv2 = _wgrad(dkv2, sv["img2"], out=g["wkv2"], db=g["bkv2"])
+            dbkv2 = g["bkv2"]
             g["crossattention_t2i.self.key.weight"], g["crossattention_t2i.self.value.weight"] = dwkv2[:C], dwkv2[C:]
             g["crossattention_t2i.self.key.bias"], g["crossattention_t2i.self.value.bias"] = dbkv2[:C], dbkv2[C:]
             if ctx.needs_input_grad[2]:
                 dimage = K.gemm(dkv2, sv["wkv2_t"]).view(sv["image_shape"])
-            _wgrad(dq2, sv["a"], out=g["crossattention_t2i.self.query.weight"])
-            K.colsum(dq2, out=g["crossattention_t2i.self.query.bias"])
+            _wgrad(dq2, sv["a"], out=g["crossattention_t2i.self.query.weight"],
+                   db=g["crossattention_t2i.self.query.bias"])
             da = K.gemm(dq2, sv["wq2_t"], residual=ds1)
         else:
             da = ds1
         if p_h > 0:
             da = K.dropout(da, p_h, sv["seed_o"])
-        _wgrad(da, sv["ctxv"], out=g["attention.output.dense.weight"])
-        K.colsum(da, out=g["attention.output.dense.bias"])
+        _wgrad(da, sv["ctxv"], out=g["attention.output.dense.weight"], db=g["attention.output.dense.bias"])
         dctx = K.gemm(da, sv["wo_t"])
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
         K.attn_bwd(dctx, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], sv["ctxv"], sv["lse"], nh, hd, scale,
                    dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], groups=B, lq=L, lk=L, key_mask=sv["km"],
                    drop_p=p_a, seed=sv["seed_a"])
-        dwqkv = _wgrad(dqkv, sv["h2"], out=g["wqkv"])
-        dbqkv = K.colsum(dqkv, out=g["bqkv"])
+        dwqkv = _wgrad(dqkv, sv["h2"], out=g["wqkv"], db=g["bqkv"])
+        dbqkv = g["bqkv"]
         for i, n in enumerate(("query", "key", "value")):
             g["attention.self.%s.weight" % n] = dwqkv[i * C:(i + 1) * C]
             g["attention.self.%s.bias" % n] = dbqkv[i * C:(i + 1) * C]

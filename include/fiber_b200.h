@@ -64,6 +64,9 @@ typedef struct fiber_gemm_args {
   int32_t act;
   int32_t out_mode;
   int32_t splits; /* 0 = choose */
+  /* MN-major (wgrad) only, out_mode 1 / 2: colsum[m] += scale * sum_k A[k, m] — the bias gradient
+   * db = dY^T 1 that goes with dW = dY^T X (one extra 128 x 16 MMA per k-step against a tile of ones). */
+  float* colsum;
 } fiber_gemm_args;
 
 int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream);

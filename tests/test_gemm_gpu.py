@@ -42,6 +42,12 @@ def test_gemm_mnmajor_wgrad(cuda_dev, m, n, k):
     torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
     out1 = K.gemm(dy, x, mn_major=True, out_dtype=torch.float32)
     torch.testing.assert_close(out1, ref, rtol=2e-3, atol=2e-3)
+    # fused bias gradient: db[m] = scale * sum_k dy[k, m] from the same kernel (ones-tile MMA)
+    db = torch.zeros(m, device=cuda_dev)
+    alpha = torch.tensor([0.5], device=cuda_dev)
+    out2 = K.gemm(dy, x, mn_major=True, accumulate=True, scale=alpha, colsum=db)
+    torch.testing.assert_close(out2, 0.5 * ref, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(db, 0.5 * dy.float().sum(0), rtol=2e-3, atol=2e-3 * max(1.0, k ** 0.5 * k ** -0.5))
 
 
 def test_gemm_epilogue(cuda_dev):
