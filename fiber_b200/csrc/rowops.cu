@@ -316,6 +316,208 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 2 : 1) ln_bwd_kernel(const L
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast paths (plain rows: no second input, no PatchMerging gather, C == 8 * VPL * LPR exactly) — the
+// Swin norm1 / norm2 / norm_i2t and final-norm LayerNorms, i.e. almost all LayerNorm bytes of a step.
+// Every 16-byte load of a warp iteration (x [, dy, dres]) is issued before anything is consumed and the
+// rows stay PACKED (bf16) in registers; x_hat / dy*gamma are recomputed in the second pass instead of
+// being kept as fp32.  That puts ROWS*VPL*(1 or 3)*16 bytes per lane in flight with ONE exposed memory
+// latency per iteration (the generic kernels expose two and hold a third of the bytes).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&x)[8]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16(w[e]);
+    x[2 * e] = f.x; x[2 * e + 1] = f.y;
+  }
+}
+// Compiler barrier on a packed vector: stops CSE from keeping the fp32 unpacking of pass 1 alive for pass 2
+// (the point of the fast kernels is that only the packed registers persist).
+__device__ __forceinline__ void keep_packed(uint4& u) {
+  asm volatile("" : "+r"(u.x), "+r"(u.y), "+r"(u.z), "+r"(u.w));
+}
+__device__ __forceinline__ void ldg8f(const float* ptr, float (&x)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(ptr));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(ptr + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+
+template <int VPL, int LPR, int ROWS>
+__global__ void __launch_bounds__(256, 3) ln_fwd_fast_kernel(const LnParams p) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invC = 1.0f / p.C;
+  for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
+    uint4 xp[ROWS][VPL];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        xp[r][v] = row < p.rows ? *reinterpret_cast<const uint4*>(p.in1 + row * p.ld1 + (sl + LPR * v) * 8)
+                                : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float s1[ROWS], s2[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      s1[r] = s2[r] = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float x[8];
+        unpack8(xp[r][v], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s1[r] += x[e];
+          s2[r] = fmaf(x[e], x[e], s2[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      s1[r] = group_sum<LPR>(s1[r]);
+      s2[r] = group_sum<LPR>(s2[r]);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) keep_packed(xp[r][v]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+      const float mean = s1[r] * invC;
+      const float rstd = rsqrtf(fmaxf(s2[r] * invC - mean * mean, 0.f) + p.eps);
+      if (row < p.rows) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int col = (sl + LPR * v) * 8;
+          float x[8], g[8], b[8], y[8];
+          unpack8(xp[r][v], x);
+          ldg8f(p.gamma + col, g);
+          ldg8f(p.beta + col, b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = fmaf((x[e] - mean) * rstd, g[e], b[e]);
+          store8(p.out + row * p.ldo + col, y);
+        }
+        if (sl == 0) {
+          if (p.mean) p.mean[row] = mean;
+          if (p.rstd) p.rstd[row] = rstd;
+        }
+      }
+    }
+  }
+}
+
+template <int VPL, int LPR, int ROWS>
+__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
+  constexpr int RPW = 32 / LPR;
+  extern __shared__ float s_acc[];  // [2][C]: dgamma, dbeta block partials
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float invC = 1.0f / p.C;
+  const bool has_res = p.dres != nullptr;
+  float dg[VPL][8], db[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[v][e] = db[v][e] = 0.f;
+
+  for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
+    uint4 xp[ROWS][VPL], yp[ROWS][VPL], rp[ROWS][VPL];
+    float mean[ROWS], rs[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r * RPW + sr;
+      const bool rv = row < p.rows;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (sl + LPR * v) * 8;
+        xp[r][v] = rv ? *reinterpret_cast<const uint4*>(p.in1 + row * p.ld1 + col) : make_uint4(0u, 0u, 0u, 0u);
+        yp[r][v] = rv ? *reinterpret_cast<const uint4*>(p.dy + row * p.lddy + col) : make_uint4(0u, 0u, 0u, 0u);
+        rp[r][v] = (rv && has_res) ? *reinterpret_cast<const uint4*>(p.dres + row * p.lddres + col)
+                                   : make_uint4(0u, 0u, 0u, 0u);
+      }
+      mean[r] = rv ? p.mean[row] : 0.f;
+      rs[r] = rv ? p.rstd[row] : 0.f;
+    }
+    float c1[ROWS], c2[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) c1[r] = c2[r] = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float gam[8];
+      ldg8f(p.gamma + (sl + LPR * v) * 8, gam);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        float x[8], dy[8];
+        unpack8(xp[r][v], x);
+        unpack8(yp[r][v], dy);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xhat = (x[e] - mean[r]) * rs[r];
+          const float gy = dy[e] * gam[e];
+          c1[r] += gy;
+          c2[r] = fmaf(gy, xhat, c2[r]);
+          dg[v][e] = fmaf(dy[e], xhat, dg[v][e]);
+          db[v][e] += dy[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      c1[r] = group_sum<LPR>(c1[r]);
+      c2[r] = group_sum<LPR>(c2[r]);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        keep_packed(xp[r][v]);
+        keep_packed(yp[r][v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (sl + LPR * v) * 8;
+      float gam[8];
+      ldg8f(p.gamma + col, gam);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const long long row = row0 + r * RPW + sr;
+        if (row < p.rows) {
+          const float k1 = c1[r] * invC, k2 = c2[r] * invC;
+          float x[8], dy[8], rr[8], dx[8];
+          unpack8(xp[r][v], x);
+          unpack8(yp[r][v], dy);
+          unpack8(rp[r][v], rr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xhat = (x[e] - mean[r]) * rs[r];
+            dx[e] = fmaf(rs[r], dy[e] * gam[e] - k1 - xhat * k2, rr[e]);
+          }
+          store8(p.dx + row * p.lddx + col, dx);
+        }
+      }
+    }
+  }
+  if (p.dgamma) {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = (sl + LPR * v) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_acc[col + e], dg[v][e]);
+        atomicAdd(&s_acc[p.C + col + e], db[v][e]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      atomicAdd(p.dgamma + i, s_acc[i]);
+      atomicAdd(p.dbeta + i, s_acc[p.C + i]);
+    }
+  }
+}
+
 static int ln_grid(long long rows, int rows_per_warp, int blocks_per_sm) {
   const long long blocks = (rows + 8 * rows_per_warp - 1) / (8 * rows_per_warp);  // 8 warps per block
   const long long cap = static_cast<long long>(num_sms()) * blocks_per_sm;
@@ -336,12 +538,40 @@ static int ln_launch(const LnParams& p, bool bwd, cudaStream_t stream) {
   return 0;
 }
 
+template <int VPL, int LPR, int ROWS>
+static int ln_launch_fast(const LnParams& p, bool bwd, cudaStream_t stream) {
+  const int rpw = ROWS * (32 / LPR);
+  if (!bwd) {
+    ln_fwd_fast_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 3), 256, 0, stream>>>(p);
+  } else {
+    ln_bwd_fast_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 2), 256, 2 * p.C * sizeof(float), stream>>>(p);
+  }
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static bool ln_aligned16(const void* ptr, long long ld) {
+  return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0);
+}
+
 int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
   FIBER_CHECK(p.C % 8 == 0 && p.C >= 8 && p.C <= 2048, "LayerNorm width must be a multiple of 8 in [8, 2048] (got %d)", p.C);
   FIBER_CHECK(p.rows > 0, "LayerNorm needs rows > 0");
   if (p.merge) {
     FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
                 "bad PatchMerging LayerNorm geometry");
+  }
+  static const bool fast_on = [] { const char* e = getenv("FIBER_LN_FAST"); return !(e && e[0] == '0'); }();
+  const bool plain = !p.merge && !p.in2 && !p.sum_out && ln_aligned16(p.in1, p.ld1) &&
+                     (bwd ? (ln_aligned16(p.dy, p.lddy) && ln_aligned16(p.dres, p.lddres) && ln_aligned16(p.dx, p.lddx))
+                          : ln_aligned16(p.out, p.ldo));
+  if (fast_on && plain) {  // ROWS * VPL = 4 vectors per lane and tensor in flight
+    if (p.C == 128) return ln_launch_fast<1, 16, 4>(p, bwd, stream);
+    if (p.C == 256) return ln_launch_fast<1, 32, 4>(p, bwd, stream);
+    if (p.C == 512) return bwd ? ln_launch_fast<2, 32, 1>(p, true, stream) : ln_launch_fast<2, 32, 2>(p, false, stream);
+    if (!bwd && p.C == 768) return ln_launch_fast<3, 32, 1>(p, false, stream);
+    if (!bwd && p.C == 1024) return ln_launch_fast<4, 32, 1>(p, false, stream);
   }
   // unroll depths picked from tools/bench_ln.py on B200
   if (p.C <= 128) return ln_launch<1, 16, 2>(p, bwd, stream);

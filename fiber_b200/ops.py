@@ -60,8 +60,8 @@ class _WeightCache:
     def _alive(refs, ps):
         return all(r() is p for r, p in zip(refs, ps))
 
-    def weights(self, ps, need_t=True, pad_k=0):
-        """ps: tuple of fp32 [N_i, K] (or conv [N, ...]) weights packed along N."""
+    def weights(self, ps, need_t=True, pad_k=0, pad_n=0):
+        """ps: tuple of fp32 [N_i, K] (or conv [N, ...]) weights packed along N (zero rows up to pad_n)."""
         ids, vers = self._key(ps)
         hit = self._w.get(ids)
         if hit is not None and hit[0] == vers and self._alive(hit[3], ps) and (hit[2] is not None or not need_t):
@@ -70,10 +70,12 @@ class _WeightCache:
             mats = [p.detach().reshape(p.shape[0], -1) for p in ps]
             k = mats[0].shape[1]
             kp = max(k, pad_k)
-            n_total = sum(m.shape[0] for m in mats)
+            n_rows = sum(m.shape[0] for m in mats)
+            n_total = max(n_rows, pad_n)
             dev = mats[0].device
-            w = (torch.zeros if kp != k else torch.empty)((n_total, kp), device=dev, dtype=BF16)
-            wt = torch.empty((k, n_total), device=dev, dtype=BF16) if need_t else None
+            padded = kp != k or n_total != n_rows
+            w = (torch.zeros if padded else torch.empty)((n_total, kp), device=dev, dtype=BF16)
+            wt = (torch.zeros if padded else torch.empty)((k, n_total), device=dev, dtype=BF16) if need_t else None
             n0 = 0
             for m in mats:
                 n = m.shape[0]
@@ -167,6 +169,36 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dy2, wt, out_dtype=F32 if xdtype == F32 else BF16).view(xshape)
         return dx, dw, db, None
+
+
+class VocabDecoderFn(torch.autograd.Function):
+    """MLM decoder (heads.py:40-43): logits = x W^T + b over the 50265-word vocabulary, fp32 out.
+    The vocabulary is not a multiple of 8 (TMA rows are 16 bytes), so the cached bf16 weight copy carries
+    zero rows up to the next multiple and the returned logits are the [..., :V] view of the padded buffer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        V = weight.shape[0]
+        Vp = (V + 7) // 8 * 8
+        x2 = _to_bf16_2d(x)
+        w, wt = CACHE.weights((weight,), pad_n=Vp)
+        bp = torch.zeros(Vp, device=x2.device, dtype=F32)
+        bp[:V] = bias.detach()
+        y = K.gemm(x2, w, bias=bp, out_dtype=F32)
+        ctx.saved = (x2, wt, V, Vp, x.shape, x.dtype)
+        return y.view(*x.shape[:-1], Vp)[..., :V]
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wt, V, Vp, xshape, xdtype = ctx.saved
+        dyp = torch.zeros((x2.shape[0], Vp), device=x2.device, dtype=BF16)
+        dyp[:, :V] = dy.reshape(-1, V)
+        dbp = torch.zeros(Vp, device=x2.device, dtype=F32)
+        dw = _wgrad(dyp, x2, db=dbp)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dyp, wt, out_dtype=F32 if xdtype == F32 else BF16).view(xshape)
+        return dx, dw[:V], dbp[:V]
 
 
 class LayerNormFn(torch.autograd.Function):

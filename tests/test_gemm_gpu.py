@@ -138,3 +138,28 @@ def test_gemm_specialised_epilogues(cuda_dev, combo):
         ref = (acc + bias) * 0.6 * rsf + res.float()
         torch.testing.assert_close(pre.float(), acc + bias, rtol=RTOL, atol=ATOL)
     torch.testing.assert_close(out.float(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_vocab_decoder_padded(cuda_dev):
+    """ops.VocabDecoderFn: vocabulary size that is not a multiple of 8 (MLM head), forward + all gradients."""
+    from fiber_b200 import ops
+    torch.manual_seed(0)
+    V, Kd = 1003, 96
+    x = (torch.randn(3, 40, Kd, device=cuda_dev)).requires_grad_(True)
+    w = (torch.randn(V, Kd, device=cuda_dev) * Kd ** -0.5).requires_grad_(True)
+    b = torch.randn(V, device=cuda_dev).requires_grad_(True)
+    y = ops.VocabDecoderFn.apply(x, w, b)
+    assert y.shape == (3, 40, V)
+    labels = torch.randint(0, V, (120,), device=cuda_dev)
+    labels[::3] = -100
+    loss = torch.nn.functional.cross_entropy(y.view(-1, V).float(), labels, ignore_index=-100)
+    loss.backward()
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    yr = xr.to(torch.bfloat16).float() @ wr.to(torch.bfloat16).float().t() + br
+    lr = torch.nn.functional.cross_entropy(yr.view(-1, V), labels, ignore_index=-100)
+    lr.backward()
+    torch.testing.assert_close(y, yr, rtol=RTOL, atol=ATOL)
+    assert abs(loss.item() - lr.item()) < 2e-3
+    for name, a, r in (("dx", x.grad, xr.grad), ("dw", w.grad, wr.grad), ("db", b.grad, br.grad)):
+        err = (a - r).abs().max().item()
+        assert err <= 2e-2 * max(r.abs().max().item(), 1e-6), "%s: %g vs %g" % (name, err, r.abs().max().item())

@@ -21,7 +21,9 @@ def _close(a, b, tol, name):
 
 
 @pytest.mark.parametrize("rows,C,add", [(1000, 128, False), (333, 256, True), (77, 512, False), (2560, 768, True),
-                                        (500, 1024, False), (144, 2048, False), (9, 8, False)])
+                                        (500, 1024, False), (144, 2048, False), (9, 8, False),
+                                        (30001, 256, False), (40999, 512, False), (2560, 768, False),
+                                        (70003, 128, False)])
 def test_layernorm_fwd_bwd(cuda_dev, rows, C, add):
     from fiber_b200 import kernels as K
     x = _rand((rows, C), cuda_dev, 1)
