@@ -10,7 +10,6 @@
 // (shared-memory atomics -> one global atomic per table entry per CTA).
 #include "attention.cuh"
 #include "../../include/fiber_b200.h"
-#include <cstdlib>
 
 namespace fiber {
 
@@ -381,343 +380,6 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// D[row, head] = sum_d dO[row, h*HD + d] * O[row, h*HD + d]   (pre-pass of the window backward)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ o, long long ldo,
-                                                            const bf16* __restrict__ d_o, long long lddo,
-                                                            float* __restrict__ D, long long rows, int C, int hd) {
-  const int vec_per_row = C / 8;
-  const int lanes_per_head = hd / 8;  // 4 (hd 32) or 8 (hd 64): consecutive lanes, warp-aligned
-  const long long total = rows * vec_per_row;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x; i0 < total; i0 += stride) {
-    const long long i = i0 + threadIdx.x;
-    float part = 0.f;
-    long long r = 0;
-    int c = 0;
-    if (i < total) {
-      r = i / vec_per_row;
-      c = static_cast<int>(i % vec_per_row) * 8;
-      const uint4 a = *reinterpret_cast<const uint4*>(o + r * ldo + c);
-      const uint4 b = *reinterpret_cast<const uint4*>(d_o + r * lddo + c);
-      const uint32_t* au = reinterpret_cast<const uint32_t*>(&a);
-      const uint32_t* bu = reinterpret_cast<const uint32_t*>(&b);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 x = unpack_bf16(au[e]), y = unpack_bf16(bu[e]);
-        part += x.x * y.x + x.y * y.y;
-      }
-    }
-    for (int off = lanes_per_head / 2; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-    if (i < total && (threadIdx.x % lanes_per_head) == 0) D[r * (C / hd) + c / hd] = part;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Window attention backward, specialised: ws*ws <= 144 tokens, head_dim 32, one CTA (9 warps)
-// persistent over the windows of one head.  The Q/dO/K/V tiles, LSE and D of window i+1 are
-// prefetched with cp.async into the second smem buffer while window i is computed.
-// ---------------------------------------------------------------------------------------------
-constexpr int WB_HD = 32;
-constexpr int WB_PITCH = WB_HD + 8;
-constexpr int WB_TILE = BW_QROWS * WB_PITCH;  // elements per tile
-
-__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void* gptr, bool valid) {
-  const int sz = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct WinGeom {
-  int H, W, ws, shift, nWw, nW, N;
-  __device__ __forceinline__ int src_row(int g, int i) const {  // global activation row of window token i
-    const int b = g / nW, w = g % nW, wh = w / nWw, ww = w % nWw;
-    const int hp = wh * ws + i / ws, wp = ww * ws + i % ws;
-    return b * H * W + ((hp + shift) % H) * W + (wp + shift) % W;
-  }
-  __device__ __forceinline__ int rid(int g, int i) const {
-    const int w = g % nW, wh = w / nWw, ww = w % nWw;
-    const int hp = wh * ws + i / ws, wp = ww * ws + i % ws;
-    return 3 * ((hp >= H - ws) + (hp >= H - shift)) + (wp >= W - ws) + (wp >= W - shift);
-  }
-};
-
-__global__ void __launch_bounds__(BW_NWARPS * 32, 1) win_attn_bwd_kernel(const AttnParams p, const float* __restrict__ Dg) {
-  constexpr int HD = WB_HD, PITCH = WB_PITCH, CPR = HD / 8;
-  extern __shared__ __align__(16) uint8_t smem[];
-  bf16* tiles = reinterpret_cast<bf16*>(smem);                 // [2 buffers][Q, dO, K, V][144][PITCH]
-  bf16* sP = tiles + 2 * 4 * WB_TILE;
-  bf16* sdS = sP + BW_QROWS * BW_SP;
-  float* sLse = reinterpret_cast<float*>(sdS + BW_QROWS * BW_SP);  // [2][144]
-  float* sD = sLse + 2 * BW_QROWS;                                  // [2][144]
-  float* sTbl = sD + 2 * BW_QROWS;
-  float* sdTbl = sTbl + ATT_MAXTBL;
-  int16_t* sB = reinterpret_cast<int16_t*>(sdTbl + ATT_MAXTBL);  // (j/ws)*(2ws-1) + j%ws
-  uint8_t* sRid = reinterpret_cast<uint8_t*>(sB + BW_QROWS);     // [2][144]
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x;
-  WinGeom wg;
-  wg.H = p.H; wg.W = p.W; wg.ws = p.ws; wg.shift = p.shift;
-  wg.nWw = p.W / p.ws; wg.nW = (p.H / p.ws) * wg.nWw; wg.N = p.Lq;
-  const int N = wg.N, ws = p.ws, tw2 = 2 * ws - 1;
-  const int n_groups = p.G * wg.nW;
-  const int n_tiles = (N + 15) / 16;
-  const int nk_pad = ((N + ATT_KCHUNK - 1) / ATT_KCHUNK) * ATT_KCHUNK;
-  const int r_lo = lane >> 2;
-
-  float dbacc[18][4];
-#pragma unroll
-  for (int i = 0; i < 18; ++i) dbacc[i][0] = dbacc[i][1] = dbacc[i][2] = dbacc[i][3] = 0.f;
-  for (int t = tid; t < tw2 * tw2; t += blockDim.x) {
-    sTbl[t] = p.bias_table[t * p.nH + h];
-    sdTbl[t] = 0.f;
-  }
-  for (int i = tid; i < BW_QROWS; i += blockDim.x) sB[i] = i < N ? (i / ws) * tw2 + i % ws : 0;
-
-  auto prefetch = [&](int g, int buf) {
-    bf16* tb = tiles + buf * 4 * WB_TILE;
-    for (int c = tid; c < BW_QROWS * CPR; c += blockDim.x) {
-      const int r = c / CPR, cc = c % CPR;
-      const bool valid = r < N;
-      const long long grow = valid ? wg.src_row(g, r) : 0;
-      const int col = h * HD + cc * 8;
-      const uint32_t so = smem_u32(tb + r * PITCH + cc * 8);
-      cp_async16(so, p.q + grow * p.ldq + col, valid);
-      cp_async16(so + WB_TILE * 2, p.d_o + grow * p.lddo + col, valid);
-      cp_async16(so + 2 * WB_TILE * 2, p.k + grow * p.ldk + col, valid);
-      cp_async16(so + 3 * WB_TILE * 2, p.v + grow * p.ldv + col, valid);
-    }
-    for (int i = tid; i < BW_QROWS; i += blockDim.x) {
-      const bool valid = i < N;
-      const long long grow = valid ? wg.src_row(g, i) : 0;
-      cp_async4(smem_u32(sLse + buf * BW_QROWS + i), p.lse + (static_cast<long long>(g) * p.nH + h) * N + (valid ? i : 0), valid);
-      cp_async4(smem_u32(sD + buf * BW_QROWS + i), Dg + grow * p.nH + h, valid);
-      sRid[buf * BW_QROWS + i] = valid ? wg.rid(g, i) : 0;
-    }
-    cp_async_commit();
-  };
-
-  int it = 0;
-  if (static_cast<int>(blockIdx.y) < n_groups) prefetch(blockIdx.y, 0);
-  for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++it) {
-    const int cur = it & 1;
-    __syncthreads();  // everyone is done with buffer cur^1 (previous window) before it is refilled
-    const int g_next = g + gridDim.y;
-    if (g_next < n_groups) {
-      prefetch(g_next, cur ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    bf16* sQ = tiles + cur * 4 * WB_TILE;
-    bf16* sdO = sQ + WB_TILE;
-    bf16* sK = sdO + WB_TILE;
-    bf16* sV = sK + WB_TILE;
-    const float* lse_s = sLse + cur * BW_QROWS;
-    const float* d_s = sD + cur * BW_QROWS;
-    const uint8_t* rid_s = sRid + cur * BW_QROWS;
-
-    float dq[HD / 8][4];
-    // ================= phase A: 16 query rows per warp =================
-    if (warp < n_tiles) {
-      uint32_t qf[HD / 16][4], dof[HD / 16][4];
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
-        const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int col = ks * 16 + (lane >> 4) * 8;
-        ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-        ldsm_x4(smem_u32(sdO + row * PITCH + col), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
-      }
-      const int rl0 = warp * 16 + r_lo;
-      const float lse0 = lse_s[rl0], lse1 = lse_s[rl0 + 8];
-      const float D0 = d_s[rl0], D1 = d_s[rl0 + 8];
-      const int aq0 = sB[rl0] + (ws - 1) * (tw2 + 1), aq1 = sB[rl0 + 8] + (ws - 1) * (tw2 + 1);
-      const int rid0 = rid_s[rl0], rid1 = rid_s[rl0 + 8];
-      const int wcur = g % wg.nW;
-      const bool has_mask = p.shift > 0 && (wcur / wg.nWw == p.H / ws - 1 || wcur % wg.nWw == wg.nWw - 1);
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-#pragma unroll
-      for (int sub = 0; sub < ATT_SKEYS / ATT_KCHUNK; ++sub) {
-        if (sub * ATT_KCHUNK < nk_pad) {
-          float s[6][4], dp[6][4];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-            dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-          }
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks) {
-#pragma unroll
-            for (int nt2 = 0; nt2 < 3; ++nt2) {
-              const int row = sub * ATT_KCHUNK + nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
-              const int col = ks * 16 + ((lane >> 3) & 1) * 8;
-              uint32_t b0, b1, b2, b3;
-              ldsm_x4(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
-              mma16816(s[2 * nt2], qf[ks], b0, b1);
-              mma16816(s[2 * nt2 + 1], qf[ks], b2, b3);
-              ldsm_x4(smem_u32(sV + row * PITCH + col), b0, b1, b2, b3);
-              mma16816(dp[2 * nt2], dof[ks], b0, b1);
-              mma16816(dp[2 * nt2 + 1], dof[ks], b2, b3);
-            }
-          }
-#pragma unroll
-          for (int nt = 0; nt < 6; ++nt) {
-            const int j0 = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;  // keys j0, j0+1
-            const int jj0 = j0 < N ? j0 : 0, jj1 = j0 + 1 < N ? j0 + 1 : 0;
-            const int bj0 = sB[jj0], bj1 = sB[jj1];
-            const int ridj0 = has_mask ? rid_s[jj0] : 0, ridj1 = has_mask ? rid_s[jj1] : 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const bool hi = e >> 1, odd = e & 1;
-              const int j = j0 + odd;
-              const int ridq = hi ? rid1 : rid0, ridj = odd ? ridj1 : ridj0;
-              float v = s[nt][e] * p.scale + sTbl[(hi ? aq1 : aq0) - (odd ? bj1 : bj0)];
-              if (has_mask && ridq != ridj) v += -100.0f;
-              const float pr = (j < N) ? fast_exp(v - (hi ? lse1 : lse0)) : 0.f;
-              const float ds = pr * (dp[nt][e] - (hi ? D1 : D0));
-              s[nt][e] = pr;
-              dp[nt][e] = ds;
-              dbacc[sub * 6 + nt][e] += ds;
-            }
-          }
-#pragma unroll
-          for (int nt = 0; nt < 6; ++nt) {
-            const int col = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;
-            *reinterpret_cast<uint32_t*>(sP + rl0 * BW_SP + col) = pack_bf16(s[nt][0], s[nt][1]);
-            *reinterpret_cast<uint32_t*>(sP + (rl0 + 8) * BW_SP + col) = pack_bf16(s[nt][2], s[nt][3]);
-            *reinterpret_cast<uint32_t*>(sdS + rl0 * BW_SP + col) = pack_bf16(dp[nt][0], dp[nt][1]);
-            *reinterpret_cast<uint32_t*>(sdS + (rl0 + 8) * BW_SP + col) = pack_bf16(dp[nt][2], dp[nt][3]);
-          }
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            uint32_t a[4];
-            a[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
-            a[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
-            a[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
-            a[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
-#pragma unroll
-            for (int dt2 = 0; dt2 < HD / 16; ++dt2) {
-              const int row = sub * ATT_KCHUNK + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-              const int col = dt2 * 16 + (lane >> 4) * 8;
-              uint32_t b0, b1, b2, b3;
-              ldsm_x4_t(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
-              mma16816(dq[2 * dt2], a, b0, b1);
-              mma16816(dq[2 * dt2 + 1], a, b2, b3);
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ================= phase B: 16 key rows per warp =================
-    float dkacc[HD / 8][4], dvacc[HD / 8][4];
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      dkacc[i][0] = dkacc[i][1] = dkacc[i][2] = dkacc[i][3] = 0.f;
-      dvacc[i][0] = dvacc[i][1] = dvacc[i][2] = dvacc[i][3] = 0.f;
-    }
-    if (warp < n_tiles) {
-      const int m0 = warp * 16;
-      for (int kt = 0; kt < n_tiles; ++kt) {
-        const int k0 = kt * 16;
-        uint32_t ap[4], as_[4];
-        {
-          const int row = k0 + (lane & 7) + ((lane >> 4) << 3);
-          const int col = m0 + ((lane >> 3) & 1) * 8;
-          ldsm_x4_t(smem_u32(sP + row * BW_SP + col), ap[0], ap[1], ap[2], ap[3]);
-          ldsm_x4_t(smem_u32(sdS + row * BW_SP + col), as_[0], as_[1], as_[2], as_[3]);
-        }
-#pragma unroll
-        for (int dt2 = 0; dt2 < HD / 16; ++dt2) {
-          const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int col = dt2 * 16 + (lane >> 4) * 8;
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(smem_u32(sdO + row * PITCH + col), b0, b1, b2, b3);
-          mma16816(dvacc[2 * dt2], ap, b0, b1);
-          mma16816(dvacc[2 * dt2 + 1], ap, b2, b3);
-          ldsm_x4_t(smem_u32(sQ + row * PITCH + col), b0, b1, b2, b3);
-          mma16816(dkacc[2 * dt2], as_, b0, b1);
-          mma16816(dkacc[2 * dt2 + 1], as_, b2, b3);
-        }
-      }
-    }
-    __syncthreads();  // phase B finished reading sQ / sdO: reuse this buffer's tiles as store staging
-    if (warp < n_tiles) {
-#pragma unroll
-      for (int dt = 0; dt < HD / 8; ++dt) {
-        const int col = dt * 8 + (lane & 3) * 2;
-        const int ra = (warp * 16 + r_lo) * PITCH + col, rb = ra + 8 * PITCH;
-        *reinterpret_cast<uint32_t*>(sQ + ra) = pack_bf16(dq[dt][0] * p.scale, dq[dt][1] * p.scale);
-        *reinterpret_cast<uint32_t*>(sQ + rb) = pack_bf16(dq[dt][2] * p.scale, dq[dt][3] * p.scale);
-        *reinterpret_cast<uint32_t*>(sK + ra) = pack_bf16(dkacc[dt][0] * p.scale, dkacc[dt][1] * p.scale);
-        *reinterpret_cast<uint32_t*>(sK + rb) = pack_bf16(dkacc[dt][2] * p.scale, dkacc[dt][3] * p.scale);
-        *reinterpret_cast<uint32_t*>(sV + ra) = pack_bf16(dvacc[dt][0], dvacc[dt][1]);
-        *reinterpret_cast<uint32_t*>(sV + rb) = pack_bf16(dvacc[dt][2], dvacc[dt][3]);
-      }
-      __syncwarp();
-      for (int c = lane; c < 16 * CPR; c += 32) {
-        const int r = c / CPR, cc = c % CPR, i = warp * 16 + r;
-        if (i < N) {
-          const long long grow = wg.src_row(g, i);
-          const int so = i * PITCH + cc * 8, col = h * HD + cc * 8;
-          *reinterpret_cast<uint4*>(p.dq + grow * p.lddq + col) = *reinterpret_cast<const uint4*>(sQ + so);
-          *reinterpret_cast<uint4*>(p.dk + grow * p.lddk + col) = *reinterpret_cast<const uint4*>(sK + so);
-          *reinterpret_cast<uint4*>(p.dv + grow * p.lddv + col) = *reinterpret_cast<const uint4*>(sV + so);
-        }
-      }
-    }
-  }
-
-  // flush the register-resident d(bias) sums: smem atomics, then one global atomic per entry
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < 18; ++t) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = t * 8 + (lane & 3) * 2 + (e & 1);
-      const int qi = warp * 16 + r_lo + (e >> 1) * 8;
-      if (qi < N && j < N)
-        atomicAdd(&sdTbl[sB[qi] + (ws - 1) * (tw2 + 1) - sB[j]], dbacc[t][e]);
-    }
-  }
-  __syncthreads();
-  for (int t = tid; t < tw2 * tw2; t += blockDim.x) atomicAdd(&p.dbias_table[t * p.nH + h], sdTbl[t]);
-}
-
-static int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
-  const long long rows = static_cast<long long>(p.G) * p.H * p.W;
-  const int C = p.nH * WB_HD;
-  {
-    long long blocks = (rows * (C / 8) + 255) / 256;
-    const long long cap = static_cast<long long>(num_sms()) * 8;
-    if (blocks > cap) blocks = cap;
-    attn_bwd_prep_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.o, p.ldo, p.d_o, p.lddo, D, rows, C, WB_HD);
-    FIBER_CUDA(cudaGetLastError());
-    count_launch();
-  }
-  const size_t smem = 2 * 4 * WB_TILE * 2 + 2 * BW_QROWS * BW_SP * 2 + 4 * BW_QROWS * 4 + 2 * ATT_MAXTBL * 4 +
-                      4 * BW_QROWS + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FIBER_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int n_groups = p.G * (p.H / p.ws) * (p.W / p.ws);
-  int gy = num_sms() / p.nH;  // at most one CTA per SM (single wave), persistent over windows
-  if (gy < 1) gy = 1;
-  if (gy > n_groups) gy = n_groups;
-  win_attn_bwd_kernel<<<dim3(p.nH, gy), BW_NWARPS * 32, smem, stream>>>(p, D);
-  FIBER_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 template <int HD, bool WINDOW>
 static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int PITCH = HD + 8;
@@ -746,13 +408,8 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
-bool win_attn_supported(const AttnParams& p, int hd);
-int launch_win_bwd2(const AttnParams& p, float* D, cudaStream_t stream);
-// A/B switch for the round-1 measurements only: FIBER_WINATTN_V1=1 selects the first-generation kernels.
-bool win_attn_use_v1() {
-  static const bool v1 = [] { const char* e = getenv("FIBER_WINATTN_V1"); return e && e[0] == '1'; }();
-  return v1;
-}
+bool win_attn_supported(const AttnParams& p, int hd);                        // window_attn.cu
+int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream);  // window_attn.cu
 
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
@@ -760,8 +417,7 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
   if (p.mode == 1) {
     FIBER_CHECK(hd == 32, "window attention uses head_dim 32");
     FIBER_CHECK(p.dbias_table != nullptr, "window backward needs dbias_table");
-    if (win_attn_supported(p, hd) && d_scratch != nullptr)
-      return win_attn_use_v1() ? launch_win_bwd(p, d_scratch, stream) : launch_win_bwd2(p, d_scratch, stream);
+    if (win_attn_supported(p, hd) && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
   }
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);

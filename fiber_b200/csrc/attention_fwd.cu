@@ -238,223 +238,6 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Window attention forward, specialised: ws*ws <= 144 tokens, head_dim 32.  CTAs are persistent over
-// the windows of one head; the Q/K/V tiles of window i+1 are prefetched with cp.async into the second
-// shared-memory buffer while window i is computed (two CTAs per SM).
-// ---------------------------------------------------------------------------------------------
-constexpr int WF_NWARPS = 9;
-constexpr int WF_ROWS = 16 * WF_NWARPS;  // 144
-constexpr int WF_HD = 32;
-constexpr int WF_PITCH = WF_HD + 8;
-constexpr int WF_TILE = WF_ROWS * WF_PITCH;
-
-__global__ void __launch_bounds__(WF_NWARPS * 32, 2) win_attn_fwd_kernel(const AttnParams p) {
-  constexpr int HD = WF_HD, PITCH = WF_PITCH, CPR = HD / 8;
-  extern __shared__ __align__(16) uint8_t smem[];
-  bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, K, V][144][PITCH]
-  float* sTbl = reinterpret_cast<float*>(tiles + 2 * 3 * WF_TILE);
-  int16_t* sB = reinterpret_cast<int16_t*>(sTbl + ATT_MAXTBL);
-  uint8_t* sRid = reinterpret_cast<uint8_t*>(sB + WF_ROWS);  // [2][144]
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x;
-  const int ws = p.ws, tw2 = 2 * ws - 1, N = p.Lq;
-  const int nWw = p.W / ws, nWh = p.H / ws, nW = nWh * nWw;
-  const int n_groups = p.G * nW;
-  const int n_tiles = (N + 15) / 16;
-  const int nk_pad = ((N + ATT_KCHUNK - 1) / ATT_KCHUNK) * ATT_KCHUNK;
-  const int r_lo = lane >> 2;
-
-  for (int t = tid; t < tw2 * tw2; t += blockDim.x) sTbl[t] = p.bias_table[t * p.nH + h];
-  for (int i = tid; i < WF_ROWS; i += blockDim.x) sB[i] = i < N ? (i / ws) * tw2 + i % ws : 0;
-
-  auto src_row = [&](int g, int i) -> long long {
-    const int b = g / nW, w = g % nW, wh = w / nWw, ww = w % nWw;
-    const int hp = wh * ws + i / ws, wp = ww * ws + i % ws;
-    return static_cast<long long>(b) * p.H * p.W + ((hp + p.shift) % p.H) * p.W + (wp + p.shift) % p.W;
-  };
-  auto prefetch = [&](int g, int buf) {
-    bf16* tb = tiles + buf * 3 * WF_TILE;
-    for (int c = tid; c < WF_ROWS * CPR; c += blockDim.x) {
-      const int r = c / CPR, cc = c % CPR;
-      const bool valid = r < N;
-      const long long grow = valid ? src_row(g, r) : 0;
-      const int col = h * HD + cc * 8;
-      const uint32_t so = smem_u32(tb + r * PITCH + cc * 8);
-      cp_async16(so, p.q + grow * p.ldq + col, valid);
-      cp_async16(so + WF_TILE * 2, p.k + grow * p.ldk + col, valid);
-      cp_async16(so + 2 * WF_TILE * 2, p.v + grow * p.ldv + col, valid);
-    }
-    const int w = g % nW, wh = w / nWw, ww = w % nWw;
-    for (int i = tid; i < WF_ROWS; i += blockDim.x) {
-      int rid = 0;
-      if (i < N) {
-        const int hp = wh * ws + i / ws, wp = ww * ws + i % ws;
-        rid = 3 * ((hp >= p.H - ws) + (hp >= p.H - p.shift)) + (wp >= p.W - ws) + (wp >= p.W - p.shift);
-      }
-      sRid[buf * WF_ROWS + i] = rid;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int it = 0;
-  if (static_cast<int>(blockIdx.y) < n_groups) prefetch(blockIdx.y, 0);
-  for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++it) {
-    const int cur = it & 1;
-    __syncthreads();  // everyone is done with buffer cur^1 (previous window) before it is refilled
-    const int g_next = g + gridDim.y;
-    if (g_next < n_groups) {
-      prefetch(g_next, cur ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp >= n_tiles) continue;
-    bf16* sQ = tiles + cur * 3 * WF_TILE;
-    bf16* sK = sQ + WF_TILE;
-    bf16* sV = sK + WF_TILE;
-    const uint8_t* rid_s = sRid + cur * WF_ROWS;
-    const int wcur = g % nW;
-    const bool has_mask = p.shift > 0 && (wcur / nWw == nWh - 1 || wcur % nWw == nWw - 1);
-
-    uint32_t qf[HD / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-      const int col = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    }
-    const int rl0 = warp * 16 + r_lo;
-    const int aq0 = sB[rl0] + (ws - 1) * (tw2 + 1), aq1 = sB[rl0 + 8] + (ws - 1) * (tw2 + 1);
-    const int rid0 = rid_s[rl0], rid1 = rid_s[rl0 + 8];
-    float m_run[2] = {-1e30f, -1e30f}, l_run[2] = {0.f, 0.f};
-    float oacc[HD / 8][4];
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-
-#pragma unroll 1
-    for (int sub = 0; sub < nk_pad / ATT_KCHUNK; ++sub) {
-      float s[6][4];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
-#pragma unroll
-        for (int nt2 = 0; nt2 < 3; ++nt2) {
-          const int row = sub * ATT_KCHUNK + nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
-          const int col = ks * 16 + ((lane >> 3) & 1) * 8;
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
-          mma16816(s[2 * nt2], qf[ks], b0, b1);
-          mma16816(s[2 * nt2 + 1], qf[ks], b2, b3);
-        }
-      }
-      float mx[2] = {-1e30f, -1e30f};
-#pragma unroll
-      for (int nt = 0; nt < 6; ++nt) {
-        const int j0 = sub * ATT_KCHUNK + nt * 8 + (lane & 3) * 2;
-        const int jj0 = j0 < N ? j0 : 0, jj1 = j0 + 1 < N ? j0 + 1 : 0;
-        const int bj0 = sB[jj0], bj1 = sB[jj1];
-        const int ridj0 = has_mask ? rid_s[jj0] : 0, ridj1 = has_mask ? rid_s[jj1] : 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool hi = e >> 1, odd = e & 1;
-          float v = s[nt][e] * p.scale + sTbl[(hi ? aq1 : aq0) - (odd ? bj1 : bj0)];
-          if (has_mask && (hi ? rid1 : rid0) != (odd ? ridj1 : ridj0)) v += -100.0f;
-          if (j0 + odd >= N) v = -1e30f;
-          s[nt][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
-        }
-      }
-      float corr[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        const float m_new = fmaxf(m_run[r], mx[r]);
-        corr[r] = fast_exp(m_run[r] - m_new);
-        m_run[r] = m_new;
-        l_run[r] *= corr[r];
-      }
-#pragma unroll
-      for (int nt = 0; nt < 6; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pv = fast_exp(s[nt][e] - m_run[e >> 1]);
-          l_run[e >> 1] += pv;
-          s[nt][e] = pv;
-        }
-      }
-#pragma unroll
-      for (int dt = 0; dt < HD / 8; ++dt) {
-        oacc[dt][0] *= corr[0]; oacc[dt][1] *= corr[0];
-        oacc[dt][2] *= corr[1]; oacc[dt][3] *= corr[1];
-      }
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        uint32_t a[4];
-        a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-        for (int dt2 = 0; dt2 < HD / 16; ++dt2) {
-          const int row = sub * ATT_KCHUNK + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int col = dt2 * 16 + (lane >> 4) * 8;
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(smem_u32(sV + row * PITCH + col), b0, b1, b2, b3);
-          mma16816(oacc[2 * dt2], a, b0, b1);
-          mma16816(oacc[2 * dt2 + 1], a, b2, b3);
-        }
-      }
-    }
-    float inv[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float l = l_run[r];
-      l += __shfl_xor_sync(0xffffffffu, l, 1);
-      l += __shfl_xor_sync(0xffffffffu, l, 2);
-      inv[r] = 1.0f / l;
-      const int qi = rl0 + r * 8;
-      if ((lane & 3) == 0 && qi < N && p.lse)
-        p.lse[(static_cast<long long>(g) * p.nH + h) * N + qi] = m_run[r] + __logf(l);
-    }
-    __syncwarp();  // this warp's Q rows are consumed (fragments in registers): reuse them as staging
-#pragma unroll
-    for (int dt = 0; dt < HD / 8; ++dt) {
-      const int col = dt * 8 + (lane & 3) * 2;
-      *reinterpret_cast<uint32_t*>(sQ + rl0 * PITCH + col) = pack_bf16(oacc[dt][0] * inv[0], oacc[dt][1] * inv[0]);
-      *reinterpret_cast<uint32_t*>(sQ + (rl0 + 8) * PITCH + col) = pack_bf16(oacc[dt][2] * inv[1], oacc[dt][3] * inv[1]);
-    }
-    __syncwarp();
-    for (int c = lane; c < 16 * CPR; c += 32) {
-      const int r = c / CPR, cc = c % CPR, i = warp * 16 + r;
-      if (i < N)
-        *reinterpret_cast<uint4*>(p.o + src_row(g, i) * p.ldo + h * HD + cc * 8) =
-            *reinterpret_cast<const uint4*>(sQ + i * PITCH + cc * 8);
-    }
-  }
-}
-
-static int launch_win_fwd(const AttnParams& p, cudaStream_t stream) {
-  const size_t smem = 2 * 3 * WF_TILE * 2 + ATT_MAXTBL * 4 + WF_ROWS * 2 + 2 * WF_ROWS + 32;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FIBER_CUDA(cudaFuncSetAttribute(win_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int n_groups = p.G * (p.H / p.ws) * (p.W / p.ws);
-  int gy = 2 * num_sms() / p.nH;  // two CTAs per SM, single wave, persistent over windows
-  if (gy < 1) gy = 1;
-  if (gy > n_groups) gy = n_groups;
-  win_attn_fwd_kernel<<<dim3(p.nH, gy), WF_NWARPS * 32, smem, stream>>>(p);
-  FIBER_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 template <int HD, int NWARPS>
 static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int QROWS = 16 * NWARPS;
@@ -490,13 +273,12 @@ int attn_check(const AttnParams& p, int hd) {
   return 0;
 }
 
-bool win_attn_supported(const AttnParams& p, int hd);
-int launch_win_fwd2(const AttnParams& p, cudaStream_t stream);
-bool win_attn_use_v1();
+bool win_attn_supported(const AttnParams& p, int hd);             // window_attn.cu
+int launch_win_fwd(const AttnParams& p, cudaStream_t stream);  // window_attn.cu
 
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
-  if (win_attn_supported(p, hd)) return win_attn_use_v1() ? launch_win_fwd(p, stream) : launch_win_fwd2(p, stream);
+  if (win_attn_supported(p, hd)) return launch_win_fwd(p, stream);  // ws*ws <= 144 tokens, head_dim 32
   if (hd == 32) {
     if (p.Lq <= 48) return launch_fwd<32, 3>(p, stream);
     if (p.Lq <= 64) return launch_fwd<32, 4>(p, stream);

@@ -60,6 +60,7 @@ struct LnParams {
   int merge, H, W, Cin;
   const bf16* dy; long long lddy; const bf16* dres; long long lddres; bf16* dx; long long lddx;
   float* dgamma; float* dbeta;
+  const float* row_scale; int rps; bf16* dx2; long long lddx2;
 };
 int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream);
 int colsum_dispatch(const bf16*, long long, long long, int, float*, const float*, const float*, int, cudaStream_t);
@@ -85,6 +86,8 @@ static LnParams to_ln(const fiber_ln_args* a) {
   p.dy = reinterpret_cast<const bf16*>(a->dy); p.lddy = a->lddy;
   p.dres = reinterpret_cast<const bf16*>(a->dres); p.lddres = a->lddres;
   p.dx = reinterpret_cast<bf16*>(a->dx); p.lddx = a->lddx; p.dgamma = a->dgamma; p.dbeta = a->dbeta;
+  p.row_scale = a->row_scale; p.rps = a->rows_per_scale > 0 ? a->rows_per_scale : 1;
+  p.dx2 = reinterpret_cast<bf16*>(a->dx_scaled); p.lddx2 = a->lddxs;
   return p;
 }
 
@@ -143,6 +146,9 @@ int fiber_layernorm_bwd(const fiber_ln_args* a, fiber_stream_t s) {
     fiber::set_last_error("layernorm_bwd: null argument"); return -1;
   }
   if ((a->dgamma == nullptr) != (a->dbeta == nullptr)) { fiber::set_last_error("layernorm_bwd: dgamma/dbeta go together"); return -1; }
+  if ((a->dx_scaled != nullptr) && (a->row_scale == nullptr || a->merge)) {
+    fiber::set_last_error("layernorm_bwd: dx_scaled needs row_scale and plain (non-merging) rows"); return -1;
+  }
   return fiber::ln_dispatch(fiber::to_ln(a), true, FIBER_S(s));
 }
 int fiber_colsum(const void* x, int64_t ld, int64_t m, int32_t n, float* out, const float* scale,

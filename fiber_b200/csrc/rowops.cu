@@ -41,6 +41,11 @@ struct LnParams {
   long long lddx;
   float* dgamma;
   float* dbeta;
+  // optional second backward output: dx2[row,:] = dx[row,:] * row_scale[row / rps] (DropPath of the consumer)
+  const float* row_scale;
+  int rps;
+  bf16* dx2;
+  long long lddx2;
 };
 
 __device__ __forceinline__ long long ln_src_offset(const LnParams& p, long long row, int col) {
@@ -291,6 +296,12 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 2 : 1) ln_bwd_kernel(const L
             const long long off = p.merge ? ln_src_offset(p, row, col) / p.ld1 * p.lddx + (col % p.Cin)
                                           : row * p.lddx + col;
             store8(p.dx + off, dx);
+            if (p.dx2) {  // non-merging rows only (checked at the C-ABI)
+              const float sc = __ldg(p.row_scale + row / p.rps);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dx[e] *= sc;
+              store8(p.dx2 + row * p.lddx2 + col, dx);
+            }
           }
         }
       }
@@ -496,6 +507,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
             dx[e] = fmaf(rs[r], dy[e] * gam[e] - k1 - xhat * k2, rr[e]);
           }
           store8(p.dx + row * p.lddx + col, dx);
+          if (p.dx2) {
+            const float sc = __ldg(p.row_scale + row / p.rps);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dx[e] *= sc;
+            store8(p.dx2 + row * p.lddx2 + col, dx);
+          }
         }
       }
     }
@@ -562,11 +579,11 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
     FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
                 "bad PatchMerging LayerNorm geometry");
   }
-  static const bool fast_on = [] { const char* e = getenv("FIBER_LN_FAST"); return !(e && e[0] == '0'); }();
   const bool plain = !p.merge && !p.in2 && !p.sum_out && ln_aligned16(p.in1, p.ld1) &&
-                     (bwd ? (ln_aligned16(p.dy, p.lddy) && ln_aligned16(p.dres, p.lddres) && ln_aligned16(p.dx, p.lddx))
+                     (bwd ? (ln_aligned16(p.dy, p.lddy) && ln_aligned16(p.dres, p.lddres) && ln_aligned16(p.dx, p.lddx) &&
+                             ln_aligned16(p.dx2, p.lddx2))
                           : ln_aligned16(p.out, p.ldo));
-  if (fast_on && plain) {  // ROWS * VPL = 4 vectors per lane and tensor in flight
+  if (plain) {  // ROWS * VPL = 4 vectors per lane and tensor in flight
     if (p.C == 128) return ln_launch_fast<1, 16, 4>(p, bwd, stream);
     if (p.C == 256) return ln_launch_fast<1, 32, 4>(p, bwd, stream);
     if (p.C == 512) return bwd ? ln_launch_fast<2, 32, 1>(p, true, stream) : ln_launch_fast<2, 32, 2>(p, false, stream);

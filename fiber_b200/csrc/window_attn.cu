@@ -17,8 +17,6 @@
 #include "attention.cuh"
 #include "../../include/fiber_b200.h"
 
-#include <cstdlib>
-
 namespace fiber {
 
 void count_launch(int n = 1);
@@ -204,7 +202,7 @@ __device__ __forceinline__ void wf_tile(const bf16* sQ, const bf16* sK, const bf
   }
 }
 
-__global__ void __launch_bounds__(WF_THREADS, 2) win_attn_fwd2_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(WF_THREADS, 2) win_attn_fwd_kernel(const AttnParams p) {
   constexpr int PITCH = WA_PITCH;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, K, V][144][PITCH]
@@ -310,99 +308,8 @@ __global__ void __launch_bounds__(WF_THREADS, 2) win_attn_fwd2_kernel(const Attn
   }
 }
 
-// =================================================================================================
-// Backward: 12 warps (3 per scheduler), one CTA per SM.  Per window
-//   phase A  27 jobs (16 query rows x 48 keys): S = QK^T and dP = dO V^T start from accumulators
-//            preloaded with -lse/scale and -D, P = exp2(.), dS = P * dP; P and dS go to shared memory
-//            as bf16; d(bias) is summed over all windows of the CTA IN REGISTERS (every thread owns
-//            fixed (i, j) positions of its job slots) and flushed once at the end.
-//   phase B  27 jobs (16 output rows x 32): dV = P^T dO, dK = dS^T Q, dQ = dS K from shared memory;
-//            results leave through a per-warp staging tile as 16-byte stores.
-// Jobs are dealt round-robin (job = warp + 12*slot), which loads the four schedulers 7/7/7/6.
-// Two __syncthreads per window; the next window's tiles stream in during both phases.
-// =================================================================================================
-constexpr int WB_WARPS = 12;
-constexpr int WB_THREADS = WB_WARPS * 32;
 constexpr int WB_ACCP = 146;  // fp32 pitch of the d(bias) flush matrix (144 x 146 x 4 B fits in the P + dS tiles)
 static_assert(WA_ROWS * WB_ACCP * 4 <= 2 * WA_ROWS * WA_SP * 2, "flush matrix must fit in the P / dS tiles");
-
-template <bool MASKED>
-__device__ __forceinline__ void wb_phase_a(const bf16* sQ, const bf16* sdO, const bf16* sK, const bf16* sV, bf16* sP,
-                                           bf16* sdS, const float* lse_s, const float* d_s, const WinTables& T,
-                                           const char* tbl_bytes, int rt, int third, int lane, float scale2,
-                                           float inv_scale, int emask, float (&dbacc)[6][4]) {
-  constexpr int PITCH = WA_PITCH, SP = WA_SP;
-  uint32_t qf[2][4], dof[2][4];
-  {
-    const int row = rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int col = (lane >> 4) * 8;
-    ldsm_x4(smem_u32(sQ + row * PITCH + col), qf[0][0], qf[0][1], qf[0][2], qf[0][3]);
-    ldsm_x4(smem_u32(sQ + row * PITCH + col + 16), qf[1][0], qf[1][1], qf[1][2], qf[1][3]);
-    ldsm_x4(smem_u32(sdO + row * PITCH + col), dof[0][0], dof[0][1], dof[0][2], dof[0][3]);
-    ldsm_x4(smem_u32(sdO + row * PITCH + col + 16), dof[1][0], dof[1][1], dof[1][2], dof[1][3]);
-  }
-  const int rl0 = rt * 16 + (lane >> 2);
-  const int c2 = (lane & 3) * 2;
-  // accumulators start at -lse/scale and -D:  (qk - lse/scale) * scale*log2e + bias2 = score2 - lse2
-  const float nl0 = -lse_s[rl0] * inv_scale, nl1 = -lse_s[rl0 + 8] * inv_scale;
-  const float nd0 = -d_s[rl0], nd1 = -d_s[rl0 + 8];
-  float s[6][4], dp[6][4];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    s[i][0] = s[i][1] = nl0; s[i][2] = s[i][3] = nl1;
-    dp[i][0] = dp[i][1] = nd0; dp[i][2] = dp[i][3] = nd1;
-  }
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-    for (int nt2 = 0; nt2 < 3; ++nt2) {
-      const int row = third * 48 + nt2 * 16 + (lane & 7) + ((lane >> 4) << 3);
-      const int col = ks * 16 + ((lane >> 3) & 1) * 8;
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(smem_u32(sK + row * PITCH + col), b0, b1, b2, b3);
-      mma16816(s[2 * nt2], qf[ks], b0, b1);
-      mma16816(s[2 * nt2 + 1], qf[ks], b2, b3);
-      ldsm_x4(smem_u32(sV + row * PITCH + col), b0, b1, b2, b3);
-      mma16816(dp[2 * nt2], dof[ks], b0, b1);
-      mma16816(dp[2 * nt2 + 1], dof[ks], b2, b3);
-    }
-  }
-  const int aq0 = T.aq4[rl0], aq1 = T.aq4[rl0 + 8];
-  int ci0 = 0, ci1 = 0;
-  if (MASKED) {
-    ci0 = T.code[rl0] & emask;
-    ci1 = T.code[rl0 + 8] & emask;
-  }
-#pragma unroll
-  for (int nt = 0; nt < 6; ++nt) {
-    const int j0 = third * 48 + nt * 8 + c2;
-    const int2 bj = *reinterpret_cast<const int2*>(T.bj4 + j0);
-    int2 cj = make_int2(0, 0);
-    if (MASKED) {
-      cj = *reinterpret_cast<const int2*>(T.code + j0);
-      cj.x &= emask;
-      cj.y &= emask;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const bool hi = e >> 1, odd = e & 1;
-      const float t = *reinterpret_cast<const float*>(tbl_bytes + ((hi ? aq1 : aq0) - (odd ? bj.y : bj.x)));
-      float v = fmaf(s[nt][e], scale2, t);
-      if (MASKED) {
-        if ((hi ? ci1 : ci0) != (odd ? cj.y : cj.x)) v += WA_MASK2;
-      }
-      const float pr = ex2_approx(v);
-      const float ds = pr * dp[nt][e];
-      dbacc[nt][e] += ds;
-      s[nt][e] = pr;
-      dp[nt][e] = ds;
-    }
-    *reinterpret_cast<uint32_t*>(sP + rl0 * SP + j0) = pack_bf16(s[nt][0], s[nt][1]);
-    *reinterpret_cast<uint32_t*>(sP + (rl0 + 8) * SP + j0) = pack_bf16(s[nt][2], s[nt][3]);
-    *reinterpret_cast<uint32_t*>(sdS + rl0 * SP + j0) = pack_bf16(dp[nt][0], dp[nt][1]);
-    *reinterpret_cast<uint32_t*>(sdS + (rl0 + 8) * SP + j0) = pack_bf16(dp[nt][2], dp[nt][3]);
-  }
-}
 
 // type 0: dV[tile] = P^T dO;  type 1: dK[tile] = dS^T Q;  type 2: dQ[tile] = dS K
 __device__ __forceinline__ void wb_phase_b(int type, int tile, int n_tiles, const bf16* sQ, const bf16* sdO,
@@ -445,174 +352,8 @@ __device__ __forceinline__ void wb_phase_b(int type, int tile, int n_tiles, cons
   }
 }
 
-__global__ void __launch_bounds__(WB_THREADS, 1) win_attn_bwd2_kernel(const AttnParams p, const float* __restrict__ Dg) {
-  constexpr int PITCH = WA_PITCH, SP = WA_SP;
-  extern __shared__ __align__(16) uint8_t smem[];
-  bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, dO, K, V][144][PITCH]
-  bf16* sP = tiles + 2 * 4 * WA_TILE;
-  bf16* sdS = sP + WA_ROWS * SP;
-  bf16* stage = sdS + WA_ROWS * SP;             // [12 warps][16][PITCH]
-  float* sLse = reinterpret_cast<float*>(stage + WB_WARPS * 16 * PITCH);  // [2][144]
-  float* sD = sLse + 2 * WA_ROWS;                                          // [2][144]
-  WinTables T;
-  T.tbl2 = sD + 2 * WA_ROWS;
-  T.aq4 = reinterpret_cast<int*>(T.tbl2 + 2 * WA_MAXTBL + 2);
-  T.bj4 = T.aq4 + WA_ROWS;
-  T.code = T.bj4 + WA_ROWS;
-  T.tok = T.code + WA_ROWS;
-  const char* tbl_bytes = reinterpret_cast<const char*>(T.tbl2);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x;
-  const int N = p.Lq;
-  WinGeo geo;
-  geo.H = p.H; geo.W = p.W; geo.ws = p.ws; geo.shift = p.shift;
-  geo.nWw = p.W / p.ws; geo.nWh = p.H / p.ws; geo.nW = geo.nWh * geo.nWw;
-  const int n_groups = p.G * geo.nW;
-  const int n_tiles = (N + 15) / 16;
-  const int n_jobs_a = n_tiles * ((N + 47) / 48);
-  const int n_jobs_b = 3 * n_tiles;
-  const float scale2 = p.scale * WA_LOG2E;
-  const float inv_scale = 1.0f / p.scale;
-  const int tw2 = 2 * p.ws - 1;
-
-  fill_tables(T, p.bias_table, p.nH, h, p.ws, p.shift, N, tid, WB_THREADS);
-
-  float dbacc[3][6][4];
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dbacc[k][i][0] = dbacc[k][i][1] = dbacc[k][i][2] = dbacc[k][i][3] = 0.f;
-
-  // prefetch assignment: 576 16-byte chunks per tile; thread t takes chunk t and (t < 192) chunk t + 384
-  const int pr0 = tid >> 2, pcc = tid & 3;
-  const int pth0 = pr0 / p.ws, ptw0 = pr0 % p.ws;
-  const int pth1 = (pr0 + 96) / p.ws, ptw1 = (pr0 + 96) % p.ws;
-  const int col0 = h * WA_HD + pcc * 8;
-
-  auto prefetch = [&](int g, int buf) {
-    long long img_base; int h0, w0, em;
-    geo.decode(g, img_base, h0, w0, em);
-    bf16* tb = tiles + buf * 4 * WA_TILE;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 1 && tid >= 192) break;
-      const int r = pr0 + 96 * k;
-      const bool valid = r < N;
-      const long long grow = valid ? geo.row(img_base, h0, w0, k ? pth1 : pth0, k ? ptw1 : ptw0) : 0;
-      const uint32_t so = smem_u32(tb + r * PITCH + pcc * 8);
-      cp_async16(so, p.q + grow * p.ldq + col0, valid);
-      cp_async16(so + WA_TILE * 2, p.d_o + grow * p.lddo + col0, valid);
-      cp_async16(so + 2 * WA_TILE * 2, p.k + grow * p.ldk + col0, valid);
-      cp_async16(so + 3 * WA_TILE * 2, p.v + grow * p.ldv + col0, valid);
-      if (pcc == 0) cp_async4(smem_u32(sD + buf * WA_ROWS + r), Dg + grow * p.nH + h, valid);
-      if (pcc == 1)
-        cp_async4(smem_u32(sLse + buf * WA_ROWS + r),
-                  p.lse + (static_cast<long long>(g) * p.nH + h) * N + (valid ? r : 0), valid);
-    }
-    cp_async_commit();
-  };
-
-  int it = 0;
-  if (static_cast<int>(blockIdx.y) < n_groups) prefetch(blockIdx.y, 0);
-  for (int g = blockIdx.y; g < n_groups; g += gridDim.y, ++it) {
-    const int cur = it & 1;
-    cp_async_wait0();
-    __syncthreads();  // (a) tiles[cur] visible; phase B of the previous window is complete everywhere
-    const int g_next = g + gridDim.y;
-    if (g_next < n_groups) prefetch(g_next, cur ^ 1);
-    const bf16* sQ = tiles + cur * 4 * WA_TILE;
-    const bf16* sdO = sQ + WA_TILE;
-    const bf16* sK = sdO + WA_TILE;
-    const bf16* sV = sK + WA_TILE;
-    const float* lse_s = sLse + cur * WA_ROWS;
-    const float* d_s = sD + cur * WA_ROWS;
-    long long img_base; int h0, w0, emask;
-    geo.decode(g, img_base, h0, w0, emask);
-
-    // ================= phase A =================
-#pragma unroll
-    for (int slot = 0; slot < 3; ++slot) {
-      const int job = warp + WB_WARPS * slot;
-      if (job < n_jobs_a) {
-        const int third = job / n_tiles, rt = job - third * n_tiles;
-        if (emask)
-          wb_phase_a<true>(sQ, sdO, sK, sV, sP, sdS, lse_s, d_s, T, tbl_bytes, rt, third, lane, scale2, inv_scale,
-                           emask, dbacc[slot]);
-        else
-          wb_phase_a<false>(sQ, sdO, sK, sV, sP, sdS, lse_s, d_s, T, tbl_bytes, rt, third, lane, scale2, inv_scale,
-                            0, dbacc[slot]);
-      }
-    }
-    __syncthreads();  // (b) P / dS complete
-
-    // ================= phase B =================
-    bf16* stg = stage + warp * 16 * PITCH;
-#pragma unroll 1
-    for (int job = warp; job < n_jobs_b; job += WB_WARPS) {
-      const int type = job / n_tiles, tile = job - type * n_tiles;
-      float acc[4][4];
-      wb_phase_b(type, tile, n_tiles, sQ, sdO, sK, sP, sdS, lane, acc);
-      const float sc = type == 0 ? 1.0f : p.scale;
-      const int r_lo = lane >> 2;
-#pragma unroll
-      for (int dt = 0; dt < 4; ++dt) {
-        const int col = dt * 8 + (lane & 3) * 2;
-        *reinterpret_cast<uint32_t*>(stg + r_lo * PITCH + col) = pack_bf16(acc[dt][0] * sc, acc[dt][1] * sc);
-        *reinterpret_cast<uint32_t*>(stg + (r_lo + 8) * PITCH + col) = pack_bf16(acc[dt][2] * sc, acc[dt][3] * sc);
-      }
-      __syncwarp();
-      bf16* outp = type == 0 ? p.dv : (type == 1 ? p.dk : p.dq);
-      const long long ldo = type == 0 ? p.lddv : (type == 1 ? p.lddk : p.lddq);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c = lane + 32 * k;
-        const int r = c >> 2, cc = c & 3, i = tile * 16 + r;
-        if (i < N) {
-          const int tok = T.tok[i];
-          const long long grow = geo.row(img_base, h0, w0, tok & 255, tok >> 8);
-          *reinterpret_cast<uint4*>(outp + grow * ldo + h * WA_HD + cc * 8) =
-              *reinterpret_cast<const uint4*>(stg + r * PITCH + cc * 8);
-        }
-      }
-      __syncwarp();  // staging tile is free again
-    }
-  }
-
-  // Flush the register-resident d(bias) sums.  Every (i, j) position is owned by exactly one thread, so the
-  // sums go to an fp32 [144][WB_ACCP] matrix aliased onto the P / dS tiles without atomics; each table entry
-  // (dh, dw) is then the sum over the <= 144 token pairs with that offset: one global atomic per entry.
-  cp_async_wait0();
-  __syncthreads();
-  float* sAcc = reinterpret_cast<float*>(sP);
-#pragma unroll
-  for (int slot = 0; slot < 3; ++slot) {
-    const int job = warp + WB_WARPS * slot;
-    if (job < n_jobs_a) {
-      const int third = job / n_tiles, rt = job - third * n_tiles;
-      const int qi = rt * 16 + (lane >> 2);
-#pragma unroll
-      for (int nt = 0; nt < 6; ++nt) {
-        const int j0 = third * 48 + nt * 8 + (lane & 3) * 2;
-        *reinterpret_cast<float2*>(sAcc + qi * WB_ACCP + j0) = make_float2(dbacc[slot][nt][0], dbacc[slot][nt][1]);
-        *reinterpret_cast<float2*>(sAcc + (qi + 8) * WB_ACCP + j0) = make_float2(dbacc[slot][nt][2], dbacc[slot][nt][3]);
-      }
-    }
-  }
-  __syncthreads();
-  const int ws = p.ws;
-  for (int t = tid; t < tw2 * tw2; t += WB_THREADS) {
-    const int dh = t / tw2 - (ws - 1), dw = t % tw2 - (ws - 1);
-    const int ih0 = max(0, dh), ih1 = min(ws, ws + dh), iw0 = max(0, dw), iw1 = min(ws, ws + dw);
-    float sum = 0.f;
-    for (int ih = ih0; ih < ih1; ++ih)
-      for (int iw = iw0; iw < iw1; ++iw) sum += sAcc[(ih * ws + iw) * WB_ACCP + (ih - dh) * ws + (iw - dw)];
-    atomicAdd(&p.dbias_table[t * p.nH + h], sum);
-  }
-}
-
 // =================================================================================================
-// Backward, generation 3: 16 warps (4 per scheduler), ONE __syncthreads per window.
+// Backward: 16 warps (4 per scheduler), one CTA per SM, ONE __syncthreads per window.
 // The 27 score jobs (A) and 27 output jobs (B) of a window form one dependency-ordered list
 //     A(third 0) x9, A(third 1) x9, A(third 2) x9,
 //     [dV, dK](key tiles of third 0), [dV, dK](third 1), [dV, dK](third 2), dQ x9
@@ -706,7 +447,7 @@ __device__ __forceinline__ void w3_job_a(const bf16* sQ, const bf16* sdO, const 
   }
 }
 
-__global__ void __launch_bounds__(W3_THREADS, 1) win_attn_bwd3_kernel(const AttnParams p, const float* __restrict__ Dg) {
+__global__ void __launch_bounds__(W3_THREADS, 1) win_attn_bwd_kernel(const AttnParams p, const float* __restrict__ Dg) {
   constexpr int PITCH = WA_PITCH, SP = WA_SP;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, dO, K, V][144][PITCH]
@@ -874,8 +615,9 @@ __global__ void __launch_bounds__(W3_THREADS, 1) win_attn_bwd3_kernel(const Attn
     }
   }
 
-  // Flush the register-resident d(bias) sums (see win_attn_bwd2_kernel): plain stores into an fp32 matrix
-  // aliased onto the P / dS tiles, then one thread per table entry sums its <= 144 token pairs.
+  // Flush the register-resident d(bias) sums.  Every (i, j) position is owned by exactly one thread, so the
+  // sums go to an fp32 [144][WB_ACCP] matrix aliased onto the P / dS tiles without atomics; each table entry
+  // (dh, dw) is then the sum over the <= 144 token pairs with that offset: one global atomic per entry.
   cp_async_wait0();
   __syncthreads();
   float* sAcc = reinterpret_cast<float*>(sP);
@@ -941,24 +683,24 @@ bool win_attn_supported(const AttnParams& p, int hd) {
   return p.mode == 1 && hd == WA_HD && p.Lq <= WA_ROWS && p.ws <= 12 && p.drop_p == 0.f;
 }
 
-int launch_win_fwd2(const AttnParams& p, cudaStream_t stream) {
+int launch_win_fwd(const AttnParams& p, cudaStream_t stream) {
   const size_t smem = 2 * 3 * WA_TILE * 2 + (2 * WA_MAXTBL + 2) * 4 + 4 * WA_ROWS * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    FIBER_CUDA(cudaFuncSetAttribute(win_attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FIBER_CUDA(cudaFuncSetAttribute(win_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int n_groups = p.G * (p.H / p.ws) * (p.W / p.ws);
   int gy = 2 * num_sms() / p.nH;  // two CTAs per SM, single wave, persistent over windows
   if (gy < 1) gy = 1;
   if (gy > n_groups) gy = n_groups;
-  win_attn_fwd2_kernel<<<dim3(p.nH, gy), WF_THREADS, smem, stream>>>(p);
+  win_attn_fwd_kernel<<<dim3(p.nH, gy), WF_THREADS, smem, stream>>>(p);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-int launch_win_bwd2(const AttnParams& p, float* D, cudaStream_t stream) {
+int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
   const long long rows = static_cast<long long>(p.G) * p.H * p.W;
   const int C = p.nH * WA_HD;
   {
@@ -969,33 +711,18 @@ int launch_win_bwd2(const AttnParams& p, float* D, cudaStream_t stream) {
     FIBER_CUDA(cudaGetLastError());
     count_launch();
   }
-  static const int gen = [] {  // A/B switch for measurements: FIBER_WINATTN_BWD=2 selects the 12-warp kernel
-    const char* e = getenv("FIBER_WINATTN_BWD");
-    return e ? atoi(e) : 3;
-  }();
   const int n_groups = p.G * (p.H / p.ws) * (p.W / p.ws);
   int gy = num_sms() / p.nH;  // one CTA per SM (single wave), persistent over windows
   if (gy < 1) gy = 1;
   if (gy > n_groups) gy = n_groups;
-  const size_t common = 2 * 4 * WA_TILE * 2 + 2 * WA_ROWS * WA_SP * 2 + 4 * WA_ROWS * 4 + (2 * WA_MAXTBL + 2) * 4 +
-                        4 * WA_ROWS * 4;
-  if (gen == 2) {
-    const size_t smem = common + WB_WARPS * 16 * WA_PITCH * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-      FIBER_CUDA(cudaFuncSetAttribute(win_attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
-    win_attn_bwd2_kernel<<<dim3(p.nH, gy), WB_THREADS, smem, stream>>>(p, D);
-  } else {
-    const size_t smem = common + W3_WARPS * W3_STG * 2 + 64 * 4 + 3 * 8 + 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-      FIBER_CUDA(cudaFuncSetAttribute(win_attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
-    win_attn_bwd3_kernel<<<dim3(p.nH, gy), W3_THREADS, smem, stream>>>(p, D);
+  const size_t smem = 2 * 4 * WA_TILE * 2 + 2 * WA_ROWS * WA_SP * 2 + W3_WARPS * W3_STG * 2 + 4 * WA_ROWS * 4 +
+                      (2 * WA_MAXTBL + 2) * 4 + 4 * WA_ROWS * 4 + 64 * 4 + 3 * 8 + 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
   }
+  win_attn_bwd_kernel<<<dim3(p.nH, gy), W3_THREADS, smem, stream>>>(p, D);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

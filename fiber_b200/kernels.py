@@ -200,8 +200,10 @@ def layernorm_fwd(x, gamma, beta, eps, *, add=None, want_sum=False, merge=None, 
     return y, mean, rstd, s
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, merge=None, dres=None, dgamma=None, dbeta=None):
-    """Returns dx (shape of x).  dgamma/dbeta (fp32) are accumulated into when given."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, merge=None, dres=None, dgamma=None, dbeta=None,
+                  row_scale=None, rows_per_scale=1):
+    """Returns dx (shape of x).  dgamma/dbeta (fp32) are accumulated into when given.
+    With row_scale (fp32 per-sample DropPath scales) returns (dx, dx * row_scale[row // rows_per_scale])."""
     _req(dy, BF16, "dy"); _req(x, BF16, "x")
     a = _lib.LnArgs()
     a.in1, a.ld1 = x.data_ptr(), _rowmajor_2d(x, "x")
@@ -221,8 +223,14 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, merge=None, dres=None, 
     if dgamma is not None:
         _req(dgamma, F32, "dgamma"); _req(dbeta, F32, "dbeta")
         a.dgamma, a.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    dxs = None
+    if row_scale is not None:
+        _req(row_scale, F32, "row_scale")
+        dxs = torch.empty_like(x)
+        a.row_scale, a.rows_per_scale = row_scale.data_ptr(), rows_per_scale
+        a.dx_scaled, a.lddxs = dxs.data_ptr(), dxs.stride(0)
     _lib.check(_lib.load().fiber_layernorm_bwd(C.byref(a), _stream()), "layernorm_bwd")
-    return dx
+    return dx if row_scale is None else (dx, dxs)
 
 
 def colsum(x, out=None, scale=None, row_scale=None, rows_per_scale=1):

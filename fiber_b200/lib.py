@@ -61,6 +61,7 @@ class LnArgs(C.Structure):
         ("merge", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
         ("dy", C.c_void_p), ("lddy", C.c_int64), ("dres", C.c_void_p), ("lddres", C.c_int64),
         ("dx", C.c_void_p), ("lddx", C.c_int64), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32), ("dx_scaled", C.c_void_p), ("lddxs", C.c_int64),
     ]
 
 

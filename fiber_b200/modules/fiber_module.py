@@ -123,7 +123,7 @@ class FIBERTransformerSS(LightningModule):
         text_input = concat_all_gather(text_input)
         text_input_mask = concat_all_gather(text_input_mask)
         n = image_feats.shape[0]
-        ptr, total = int(self.queue_ptr), int(self.queue_total)
+        ptr, total = self.queue_counters()
         idx = (ptr + torch.arange(n, device=image_feats.device)) % self.queue_size
         self.image_queue[:, idx] = image_feats.T.float()
         self.text_queue[:, idx] = text_feats.T.float()
@@ -132,6 +132,18 @@ class FIBERTransformerSS(LightningModule):
         self.text_input_mask_queue[idx] = text_input_mask
         self.queue_ptr[0] = (ptr + n) % self.queue_size
         self.queue_total[0] = total + n
+        self._queue_host = ((ptr + n) % self.queue_size, total + n, self.queue_ptr._version, self.queue_total._version)
+
+    def queue_counters(self):
+        """(queue_ptr, queue_total) as Python ints.  The reference reads both device buffers with int(...) every
+        step (fiber_module.py:205, objectives.py:137): three host syncs.  Here the values written by the last
+        _dequeue_and_enqueue are mirrored on the host and re-read from the device only when somebody else
+        modified the buffers (load_state_dict, manual reset), detected through their version counters."""
+        h = getattr(self, "_queue_host", None)
+        if h is None or h[2] != self.queue_ptr._version or h[3] != self.queue_total._version:
+            h = (int(self.queue_ptr), int(self.queue_total), self.queue_ptr._version, self.queue_total._version)
+            self._queue_host = h
+        return h[0], h[1]
 
     def infer(self, batch, mask_text=False, mask_image=False, image_token_type_idx=1, img=None, text_only=False,
               image_only=False):

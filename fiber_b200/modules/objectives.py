@@ -123,7 +123,7 @@ def compute_itc(pl_module, batch):
     loss_t2i = -torch.sum(F.log_softmax(sim_t2i, dim=1) * sim_targets, dim=1).mean()
     loss_itc = (loss_i2t + loss_t2i) / 2.0
     bs = image_feat.size(0)
-    qt = int(pl_module.queue_total[0])
+    qt = pl_module.queue_counters()[1]  # host mirror of queue_total (no device sync in steady state)
     with torch.no_grad():
         weights_i2t = F.softmax(sim_i2t[:, :bs + qt], dim=1)
         weights_t2i = F.softmax(sim_t2i[:, :bs + qt], dim=1)

@@ -351,10 +351,14 @@ class SwinBlockFn(torch.autograd.Function):
         dh = K.gemm(dz, sv["w2_t"], aux=sv["h"], act=K.ACT_GELU_GRAD)
         _wgrad(dh, sv["ln2"], out=g["mlp.fc1.weight"], db=g["mlp.fc1.bias"])
         dln2 = K.gemm(dh, sv["w1_t"])
-        dx1 = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
-                              dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
-        # ---- attention branch: x1 = x + s * (z [+ alpha * y]) ----
-        dZ = K.scale_rows(dx1, s, T) if s is not None else dx1
+        # ---- attention branch: x1 = x + s * (z [+ alpha * y]); the LN backward also emits dZ = s * dx1 ----
+        if s is not None:
+            dx1, dZ = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
+                                      dgamma=g["norm2.weight"], dbeta=g["norm2.bias"], row_scale=s, rows_per_scale=T)
+        else:
+            dx1 = K.layernorm_bwd(dln2, sv["x1"], sv["mean2"], sv["rstd2"], p["norm2.weight"], dres=d_out,
+                                  dgamma=g["norm2.weight"], dbeta=g["norm2.bias"])
+            dZ = dx1
         dtext = None
         if fused:
             alpha = p["attn.alpha_i2t"]

@@ -141,6 +141,12 @@ typedef struct fiber_ln_args {
   int64_t lddx;
   float* dgamma;
   float* dbeta;
+  /* optional second output of the backward: dx_scaled[row,:] = dx[row,:] * row_scale[row / rows_per_scale]
+   * (the DropPath scale of the branch that consumes dx next, swin_transformer.py:390) */
+  const float* row_scale;
+  int32_t rows_per_scale;
+  void* dx_scaled;
+  int64_t lddxs;
 } fiber_ln_args;
 
 int fiber_layernorm_fwd(const fiber_ln_args* args, fiber_stream_t stream);

@@ -125,3 +125,22 @@ def test_embeddings_gather_scatter(cuda_dev):
     (F.embedding(ids, w2, padding_idx=1) + F.embedding(pid, p2, padding_idx=1)).backward(d.float().view(5, L, C))
     _close(dw, w2.grad, 1e-3, "dword")
     _close(dp, p2.grad, 1e-3, "dpos")
+
+
+@pytest.mark.parametrize("rows,C", [(3000, 512), (1200, 128), (720, 1024)])
+def test_layernorm_bwd_scaled_second_output(cuda_dev, rows, C):
+    """layernorm_bwd(row_scale=...) also returns dx * s[row // rps] (the DropPath scale of the consumer branch)."""
+    from fiber_b200 import kernels as K
+    x = _rand((rows, C), cuda_dev, 1)
+    g = _rand((C,), cuda_dev, 3, 0.1, torch.float32) + 1.0
+    b = _rand((C,), cuda_dev, 4, 0.1, torch.float32)
+    dy, dres = _rand((rows, C), cuda_dev, 5), _rand((rows, C), cuda_dev, 6)
+    _, mean, rstd, _ = K.layernorm_fwd(x, g, b, 1e-5)
+    rps = 120
+    s = torch.rand(rows // rps, device=cuda_dev) + 0.5
+    s[1] = 0.0
+    dg, db = torch.zeros_like(g), torch.zeros_like(b)
+    dx0 = K.layernorm_bwd(dy, x, mean, rstd, g, dres=dres)
+    dx, dxs = K.layernorm_bwd(dy, x, mean, rstd, g, dres=dres, dgamma=dg, dbeta=db, row_scale=s, rows_per_scale=rps)
+    assert torch.equal(dx, dx0)
+    _close(dxs, dx0.float() * s.repeat_interleave(rps)[:, None], 1e-2, "dx_scaled")

@@ -2,10 +2,8 @@
 backward time per launch, (window, head) problems per microsecond, and the implied mma.sync TFLOP/s.
 
     python tools/bench_attn.py [images]          # default 64 images
-    FIBER_WINATTN_V1=1 python tools/bench_attn.py   # first-generation kernels (A/B)
 
-Also checks forward/backward against the generic (non-specialised) path is NOT done here — parity is
-tests/test_attention_gpu.py's job; this only measures.
+Parity is tests/test_attention_gpu.py's job; this only measures.
 """
 import os
 import sys
@@ -38,7 +36,7 @@ def timeit(fn, n=5):
     return ts[len(ts) // 2]
 
 
-print("variant:", "v1" if os.environ.get("FIBER_WINATTN_V1") == "1" else "v2", "images:", B)
+print("images:", B)
 for H, C, nh in STAGES:
     for shift in (0, 6):
         if H == 12 and shift:
