@@ -28,6 +28,13 @@ METRIC = "image-text pairs/sec/GPU FIBER-Base 384px fwd+bwd at 1/2/4/8 B200"
 WORKLOAD = "FIBER-Base coarse pretrain step ITM+ITC+MLM (BASELINE configs[1]) 384px/40tok fwd+bwd"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from `ncu --set full`
+# (profiles/r1_gemm_plain_ncu.txt): the step's largest-FLOP shape, Swin stage-2 fc2 dgrad over the 4B-sample pass.
+GEMM_NCU_TRAFFIC = {"dram_bytes": 740.4e6,
+                    "note": "ncu capture of one launch M=147456 N=512 K=2048 (bf16 out): 606.2 MB read + 134.3 MB written "
+                            "vs 757 MB algorithmic (A 604 + B 2 + C 151); part of C was still in L2 at kernel end"}
+
+
 def config(tasks, image_size=384, max_text_len=40):
     """coarse_grained/fiber/config.py:21-92 defaults + task_pretrain_mlm_itm_itc (:95-110)."""
     loss_names = {"itm": 0, "mlm": 0, "itc": 0, "vqa": 0, "nlvr2": 0, "caption_mle": 0, "caption_gold": 0,
@@ -230,6 +237,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: ONE JSON line is the contract
         torch.distributed.init_process_group("nccl", device_id=dev)
     lib.check(lib.load().fiber_init(), "init")
     B, R, L = args.batch, args.image_size, args.text_len
@@ -325,13 +334,15 @@ def run_ours(args):
         # dominant kernel = the tcgen05 GEMM (all of its launches in one step, CUDA events on the launching
         # stream, one extra untimed step): achieved = sum(2MNK) / sum(duration)
         "roofline": {"bound": "tensor", "achieved": gemm_stats["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": gemm_stats["tflops"] / peak_tf, "traffic": None,
+                     "frac": gemm_stats["tflops"] / peak_tf, "traffic": GEMM_NCU_TRAFFIC["dram_bytes"],
+                     "traffic_note": GEMM_NCU_TRAFFIC["note"],
                      "kernel": "fiber::gemm_tcgen05_kernel", "launches_per_step": gemm_stats["launches"],
                      "kernel_ms_per_step": round(gemm_stats["ms"], 2),
                      "algorithmic_gbs": round(gemm_stats["gbs"]), "hbm_frac": gemm_stats["gbs"] / hbm,
-                     "note": "peak = %s bf16 sustained (kernel timed inside a long step); the kernel is HBM-bound "
-                             "on the K<=256 shapes of Swin stages 0/1 (hbm_frac = algorithmic bytes / HBM peak); "
-                             "traffic: see profiles/ (ncu capture per shape)" % ("measured" if peaks else "fallback")},
+                     "note": "achieved = sum(2MNK) / sum(duration) over ALL GEMM launches of one step, CUDA events on "
+                             "the launching stream; peak = %s bf16 sustained (kernel timed inside a long step); "
+                             "the kernel is HBM-bound on the K<=256 shapes of Swin stages 0/1 (hbm_frac = algorithmic "
+                             "bytes / HBM peak)" % ("measured" if peaks else "fallback")},
         "step_roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                           "frac": achieved / peak_tf,
                           "note": "whole step per GPU: pairs/s x 1636.23 GFLOP/pair"},

@@ -1,5 +1,5 @@
 """A few launches of one GEMM shape / epilogue for an `ncu --set full` capture.
-    python tools/ncu_gemm_case.py MODE [M N K]      MODE in plain | bias | gelu | gelu_grad | res"""
+    python tools/ncu_gemm_case.py MODE [M N K]      MODE in plain | bias | gelu | gelu_grad | res | wgrad"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fiber_b200 import kernels as K, lib
@@ -13,6 +13,8 @@ out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
 bias = torch.randn(N, device=dev)
 res = torch.randn(M, N, device=dev).to(torch.bfloat16)
 pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+dw = torch.zeros(N, Kd, device=dev)
+db = torch.zeros(N, device=dev)
 for _ in range(3):
     if mode == "plain":
         K.gemm(x, w, out=out)
@@ -24,4 +26,6 @@ for _ in range(3):
         K.gemm(x, w, bias=bias, preact=pre, act=K.ACT_GELU, out=out)
     elif mode == "gelu_grad":
         K.gemm(x, w, aux=res, act=K.ACT_GELU_GRAD, out=out)
+    elif mode == "wgrad":  # dW[N, Kd] = dY[M, N]^T X[M, Kd] with the fused bias gradient
+        K.gemm(res, x, mn_major=True, accumulate=True, out=dw, colsum=db)
 torch.cuda.synchronize()
