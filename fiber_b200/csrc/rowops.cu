@@ -354,21 +354,44 @@ __device__ __forceinline__ void ldg8f(const float* ptr, float (&x)[8]) {
   x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 
-template <int VPL, int LPR, int ROWS>
+// Row addressing shared by the fast kernels.  Plain rows: element offset = row * ld + col.  PatchMerging rows
+// (MERGE): the 4*Cin columns of merged row (b, h2, w2) are the Cin channels of source tokens
+// (2h2 + (seg & 1), 2w2 + (seg >> 1)), seg = col / Cin (swin_transformer.py:420-427); the two divisions happen
+// once per row, the per-vector part (segment shift, channel offset) is a per-lane constant.
+template <bool MERGE>
+__device__ __forceinline__ long long ln_row_base(const LnParams& p, long long row) {
+  if (!MERGE) return row;
+  const int W2 = p.W / 2, H2 = p.H / 2;
+  const long long b = row / (H2 * W2);
+  const int rem = static_cast<int>(row - b * (H2 * W2));
+  const int h2 = rem / W2, w2 = rem - h2 * W2;
+  return b * p.H * p.W + static_cast<long long>(2 * h2) * p.W + 2 * w2;
+}
+
+template <int VPL, int LPR, int ROWS, bool MERGE>
 __global__ void __launch_bounds__(256, 3) ln_fwd_fast_kernel(const LnParams p) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float invC = 1.0f / p.C;
+  int sadd[VPL], ccol[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (sl + LPR * v) * 8;
+    const int seg = MERGE ? col / p.Cin : 0;
+    sadd[v] = MERGE ? (seg & 1) * p.W + (seg >> 1) : 0;
+    ccol[v] = MERGE ? col - seg * p.Cin : col;
+  }
   for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
     uint4 xp[ROWS][VPL];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const long long row = row0 + r * RPW + sr;
+      const long long base = ln_row_base<MERGE>(p, row < p.rows ? row : 0);
 #pragma unroll
       for (int v = 0; v < VPL; ++v)
-        xp[r][v] = row < p.rows ? *reinterpret_cast<const uint4*>(p.in1 + row * p.ld1 + (sl + LPR * v) * 8)
+        xp[r][v] = row < p.rows ? *reinterpret_cast<const uint4*>(p.in1 + (base + sadd[v]) * p.ld1 + ccol[v])
                                 : make_uint4(0u, 0u, 0u, 0u);
     }
     float s1[ROWS], s2[ROWS];
@@ -419,36 +442,52 @@ __global__ void __launch_bounds__(256, 3) ln_fwd_fast_kernel(const LnParams p) {
   }
 }
 
-template <int VPL, int LPR, int ROWS>
+// SACC: the dgamma / dbeta partial sums of wide rows (VPL >= 3: 48-64 registers) live in a per-warp
+// shared-memory slice instead of registers, which is what lets the packed rows stay register-resident.
+template <int VPL, int LPR, int ROWS, bool MERGE, bool SACC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
   constexpr int RPW = 32 / LPR;
-  extern __shared__ float s_acc[];  // [2][C]: dgamma, dbeta block partials
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  extern __shared__ __align__(16) float s_fast[];  // [2][C] block partials (+ [8 warps][2][C] when SACC)
+  float* s_acc = s_fast;
+  const int n_acc = SACC ? 18 * p.C : 2 * p.C;
+  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
+  float* wacc = s_acc + 2 * p.C + (threadIdx.x >> 5) * 2 * p.C;  // SACC only
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float invC = 1.0f / p.C;
   const bool has_res = p.dres != nullptr;
-  float dg[VPL][8], db[VPL][8];
+  int sadd[VPL], ccol[VPL];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v)
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (sl + LPR * v) * 8;
+    const int seg = MERGE ? col / p.Cin : 0;
+    sadd[v] = MERGE ? (seg & 1) * p.W + (seg >> 1) : 0;
+    ccol[v] = MERGE ? col - seg * p.Cin : col;
+  }
+  float dg[SACC ? 1 : VPL][8], db[SACC ? 1 : VPL][8];
+#pragma unroll
+  for (int v = 0; v < (SACC ? 1 : VPL); ++v)
 #pragma unroll
     for (int e = 0; e < 8; ++e) dg[v][e] = db[v][e] = 0.f;
 
   for (long long row0 = warp_global * (ROWS * RPW); row0 < p.rows; row0 += nwarps * (ROWS * RPW)) {
     uint4 xp[ROWS][VPL], yp[ROWS][VPL], rp[ROWS][VPL];
     float mean[ROWS], rs[ROWS];
+    long long base[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const long long row = row0 + r * RPW + sr;
       const bool rv = row < p.rows;
+      base[r] = ln_row_base<MERGE>(p, rv ? row : 0);
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int col = (sl + LPR * v) * 8;
-        xp[r][v] = rv ? *reinterpret_cast<const uint4*>(p.in1 + row * p.ld1 + col) : make_uint4(0u, 0u, 0u, 0u);
+        const long long src = base[r] + sadd[v];
+        xp[r][v] = rv ? *reinterpret_cast<const uint4*>(p.in1 + src * p.ld1 + ccol[v]) : make_uint4(0u, 0u, 0u, 0u);
         yp[r][v] = rv ? *reinterpret_cast<const uint4*>(p.dy + row * p.lddy + col) : make_uint4(0u, 0u, 0u, 0u);
-        rp[r][v] = (rv && has_res) ? *reinterpret_cast<const uint4*>(p.dres + row * p.lddres + col)
+        rp[r][v] = (rv && has_res) ? *reinterpret_cast<const uint4*>(p.dres + src * p.lddres + ccol[v])
                                    : make_uint4(0u, 0u, 0u, 0u);
       }
       mean[r] = rv ? p.mean[row] : 0.f;
@@ -459,8 +498,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
     for (int r = 0; r < ROWS; ++r) c1[r] = c2[r] = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
+      const int col = (sl + LPR * v) * 8;
       float gam[8];
-      ldg8f(p.gamma + (sl + LPR * v) * 8, gam);
+      ldg8f(p.gamma + col, gam);
+      float tg[8], tb[8];  // this iteration's dgamma / dbeta contribution of vector v (SACC)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tg[e] = tb[e] = 0.f;
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
         float x[8], dy[8];
@@ -472,9 +515,24 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
           const float gy = dy[e] * gam[e];
           c1[r] += gy;
           c2[r] = fmaf(gy, xhat, c2[r]);
-          dg[v][e] = fmaf(dy[e], xhat, dg[v][e]);
-          db[v][e] += dy[e];
+          if (SACC) {
+            tg[e] = fmaf(dy[e], xhat, tg[e]);
+            tb[e] += dy[e];
+          } else {
+            dg[v][e] = fmaf(dy[e], xhat, dg[v][e]);
+            db[v][e] += dy[e];
+          }
         }
+      }
+      if (SACC) {  // lane-private columns of a warp-private slice: plain read-modify-write, no atomics
+        float4* ag = reinterpret_cast<float4*>(wacc + col);
+        float4* ab = reinterpret_cast<float4*>(wacc + p.C + col);
+        float4 g0 = ag[0], g1 = ag[1], b0 = ab[0], b1 = ab[1];
+        g0.x += tg[0]; g0.y += tg[1]; g0.z += tg[2]; g0.w += tg[3];
+        g1.x += tg[4]; g1.y += tg[5]; g1.z += tg[6]; g1.w += tg[7];
+        b0.x += tb[0]; b0.y += tb[1]; b0.z += tb[2]; b0.w += tb[3];
+        b1.x += tb[4]; b1.y += tb[5]; b1.z += tb[6]; b1.w += tb[7];
+        ag[0] = g0; ag[1] = g1; ab[0] = b0; ab[1] = b1;
       }
     }
 #pragma unroll
@@ -506,8 +564,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
             const float xhat = (x[e] - mean[r]) * rs[r];
             dx[e] = fmaf(rs[r], dy[e] * gam[e] - k1 - xhat * k2, rr[e]);
           }
-          store8(p.dx + row * p.lddx + col, dx);
-          if (p.dx2) {
+          store8(p.dx + (base[r] + sadd[v]) * p.lddx + ccol[v], dx);
+          if (!MERGE && p.dx2) {
             const float sc = __ldg(p.row_scale + row / p.rps);
 #pragma unroll
             for (int e = 0; e < 8; ++e) dx[e] *= sc;
@@ -518,19 +576,29 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
     }
   }
   if (p.dgamma) {
+    if (SACC) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
+        float t = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (sl + LPR * v) * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s_acc[col + e], dg[v][e]);
-        atomicAdd(&s_acc[p.C + col + e], db[v][e]);
+        for (int w = 0; w < 8; ++w) t += s_acc[2 * p.C + w * 2 * p.C + i];
+        atomicAdd((i < p.C ? p.dgamma : p.dbeta - p.C) + i, t);
       }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
-      atomicAdd(p.dgamma + i, s_acc[i]);
-      atomicAdd(p.dbeta + i, s_acc[p.C + i]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (sl + LPR * v) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(&s_acc[col + e], dg[v][e]);
+          atomicAdd(&s_acc[p.C + col + e], db[v][e]);
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+        atomicAdd(p.dgamma + i, s_acc[i]);
+        atomicAdd(p.dbeta + i, s_acc[p.C + i]);
+      }
     }
   }
 }
@@ -555,13 +623,23 @@ static int ln_launch(const LnParams& p, bool bwd, cudaStream_t stream) {
   return 0;
 }
 
-template <int VPL, int LPR, int ROWS>
+template <int VPL, int LPR, int ROWS, bool MERGE>
 static int ln_launch_fast(const LnParams& p, bool bwd, cudaStream_t stream) {
   const int rpw = ROWS * (32 / LPR);
   if (!bwd) {
-    ln_fwd_fast_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 3), 256, 0, stream>>>(p);
+    ln_fwd_fast_kernel<VPL, LPR, ROWS, MERGE><<<ln_grid(p.rows, rpw, 3), 256, 0, stream>>>(p);
   } else {
-    ln_bwd_fast_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 2), 256, 2 * p.C * sizeof(float), stream>>>(p);
+    constexpr bool SACC = VPL >= 3;
+    auto kern = ln_bwd_fast_kernel<VPL, LPR, ROWS, MERGE, SACC>;
+    const size_t smem = (SACC ? 18 : 2) * p.C * sizeof(float);
+    if (smem > 48 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 1024 * (int)sizeof(float)));
+        attr_set = true;
+      }
+    }
+    kern<<<ln_grid(p.rows, rpw, 2), 256, smem, stream>>>(p);
   }
   FIBER_CUDA(cudaGetLastError());
   count_launch();
@@ -579,16 +657,21 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
     FIBER_CHECK(p.C == 4 * p.Cin && p.Cin % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && !p.in2,
                 "bad PatchMerging LayerNorm geometry");
   }
-  const bool plain = !p.merge && !p.in2 && !p.sum_out && ln_aligned16(p.in1, p.ld1) &&
-                     (bwd ? (ln_aligned16(p.dy, p.lddy) && ln_aligned16(p.dres, p.lddres) && ln_aligned16(p.dx, p.lddx) &&
-                             ln_aligned16(p.dx2, p.lddx2))
-                          : ln_aligned16(p.out, p.ldo));
-  if (plain) {  // ROWS * VPL = 4 vectors per lane and tensor in flight
-    if (p.C == 128) return ln_launch_fast<1, 16, 4>(p, bwd, stream);
-    if (p.C == 256) return ln_launch_fast<1, 32, 4>(p, bwd, stream);
-    if (p.C == 512) return bwd ? ln_launch_fast<2, 32, 1>(p, true, stream) : ln_launch_fast<2, 32, 2>(p, false, stream);
-    if (!bwd && p.C == 768) return ln_launch_fast<3, 32, 1>(p, false, stream);
-    if (!bwd && p.C == 1024) return ln_launch_fast<4, 32, 1>(p, false, stream);
+  const bool fast = !p.in2 && !p.sum_out && ln_aligned16(p.in1, p.ld1) &&
+                    (bwd ? (ln_aligned16(p.dy, p.lddy) && ln_aligned16(p.dres, p.lddres) && ln_aligned16(p.dx, p.lddx) &&
+                            ln_aligned16(p.dx2, p.lddx2))
+                         : ln_aligned16(p.out, p.ldo));
+  if (fast && !p.merge) {  // ROWS * VPL = up to 4 vectors per lane and tensor in flight
+    if (p.C == 128) return ln_launch_fast<1, 16, 4, false>(p, bwd, stream);
+    if (p.C == 256) return ln_launch_fast<1, 32, 4, false>(p, bwd, stream);
+    if (p.C == 512) return bwd ? ln_launch_fast<2, 32, 1, false>(p, true, stream) : ln_launch_fast<2, 32, 2, false>(p, false, stream);
+    if (p.C == 768) return ln_launch_fast<3, 32, 1, false>(p, bwd, stream);
+    if (p.C == 1024) return ln_launch_fast<4, 32, 1, false>(p, bwd, stream);
+  }
+  if (fast && p.merge) {  // PatchMerging: C = 4 * Cin
+    if (p.C == 256) return ln_launch_fast<1, 32, 4, true>(p, bwd, stream);
+    if (p.C == 512) return bwd ? ln_launch_fast<2, 32, 1, true>(p, true, stream) : ln_launch_fast<2, 32, 2, true>(p, false, stream);
+    if (p.C == 1024) return ln_launch_fast<4, 32, 1, true>(p, bwd, stream);
   }
   // unroll depths picked from tools/bench_ln.py on B200
   if (p.C <= 128) return ln_launch<1, 16, 2>(p, bwd, stream);

@@ -47,22 +47,25 @@ def test_layernorm_fwd_bwd(cuda_dev, rows, C, add):
     _close(db, bf.grad, 1e-2, "dbeta")
 
 
-def test_layernorm_patch_merging(cuda_dev):
+@pytest.mark.parametrize("B,H,C", [(3, 12, 64), (2, 24, 128), (3, 12, 256), (2, 8, 512)])
+def test_layernorm_patch_merging(cuda_dev, B, H, C):
     from fiber_b200 import kernels as K
-    B, H, C = 3, 12, 64
     x = _rand((B * H * H, C), cuda_dev, 1)
     g = _rand((4 * C,), cuda_dev, 3, 0.1, torch.float32) + 1.0
     b = _rand((4 * C,), cuda_dev, 4, 0.1, torch.float32)
     y, mean, rstd, _ = K.layernorm_fwd(x, g, b, 1e-5, merge=(B, H, H))
     xf = x.float().view(B, H * H, C).requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
     xm = xf.view(B, H // 2, 2, H // 2, 2, C).permute(0, 1, 3, 4, 2, 5).reshape(B * (H // 2) ** 2, 4 * C)
-    ref = F.layer_norm(xm, (4 * C,), g, b, 1e-5)
+    ref = F.layer_norm(xm, (4 * C,), gf, bf, 1e-5)
     _close(y, ref, 1e-2, "y")
     dy = _rand(tuple(ref.shape), cuda_dev, 5)
     ref.backward(dy.float())
     dg, db = torch.zeros_like(g), torch.zeros_like(b)
     dx = K.layernorm_bwd(dy, x, mean, rstd, g, merge=(B, H, H), dgamma=dg, dbeta=db)
     _close(dx.view(B, H * H, C), xf.grad, 1.5e-2, "dx")
+    _close(dg, gf.grad, 1e-2, "dgamma")
+    _close(db, bf.grad, 1e-2, "dbeta")
 
 
 def test_colsum_dot_scale_dropout_cast(cuda_dev):
