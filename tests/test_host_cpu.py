@@ -48,6 +48,32 @@ def test_ctypes_structs_match_header_field_order():
         assert names == [f[0] for f in cls._fields_], cname
 
 
+def test_ctypes_struct_layout_matches_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every args struct as gcc lays it out == the ctypes mirrors in fiber_b200/lib.py."""
+    import ctypes
+    import shutil
+    import subprocess
+    from fiber_b200 import lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = (("fiber_gemm_args", lib.GemmArgs), ("fiber_attn_args", lib.AttnArgs), ("fiber_ln_args", lib.LnArgs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fiber_b200.h"', 'int main(void) {']
+    for cname, cls in structs:
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, "%s.%s" % (cname, fname)
+
+
 @pytest.mark.parametrize("fname,tasks,size", [("model_cfg0_224_itm_mlm.pt", ["itm", "mlm"], 224),
                                               ("model_384_infer.pt", ["itm", "mlm", "itc"], 384),
                                               ("model_224_vqa.pt", ["vqa"], 224)])
