@@ -410,6 +410,9 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
 
 bool win_attn_supported(const AttnParams& p, int hd);                        // window_attn.cu
 int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream);  // window_attn.cu
+bool win_attn_tc_supported(const AttnParams& p, int hd, bool bwd);           // window_attn_tc.cu
+int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream);   // window_attn_tc.cu
+int option_winattn_tc();                                                     // capi.cu
 
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
@@ -417,6 +420,8 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
   if (p.mode == 1) {
     FIBER_CHECK(hd == 32, "window attention uses head_dim 32");
     FIBER_CHECK(p.dbias_table != nullptr, "window backward needs dbias_table");
+    if ((option_winattn_tc() & 2) && d_scratch != nullptr && win_attn_tc_supported(p, hd, true))
+      return launch_win_tc_bwd(p, d_scratch, stream);  // opt-in tcgen05 generation
     if (win_attn_supported(p, hd) && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
   }

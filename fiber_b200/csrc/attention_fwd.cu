@@ -275,9 +275,13 @@ int attn_check(const AttnParams& p, int hd) {
 
 bool win_attn_supported(const AttnParams& p, int hd);             // window_attn.cu
 int launch_win_fwd(const AttnParams& p, cudaStream_t stream);  // window_attn.cu
+bool win_attn_tc_supported(const AttnParams& p, int hd, bool bwd);  // window_attn_tc.cu
+int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream);    // window_attn_tc.cu
+int option_winattn_tc();                                            // capi.cu
 
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
+  if ((option_winattn_tc() & 1) && win_attn_tc_supported(p, hd, false)) return launch_win_tc_fwd(p, stream);  // opt-in
   if (win_attn_supported(p, hd)) return launch_win_fwd(p, stream);  // ws*ws <= 144 tokens, head_dim 32
   if (hd == 32) {
     if (p.Lq <= 48) return launch_fwd<32, 3>(p, stream);

@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace fiber {
 
@@ -19,6 +21,19 @@ void set_last_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu).  Default from the
+// environment variable FIBER_WINATTN_TC, else 0 (the mma.sync generation).
+static std::atomic<int> g_winattn_tc{-1};
+int option_winattn_tc() {
+  int v = g_winattn_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_WINATTN_TC");
+    v = e ? (atoi(e) & 3) : 0;
+    g_winattn_tc.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 int num_sms() {
   static int cached[64] = {0};
@@ -102,6 +117,20 @@ extern "C" {
 const char* fiber_last_error(void) { return fiber::g_err; }
 int fiber_version(void) { return 100; }
 int64_t fiber_launch_count(void) { return fiber::g_launches.load(); }
+
+int fiber_set_option(const char* name, int32_t value) {
+  if (name && strcmp(name, "winattn_tc") == 0) {
+    fiber::g_winattn_tc.store(value & 3, std::memory_order_relaxed);
+    return 0;
+  }
+  fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
+  return -1;
+}
+int fiber_get_option(const char* name) {
+  if (name && strcmp(name, "winattn_tc") == 0) return fiber::option_winattn_tc();
+  fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
+  return -1;
+}
 
 int fiber_init(void) {
   int dev = 0;

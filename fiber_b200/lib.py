@@ -86,6 +86,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.fiber_last_error.restype = C.c_char_p
     lib.fiber_launch_count.restype = C.c_int64
+    lib.fiber_set_option.argtypes = [C.c_char_p, C.c_int32]
+    lib.fiber_get_option.argtypes = [C.c_char_p]
     lib.fiber_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.fiber_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.fiber_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
@@ -113,3 +115,15 @@ def check(rc, what):
 
 def launch_count():
     return int(load().fiber_launch_count())
+
+
+def set_option(name, value):
+    """Process-wide kernel selection (include/fiber_b200.h: fiber_set_option), e.g. ("winattn_tc", 3)."""
+    check(load().fiber_set_option(name.encode(), int(value)), "set_option")
+
+
+def get_option(name):
+    v = load().fiber_get_option(name.encode())
+    if v < 0:
+        raise RuntimeError("fiber_b200.get_option failed: %s" % load().fiber_last_error().decode())
+    return int(v)

@@ -29,6 +29,13 @@ int fiber_version(void);
 int fiber_init(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t fiber_launch_count(void);
+/* Process-wide kernel selection.  "winattn_tc": bit 0 / bit 1 route the forward / backward of 12x12-window
+ * attention (fiber_attn_fwd / fiber_attn_bwd, mode 1, head_dim 32) to the tcgen05 generation
+ * (csrc/window_attn_tc.cu) instead of the mma.sync one; default 0, or the FIBER_WINATTN_TC environment variable.
+ * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
+ * fiber_get_option returns the value. */
+int fiber_set_option(const char* name, int32_t value);
+int fiber_get_option(const char* name);
 
 /* ---- GEMM on tcgen05 tensor cores --------------------------------------------------------
  * C[M,N] = epilogue(A * B^T), bf16 operands, fp32 accumulate in TMEM.
