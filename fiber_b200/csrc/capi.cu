@@ -25,6 +25,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu).  Default from the
 // environment variable FIBER_WINATTN_TC, else 0 (the mma.sync generation).
 static std::atomic<int> g_winattn_tc{-1};
+static std::atomic<int> g_winattn_tc_launches{0};  // launches of the tcgen05 generation (tests check the routing)
+void count_winattn_tc_launch() { g_winattn_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 int option_winattn_tc() {
   int v = g_winattn_tc.load(std::memory_order_relaxed);
   if (v < 0) {
@@ -128,6 +130,7 @@ int fiber_set_option(const char* name, int32_t value) {
 }
 int fiber_get_option(const char* name) {
   if (name && strcmp(name, "winattn_tc") == 0) return fiber::option_winattn_tc();
+  if (name && strcmp(name, "winattn_tc_launches") == 0) return fiber::g_winattn_tc_launches.load();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;
 }

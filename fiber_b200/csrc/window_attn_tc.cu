@@ -31,37 +31,26 @@
 //   warp  9     cp.async loader of the gathered Q / K / V (/ dO) tiles (cyclic shift + partition in the address)
 //   warps 10-11 remainder rows / keys on mma.sync
 #include "window_common.cuh"
+#include "window_tc_layout.cuh"
 #include "../../include/fiber_b200.h"
 
 namespace fiber {
 
 void count_launch(int n = 1);
+void count_winattn_tc_launch();  // capi.cu
 int launch_win_bwd_prep(const AttnParams& p, float* D, cudaStream_t stream);  // window_attn.cu
 
 namespace {
 
-constexpr int TC_N = 144;                 // tokens per window
-constexpr int TC_WS = 12;
+using namespace tcl;  // layouts and descriptor builders (window_tc_layout.cuh)
+
+constexpr int TC_N = tcl::N;              // tokens per window
+constexpr int TC_WS = tcl::WS;
 constexpr int TC_TW2 = 2 * TC_WS - 1;     // 23
-constexpr int TC_TILE = TC_N * 64;        // bytes of one [144][32] bf16 tile
+constexpr int TC_TILE = tcl::TILE;        // bytes of one [144][32] bf16 tile
 constexpr int TC_THREADS = 384;
 constexpr int TC_WARP_MMA = 8, TC_WARP_LD = 9, TC_WARP_R0 = 10;
-constexpr uint32_t UMMA_LAYOUT_SW128 = 2, UMMA_LAYOUT_SW64 = 4;
 constexpr int TC_TABLE_BYTES = (2 * WA_MAXTBL + 2) * 4 + 4 * WA_ROWS * 4;  // WinTables: tbl2, aq4, bj4, code, tok
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(layout) << 61;
-  return d;
-}
-// byte offset of 16-byte piece `piece` (8 bf16) of row `row`
-__device__ __forceinline__ uint32_t sw64_off(int row, int piece) { return row * 64 + ((piece ^ ((row >> 1) & 3)) << 4); }
-__device__ __forceinline__ uint32_t sw128_off(int row, int piece) { return row * 128 + ((piece ^ (row & 7)) << 4); }
 
 __device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -120,7 +109,7 @@ __device__ __forceinline__ float tc_scores(uint32_t (&v)[72], const char* tbl_i,
 // =================================================================================================
 constexpr int TF_STAGES = 3;
 constexpr int TF_STAGE_BYTES = 3 * TC_TILE;                 // Q, K, V
-constexpr int TF_PCHUNK = 128 * 128;                        // P chunk: 128 query rows x 64 keys
+constexpr int TF_PCHUNK = tcl::F_PCHUNK;                    // P chunk: 128 query rows x 64 keys
 constexpr int TF_OFF_P = TF_STAGES * TF_STAGE_BYTES;        // 82944
 constexpr int TF_OFF_TBL = TF_OFF_P + 3 * TF_PCHUNK;        // 132096
 constexpr int TF_OFF_RMAX = TF_OFF_TBL + ((TC_TABLE_BYTES + 15) & ~15);
@@ -379,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
         o.y = pack_bf16(pr[2], pr[3]);
         o.z = pack_bf16(pr[4], pr[5]);
         o.w = pack_bf16(pr[6], pr[7]);
-        *reinterpret_cast<uint4*>(sP + (p8 >> 3) * TF_PCHUNK + sw128_off(row, p8 & 7)) = o;
+        *reinterpret_cast<uint4*>(sP + pds_piece_off(row, p8, TF_PCHUNK)) = o;
       }
       rowsum[(b * 2 + hf) * 128 + row] = sum;
       fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
@@ -409,8 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
         const uint32_t d = tmem_base + (b ? TF_S_COL1 : TF_S_COL0);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          umma_f16_ss(d, umma_desc(q_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64),
-                      umma_desc(k_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_s, ks);
+          umma_f16_ss(d, desc_tile_kmajor(q_addr, ks), desc_tile_kmajor(k_addr, ks), idesc_s, ks);
         umma_commit(&s_full[b]);
       }
       __syncwarp();
@@ -426,9 +414,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
         const uint32_t v_addr = smem_u32(smem + s * TF_STAGE_BYTES + 2 * TC_TILE), p_addr = smem_u32(sP);
 #pragma unroll
         for (int kk = 0; kk < 9; ++kk)  // 16 keys per step
-          umma_f16_ss(tmem_base + TF_O_COL,
-                      umma_desc(p_addr + (kk >> 2) * TF_PCHUNK + (kk & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                      umma_desc(v_addr + kk * 1024, 512, 512, UMMA_LAYOUT_SW64), idesc_o, kk);
+          umma_f16_ss(tmem_base + TF_O_COL, desc_pds_kmajor(p_addr, kk, TF_PCHUNK), desc_tile_mnmajor(v_addr, kk),
+                      idesc_o, kk);
         umma_commit(o_full);
         umma_commit(&stage_free[s]);
       }
@@ -537,7 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
 // =================================================================================================
 constexpr int TB_STAGES = 2;
 constexpr int TB_STAGE_BYTES = 4 * TC_TILE;                 // Q, dO, K, V
-constexpr int TB_PCHUNK = TC_N * 128;                       // P / dS chunk: 144 query rows x 64 keys (18432 B)
+constexpr int TB_PCHUNK = tcl::B_PCHUNK;                    // P / dS chunk: 144 query rows x 64 keys (18432 B)
 constexpr int TB_OFF_P = TB_STAGES * TB_STAGE_BYTES;        // 73728
 constexpr int TB_OFF_DS = TB_OFF_P + 3 * TB_PCHUNK;         // 129024
 constexpr int TB_OFF_STG = TB_OFF_DS + 3 * TB_PCHUNK;       // 184320: [2 remainder warps][16 rows][64 B]
@@ -549,11 +536,6 @@ constexpr int TB_ACCP = 146;  // fp32 pitch of the d(bias) flush matrix aliased 
 static_assert(TC_N * TB_ACCP * 4 <= 6 * TB_PCHUNK, "flush matrix must fit in the P / dS chunks");
 static_assert(TB_SMEM <= 227 * 1024, "backward shared memory");
 static_assert(TF_SMEM <= 227 * 1024, "forward shared memory");
-
-// address of the 4-byte pair (key j0, j0 + 1), j0 even, of query row `row` in a P / dS chunk set
-__device__ __forceinline__ uint32_t pds_off(int row, int j0) {
-  return (j0 >> 6) * TB_PCHUNK + sw128_off(row, (j0 & 63) >> 3) + (j0 & 7) * 2;
-}
 
 // The 72 key columns [HF * 72, +72) of one query row in nine 8-column pieces (= one 16-byte store each): P, dS,
 // d(bias) sums.  The TMEM loads of piece k + 1 are in flight while piece k is computed.
@@ -584,7 +566,7 @@ __device__ __forceinline__ void tc_bwd_row(uint32_t lane_addr, uint8_t* sP, uint
       dbacc[8 * k + e] += ds[e];
     }
     const int p8 = HF * 9 + k;  // 16-byte piece (8 keys) of the 144-key row
-    const uint32_t off = (p8 >> 3) * TB_PCHUNK + sw128_off(row, p8 & 7);
+    const uint32_t off = pds_piece_off(row, p8, TB_PCHUNK);
     uint4 a, b;
     a.x = pack_bf16(pr[0], pr[1]); a.y = pack_bf16(pr[2], pr[3]);
     a.z = pack_bf16(pr[4], pr[5]); a.w = pack_bf16(pr[6], pr[7]);
@@ -664,10 +646,10 @@ __device__ __forceinline__ void tc_bwd_rem_scores(uint32_t sQ, uint32_t sdO, uin
         s[i][e] = pr;
         dp[i][e] = ds;
       }
-      *reinterpret_cast<uint32_t*>(sP + pds_off(rl0, j0)) = pack_bf16(s[i][0], s[i][1]);
-      *reinterpret_cast<uint32_t*>(sP + pds_off(rl0 + 8, j0)) = pack_bf16(s[i][2], s[i][3]);
-      *reinterpret_cast<uint32_t*>(sdS + pds_off(rl0, j0)) = pack_bf16(dp[i][0], dp[i][1]);
-      *reinterpret_cast<uint32_t*>(sdS + pds_off(rl0 + 8, j0)) = pack_bf16(dp[i][2], dp[i][3]);
+      *reinterpret_cast<uint32_t*>(sP + pds_off(rl0, j0, TB_PCHUNK)) = pack_bf16(s[i][0], s[i][1]);
+      *reinterpret_cast<uint32_t*>(sP + pds_off(rl0 + 8, j0, TB_PCHUNK)) = pack_bf16(s[i][2], s[i][3]);
+      *reinterpret_cast<uint32_t*>(sdS + pds_off(rl0, j0, TB_PCHUNK)) = pack_bf16(dp[i][0], dp[i][1]);
+      *reinterpret_cast<uint32_t*>(sdS + pds_off(rl0 + 8, j0, TB_PCHUNK)) = pack_bf16(dp[i][2], dp[i][3]);
     }
   }
 }
@@ -735,7 +717,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
   uint64_t* pds_ready = bars + 6;   //     P and dS complete in smem                         (8 + 2 warps)
   uint64_t* acc_full = bars + 7;    //     dV / dK / dQ accumulators written, P / dS consumed (commit)
   uint64_t* acc_empty = bars + 8;   //     accumulators drained                              (8 element-wise warps)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* rem_done = bars + 9;    //     remainder warps have read P / dS of the window    (2 remainder warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x;
@@ -758,6 +741,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       mbar_init(pds_ready, 10);
       mbar_init(acc_full, 1);
       mbar_init(acc_empty, 8);
+      mbar_init(rem_done, 2);
       mbar_fence_init();
     }
     __syncwarp();
@@ -801,7 +785,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
 
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      // P / dS buffers are free: this thread waited for acc_full of the previous window in its drain below
+      // P / dS buffers are free: the tensor core is done with them (this thread waited for acc_full of the previous
+      // window in its drain below) and so are the remainder warps' output jobs
+      if (it > 0) mbar_wait(rem_done, (it - 1) & 1);
       if (hf == 0) {
         if (emask) tc_bwd_row<0, true>(lane_addr, sP, sdS, row, tbl_i, scale2, nlse2, negD, madd, dbacc);
         else       tc_bwd_row<0, false>(lane_addr, sP, sdS, row, tbl_i, scale2, nlse2, negD, madd, dbacc);
@@ -862,12 +848,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       if (lane == 0) {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          umma_f16_ss(tmem_base + TB_S_COL, umma_desc(q_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64),
-                      umma_desc(k_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_s, ks);
+          umma_f16_ss(tmem_base + TB_S_COL, desc_tile_kmajor(q_addr, ks), desc_tile_kmajor(k_addr, ks), idesc_s, ks);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          umma_f16_ss(tmem_base + TB_DP_COL, umma_desc(do_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64),
-                      umma_desc(v_addr + ks * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_s, ks);
+          umma_f16_ss(tmem_base + TB_DP_COL, desc_tile_kmajor(do_addr, ks), desc_tile_kmajor(v_addr, ks), idesc_s, ks);
         umma_commit(s_full);
       }
       __syncwarp();
@@ -877,16 +861,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < 9; ++kk) {  // 16 queries per step
-          umma_f16_ss(tmem_base + TB_DV_COL, umma_desc(p_addr + kk * 2048, TB_PCHUNK, 1024, UMMA_LAYOUT_SW128),
-                      umma_desc(do_addr + kk * 1024, 512, 512, UMMA_LAYOUT_SW64), idesc_kv, kk);
-          umma_f16_ss(tmem_base + TB_DK_COL, umma_desc(ds_addr + kk * 2048, TB_PCHUNK, 1024, UMMA_LAYOUT_SW128),
-                      umma_desc(q_addr + kk * 1024, 512, 512, UMMA_LAYOUT_SW64), idesc_kv, kk);
+          umma_f16_ss(tmem_base + TB_DV_COL, desc_pds_mnmajor(p_addr, kk), desc_tile_mnmajor(do_addr, kk), idesc_kv, kk);
+          umma_f16_ss(tmem_base + TB_DK_COL, desc_pds_mnmajor(ds_addr, kk), desc_tile_mnmajor(q_addr, kk), idesc_kv, kk);
         }
 #pragma unroll
         for (int kk = 0; kk < 9; ++kk)  // 16 keys per step
-          umma_f16_ss(tmem_base + TB_DQ_COL,
-                      umma_desc(ds_addr + (kk >> 2) * TB_PCHUNK + (kk & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                      umma_desc(k_addr + kk * 1024, 512, 512, UMMA_LAYOUT_SW64), idesc_q, kk);
+          umma_f16_ss(tmem_base + TB_DQ_COL, desc_pds_kmajor(ds_addr, kk, TB_PCHUNK), desc_tile_mnmajor(k_addr, kk),
+                      idesc_q, kk);
         umma_commit(acc_full);
         umma_commit(&stage_free[s]);
       }
@@ -1000,7 +981,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
         }
         __syncwarp();  // staging tile is free again
       }
-      if (lane == 0) mbar_arrive(&stage_free[s]);
+      if (lane == 0) {
+        mbar_arrive(&stage_free[s]);
+        mbar_arrive(rem_done);
+      }
     }
     named_bar_sync(6, TC_THREADS);
     const int qi = 128 + (lane >> 2);
@@ -1073,6 +1057,7 @@ int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream) {
   win_attn_tc_fwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TF_SMEM, stream>>>(p);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
+  count_winattn_tc_launch();
   return 0;
 }
 
@@ -1086,6 +1071,7 @@ int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
   win_attn_tc_bwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TB_SMEM, stream>>>(p, D);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
+  count_winattn_tc_launch();
   return 0;
 }
 

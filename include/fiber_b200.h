@@ -33,7 +33,7 @@ int64_t fiber_launch_count(void);
  * attention (fiber_attn_fwd / fiber_attn_bwd, mode 1, head_dim 32) to the tcgen05 generation
  * (csrc/window_attn_tc.cu) instead of the mma.sync one; default 0, or the FIBER_WINATTN_TC environment variable.
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
- * fiber_get_option returns the value. */
+ * fiber_get_option returns the value ("winattn_tc_launches", read-only: launches of the tcgen05 generation so far). */
 int fiber_set_option(const char* name, int32_t value);
 int fiber_get_option(const char* name);
 

@@ -1,5 +1,6 @@
 """Attention kernels (window + plain modes) vs the oracle's fp32 formulation on bf16 inputs (GPU)."""
 import math
+import os
 
 import pytest
 import torch
@@ -21,10 +22,41 @@ def _close(a, b, tol, name):
     assert err <= tol * max(ref, 1e-3), "%s: max err %g vs ref max %g" % (name, err, ref)
 
 
-@pytest.mark.parametrize("B,H,ws,shift,nh", [(2, 24, 12, 0, 2), (2, 24, 12, 6, 2), (3, 14, 7, 3, 4), (1, 12, 12, 0, 3),
-                                             (2, 96, 12, 6, 4), (1, 36, 18, 9, 2), (2, 18, 18, 0, 3),
-                                             (8, 48, 12, 6, 8), (4, 28, 7, 0, 4), (2, 48, 12, 5, 2)])
+WINDOW_CASES = [(2, 24, 12, 0, 2), (2, 24, 12, 6, 2), (3, 14, 7, 3, 4), (1, 12, 12, 0, 3),
+                (2, 96, 12, 6, 4), (1, 36, 18, 9, 2), (2, 18, 18, 0, 3),
+                (8, 48, 12, 6, 8), (4, 28, 7, 0, 4), (2, 48, 12, 5, 2)]
+
+
+@pytest.mark.parametrize("B,H,ws,shift,nh", WINDOW_CASES)
 def test_window_attention_fwd_bwd(cuda_dev, B, H, ws, shift, nh):
+    _window_case(cuda_dev, B, H, ws, shift, nh)
+
+
+# The tcgen05 generation (csrc/window_attn_tc.cu) is opt-in until it has been validated on a B200: run with
+# FIBER_B200_EXPERIMENTAL=1 (tools/gpu_round2a.sh does).  Cases it does not cover (ws != 12, odd shifts) must
+# fall through to the mma.sync kernels with the option set, so every case runs; the 12x12 ones must launch it.
+TC_CASES = WINDOW_CASES + [(64, 12, 12, 0, 32), (5, 96, 12, 6, 4), (3, 24, 12, 6, 16), (1, 48, 12, 0, 8)]
+
+
+@pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: tcgen05 window attention not yet validated on hardware (FIBER_B200_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("B,H,ws,shift,nh", TC_CASES)
+def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
+    from fiber_b200 import lib
+    before = lib.get_option("winattn_tc_launches")
+    lib.set_option("winattn_tc", mode)
+    try:
+        _window_case(cuda_dev, B, H, ws, shift, nh)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("winattn_tc", 0)
+    launched = lib.get_option("winattn_tc_launches") - before
+    covered = ws == 12 and shift in (0, 6)
+    assert launched == ((mode & 1) + (mode >> 1) if covered else 0)
+
+
+def _window_case(cuda_dev, B, H, ws, shift, nh):
     from fiber_b200 import kernels as K
     hd = 32
     C = nh * hd
