@@ -40,7 +40,7 @@ TC_CASES = WINDOW_CASES + [(64, 12, 12, 0, 32), (5, 96, 12, 6, 4), (3, 24, 12, 6
 
 @pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
                     reason="opt-in: tcgen05 window attention not yet validated on hardware (FIBER_B200_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["tcfwd", "tcbwd", "tcboth"])
 @pytest.mark.parametrize("B,H,ws,shift,nh", TC_CASES)
 def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
     from fiber_b200 import lib

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round 2, first GPU call: validate the opt-in tcgen05 window attention (csrc/window_attn_tc.cu) bottom-up.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round2a.sh'
+# 1. UMMA operand-form probe (which descriptor assumption is wrong, if any)
+# 2. parity of the tcgen05 kernels against the oracle formulation, forward-only / backward-only / both
+# 3. micro-benchmark of both generations at FIBER's stage shapes, then the full bench with the option on
+# Every step runs under its own timeout; a protocol bug becomes an mbarrier-timeout trap, not a hung GPU.
+mkdir -p gpurun_out
+python -m fiber_b200.build > gpurun_out/r2a_build.log 2>&1
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr \
+    -o tools/umma_probe.bin tools/umma_probe.cu >> gpurun_out/r2a_build.log 2>&1
+timeout 120 tools/umma_probe.bin > gpurun_out/r2a_probe.txt 2>&1; echo "probe exit $?" >> gpurun_out/r2a_probe.txt
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcfwd \
+    > gpurun_out/r2a_tc_fwd.log 2>&1
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcbwd \
+    > gpurun_out/r2a_tc_bwd.log 2>&1
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcboth \
+    > gpurun_out/r2a_tc_both.log 2>&1
+timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_mma_sync.txt 2>&1
+FIBER_WINATTN_TC=1 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc_fwd.txt 2>&1
+FIBER_WINATTN_TC=3 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc.txt 2>&1
+FIBER_WINATTN_TC=3 timeout 900 python bench.py > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
+tail -n 3 gpurun_out/r2a_probe.txt gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log
+cat gpurun_out/r2a_attn_mma_sync.txt gpurun_out/r2a_attn_tc.txt
