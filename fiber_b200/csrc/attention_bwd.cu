@@ -16,12 +16,17 @@ namespace fiber {
 void count_launch(int n = 1);
 int attn_check(const AttnParams& p, int hd);
 
-constexpr int BW_NWARPS = 9;
-constexpr int BW_QROWS = 16 * BW_NWARPS;  // 144
-constexpr int BW_SP = ATT_SKEYS + 8;       // pitch of the P / dS tiles (elements)
-
-template <int HD, bool WINDOW>
-__global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnParams p) {
+// NW warps = 16 * NW query rows per chunk, SK keys staged per chunk.  <9, 144> is the general configuration
+// (one CTA per SM); <3, 48> serves problems with at most 48 queries and 48 keys (RoBERTa self-attention at 40
+// tokens: 3072 (sample, head) problems per launch) with four CTAs per SM instead of one two-thirds-idle CTA.
+template <int HD, bool WINDOW, int NW = 9, int SK = ATT_SKEYS>
+__global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : 4) attn_bwd_kernel(const AttnParams p) {
+  constexpr int BW_NWARPS = NW;
+  constexpr int BW_QROWS = 16 * NW;
+  constexpr int ATT_SKEYS = SK;        // shadows the global constant inside this kernel
+  constexpr int BW_SP = SK + 8;        // pitch of the P / dS tiles (elements)
+  static_assert(SK % ATT_KCHUNK == 0 && SK / 16 <= NW, "one key tile per warp in phase B");
+  static_assert(!WINDOW || SK == 144, "window mode sizes its d(bias) registers for 144-key chunks");
   constexpr int PITCH = HD + 8;
   constexpr int CPR = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -380,8 +385,12 @@ __global__ void __launch_bounds__(BW_NWARPS * 32, 1) attn_bwd_kernel(const AttnP
 }
 
 
-template <int HD, bool WINDOW>
+template <int HD, bool WINDOW, int NW = 9, int SK = ATT_SKEYS>
 static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
+  constexpr int BW_NWARPS = NW;
+  constexpr int BW_QROWS = 16 * NW;
+  constexpr int ATT_SKEYS = SK;
+  constexpr int BW_SP = SK + 8;
   constexpr int PITCH = HD + 8;
   const int nqc = (p.Lq + BW_QROWS - 1) / BW_QROWS, nkc = (p.Lk + ATT_SKEYS - 1) / ATT_SKEYS;
   const size_t base = (2 * BW_QROWS + 2 * ATT_SKEYS) * PITCH * 2 + 2 * BW_QROWS * BW_SP * 2 +
@@ -389,7 +398,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
                       3 * ATT_MAXTOK + 32;
   const size_t smem = base + ((nqc > 1 && nkc > 1) ? static_cast<size_t>(nqc) * BW_QROWS * HD * 4 : 0);
   FIBER_CHECK(smem <= 227 * 1024, "attention backward: Lq=%d with Lk=%d needs %zu bytes of shared memory", p.Lq, p.Lk, smem);
-  auto kern = attn_bwd_kernel<HD, WINDOW>;
+  auto kern = attn_bwd_kernel<HD, WINDOW, NW, SK>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -413,6 +422,7 @@ int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream);  // wind
 bool win_attn_tc_supported(const AttnParams& p, int hd, bool bwd);           // window_attn_tc.cu
 int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream);   // window_attn_tc.cu
 int option_winattn_tc();                                                     // capi.cu
+int option_attn_small();                                                     // capi.cu
 
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
@@ -425,6 +435,8 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
     if (win_attn_supported(p, hd) && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
   }
+  // opt-in: at most 48 queries and keys (RoBERTa self-attention at 40 tokens) on 3-warp CTAs, four per SM
+  if (hd == 64 && p.Lq <= 48 && p.Lk <= 48 && option_attn_small()) return launch_bwd<64, false, 3, 48>(p, stream);
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);
 }
 

@@ -25,6 +25,18 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu).  Default from the
 // environment variable FIBER_WINATTN_TC, else 0 (the mma.sync generation).
 static std::atomic<int> g_winattn_tc{-1};
+// "attn_small": 1 routes plain attention backward with <= 48 queries and keys (head_dim 64) to the 3-warp
+// configuration of attention_bwd.cu.  Default from FIBER_ATTN_SMALL, else 0.
+static std::atomic<int> g_attn_small{-1};
+int option_attn_small() {
+  int v = g_attn_small.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_ATTN_SMALL");
+    v = e ? (atoi(e) & 1) : 0;
+    g_attn_small.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 static std::atomic<int> g_winattn_tc_launches{0};  // launches of the tcgen05 generation (tests check the routing)
 void count_winattn_tc_launch() { g_winattn_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 int option_winattn_tc() {
@@ -125,11 +137,16 @@ int fiber_set_option(const char* name, int32_t value) {
     fiber::g_winattn_tc.store(value & 3, std::memory_order_relaxed);
     return 0;
   }
+  if (name && strcmp(name, "attn_small") == 0) {
+    fiber::g_attn_small.store(value & 1, std::memory_order_relaxed);
+    return 0;
+  }
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;
 }
 int fiber_get_option(const char* name) {
   if (name && strcmp(name, "winattn_tc") == 0) return fiber::option_winattn_tc();
+  if (name && strcmp(name, "attn_small") == 0) return fiber::option_attn_small();
   if (name && strcmp(name, "winattn_tc_launches") == 0) return fiber::g_winattn_tc_launches.load();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;

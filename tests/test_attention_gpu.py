@@ -105,6 +105,26 @@ def _window_case(cuda_dev, B, H, ws, shift, nh):
     (1, 4, 32, 1296, 50, True),     # i2t at 576 px
 ])
 def test_plain_attention_fwd_bwd(cuda_dev, B, nh, hd, Lq, Lk, masked):
+    _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
+
+
+# Opt-in 3-warp configuration of the plain backward for <= 48 queries and keys (option "attn_small").
+@pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: small-sequence backward configuration not yet validated on hardware")
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", [(3, 12, 64, 40, 40, True), (2, 12, 64, 48, 48, False),
+                                                  (4, 12, 64, 33, 47, True), (256, 12, 64, 40, 40, True),
+                                                  (2, 12, 64, 50, 50, True)])
+def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked):
+    from fiber_b200 import lib
+    lib.set_option("attn_small", 1)
+    try:
+        _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("attn_small", 0)
+
+
+def _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked):
     from fiber_b200 import kernels as K
     C = nh * hd
     q = _rand((B * Lq, C), cuda_dev, 1)
