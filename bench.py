@@ -327,7 +327,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image_size": R, "text_len": L,
                    "parallelism": "dp%d" % world, "l2": "per-step activations (>10 GB) exceed the 126 MB L2",
-                   "last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1)},
+                   "last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1),
+                   "kernel_options": _kernel_options()},
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -357,6 +358,15 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def _kernel_options():
+    """Opt-in kernel selections in effect (fiber_set_option / FIBER_* environment); all 0 = the validated defaults."""
+    try:
+        from fiber_b200 import lib
+        return {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
+    except Exception as e:  # never let a label break the measurement
+        return {"error": str(e)}
 
 
 def main():
