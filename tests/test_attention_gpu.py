@@ -47,7 +47,7 @@ def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
     before = lib.get_option("winattn_tc_launches")
     lib.set_option("winattn_tc", mode)
     try:
-        _window_case(cuda_dev, B, H, ws, shift, nh)
+        _window_case(cuda_dev, B, H, ws, shift, nh, diag=True)
         torch.cuda.synchronize()
     finally:
         lib.set_option("winattn_tc", 0)
@@ -56,7 +56,27 @@ def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
     assert launched == ((mode & 1) + (mode >> 1) if covered else 0)
 
 
-def _window_case(cuda_dev, B, H, ws, shift, nh):
+def _diag(name, got, ref, src, N, hd):
+    """Where does a window-attention tensor differ?  Error maxima by window-token class (the tcgen05 kernels treat
+    tokens 0..127 and 128..143 of a window on different code paths), head-dim half and window position."""
+    got, ref = got.float(), ref.float()
+    B, T, C = ref.shape
+    nW = src.shape[0]
+    err = (got - ref).abs()[:, src.reshape(-1)].reshape(B, nW, N, C // hd, hd)  # window order
+    scale = max(ref.abs().max().item(), 1e-3)
+    tok = err.amax(dim=(0, 1, 3, 4)) / scale
+    lines = ["%s: rel-to-max error by class (ref max %.3g)" % (name, scale)]
+    lines.append("  tokens 0..127: %.3g   tokens 128..%d: %.3g" % (tok[:128].max().item() if N > 128 else tok.max().item(),
+                                                               N - 1, tok[128:].max().item() if N > 128 else 0.0))
+    lines.append("  head-dim 0..15: %.3g   16..31: %.3g" % ((err[..., :16].max() / scale).item(), (err[..., 16:].max() / scale).item()))
+    win = err.amax(dim=(0, 2, 3, 4)) / scale
+    lines.append("  first window: %.3g   last window: %.3g   worst window %d: %.3g" % (
+        win[0].item(), win[-1].item(), int(win.argmax()), win.max().item()))
+    lines.append("  worst tokens: %s" % [(int(i), round(float(tok[i]), 4)) for i in tok.topk(min(6, N)).indices])
+    print("\n".join(lines))
+
+
+def _window_case(cuda_dev, B, H, ws, shift, nh, diag=False):
     from fiber_b200 import kernels as K
     hd = 32
     C = nh * hd
@@ -83,6 +103,8 @@ def _window_case(cuda_dev, B, H, ws, shift, nh):
     ow = (torch.softmax(s, -1) @ xw[2]).transpose(1, 2).reshape(B, nW * N, C)
     ref = torch.empty(B, T, C, device=cuda_dev)
     ref = ref.index_copy(1, src.reshape(-1), ow)
+    if diag:
+        _diag("o", o.view(B, T, C), ref.detach(), src, N, hd)
     _close(o.view(B, T, C), ref, 2e-2, "o")
     _close(lse, torch.logsumexp(s, -1), 1e-2, "lse")
     ref.backward(d_o.float().view(B, T, C))
@@ -91,6 +113,10 @@ def _window_case(cuda_dev, B, H, ws, shift, nh):
     dtable = torch.zeros_like(table)
     K.attn_bwd(d_o, qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, nh, hd, scale,
                dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dbias_table=dtable, window=win, bias_table=table)
+    if diag:
+        for i, nm in enumerate(("dq", "dk", "dv")):
+            _diag(nm, dqkv.view(B, T, 3 * C)[..., i * C:(i + 1) * C], x.grad[..., i * C:(i + 1) * C], src, N, hd)
+        print("dtable: max err %.3g vs ref max %.3g" % ((dtable - tb.grad).abs().max().item(), tb.grad.abs().max().item()))
     _close(dqkv.view(B, T, 3 * C), x.grad, 3e-2, "dqkv")
     _close(dtable, tb.grad, 3e-2, "dtable")
 

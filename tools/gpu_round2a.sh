@@ -10,11 +10,11 @@ python -m fiber_b200.build > gpurun_out/r2a_build.log 2>&1
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr \
     -o tools/umma_probe.bin tools/umma_probe.cu >> gpurun_out/r2a_build.log 2>&1
 timeout 120 tools/umma_probe.bin > gpurun_out/r2a_probe.txt 2>&1; echo "probe exit $?" >> gpurun_out/r2a_probe.txt
-FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcfwd \
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -s -k tcfwd \
     > gpurun_out/r2a_tc_fwd.log 2>&1
-FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcbwd \
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -s -k tcbwd \
     > gpurun_out/r2a_tc_bwd.log 2>&1
-FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k tcboth \
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -s -k tcboth \
     > gpurun_out/r2a_tc_both.log 2>&1
 FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k small_cfg \
     > gpurun_out/r2a_attn_small.log 2>&1
@@ -23,5 +23,5 @@ FIBER_WINATTN_TC=1 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_at
 FIBER_WINATTN_TC=3 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc.txt 2>&1
 FIBER_ATTN_SMALL=1 timeout 900 python bench.py > gpurun_out/r2a_bench_small.json 2> gpurun_out/r2a_bench_small.err
 FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=1 timeout 900 python bench.py > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
-tail -n 3 gpurun_out/r2a_attn_small.log gpurun_out/r2a_probe.txt gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log
+tail -n 4 gpurun_out/r2a_attn_small.log gpurun_out/r2a_probe.txt; grep -h "passed\|failed\|error" gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log | tail -n 6
 cat gpurun_out/r2a_attn_mma_sync.txt gpurun_out/r2a_attn_tc.txt
