@@ -19,8 +19,10 @@ int attn_check(const AttnParams& p, int hd);
 // NW warps = 16 * NW query rows per chunk, SK keys staged per chunk.  <9, 144> is the general configuration
 // (one CTA per SM); <3, 48> serves problems with at most 48 queries and 48 keys (RoBERTa self-attention at 40
 // tokens: 3072 (sample, head) problems per launch) with four CTAs per SM instead of one two-thirds-idle CTA.
+// <4, 48> serves few-key problems with many queries (i2t cross attention: 576 / 144 queries x 40 keys) with three
+// CTAs per SM that walk 64-query chunks.
 template <int HD, bool WINDOW, int NW = 9, int SK = ATT_SKEYS>
-__global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : 4) attn_bwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn_bwd_kernel(const AttnParams p) {
   constexpr int BW_NWARPS = NW;
   constexpr int BW_QROWS = 16 * NW;
   constexpr int ATT_SKEYS = SK;        // shadows the global constant inside this kernel
@@ -436,7 +438,9 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
     return launch_bwd<32, true>(p, stream);
   }
   // opt-in: at most 48 queries and keys (RoBERTa self-attention at 40 tokens) on 3-warp CTAs, four per SM
-  if (hd == 64 && p.Lq <= 48 && p.Lk <= 48 && option_attn_small()) return launch_bwd<64, false, 3, 48>(p, stream);
+  if (hd == 64 && p.Lq <= 48 && p.Lk <= 48 && (option_attn_small() & 1)) return launch_bwd<64, false, 3, 48>(p, stream);
+  // opt-in (bit 1): few keys, many queries (i2t: 576 / 144 queries x 40 text tokens) on 4-warp CTAs, three per SM
+  if (hd == 32 && p.Lk <= 48 && p.Lq > 48 && (option_attn_small() & 2)) return launch_bwd<32, false, 4, 48>(p, stream);
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);
 }
 
