@@ -79,6 +79,19 @@ __device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+// mbarrier wait that names itself when it times out (a protocol bug becomes a trap with a readable message):
+// tag = 100 * kernel (1 forward, 2 backward) + barrier number (listed next to the barrier declarations)
+__device__ __noinline__ void tc_wait_timeout(int tag, uint32_t parity, int it) {
+  printf("fiber_b200 window_attn_tc: mbarrier timeout tag %d parity %u window-iteration %d block (%d,%d) warp %d lane %d\n",
+         tag, parity, it, blockIdx.x, blockIdx.y, threadIdx.x >> 5, threadIdx.x & 31);
+  __trap();
+}
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int tag, int it) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) tc_wait_timeout(tag, parity, it);
+  }
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -239,6 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
   float* rowmax = reinterpret_cast<float*>(smem + TF_OFF_RMAX);  // [window parity][column half][128]
   float* rowsum = reinterpret_cast<float*>(smem + TF_OFF_RSUM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TF_OFF_BARS);
+  // timeout tags (tc_wait): 101 s_full, 102 o_full, 103 full, 104 s_empty, 105 p_ready, 106 stage_free
   uint64_t* full = bars;            // [3] tiles of a stage have landed              (32 loader lanes)
   uint64_t* stage_free = bars + 3;  // [3] stage may be overwritten                   (tcgen05.commit + remainder warp)
   uint64_t* s_full = bars + 6;      // [2] S accumulator written                      (tcgen05.commit)
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
       long long img_base; int h0, w0, emask;
       geo.decode(g, img_base, h0, w0, emask);
 
-      mbar_wait(&s_full[b], (it >> 1) & 1);
+      tc_wait(&s_full[b], (it >> 1) & 1, 101, it);
       tc_fence_after();
       uint32_t v[72];  // fp32 bit patterns: scores, then probabilities
       {
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
       const float m = fmaxf(mx, rowmax[(b * 2 + (hf ^ 1)) * 128 + row]);
 
       if (it > 0) {  // previous window: P V has finished (O complete, P buffer free)
-        mbar_wait(o_full, (it - 1) & 1);
+        tc_wait(o_full, (it - 1) & 1, 102, it);
         tc_fence_after();
         epilogue(b ^ 1);
       }
@@ -381,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
       grow_prev = geo.row(img_base, h0, w0, th_i, tw_i);
     }
     named_bar_sync(1 + q, 64);  // partner's row sums of the last window
-    mbar_wait(o_full, (n_my - 1) & 1);
+    tc_wait(o_full, (n_my - 1) & 1, 102, n_my);
     tc_fence_after();
     epilogue((n_my - 1) & 1);
   } else if (warp == TC_WARP_MMA) {
@@ -390,8 +404,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, WA_HD, 0, 1);  // O = P V     (V MN-major)
     auto issue_s = [&](int it) {
       const int s = it % TF_STAGES, b = it & 1;
-      mbar_wait(&full[s], (it / TF_STAGES) & 1);
-      mbar_wait(&s_empty[b], ((it >> 1) & 1) ^ 1);
+      tc_wait(&full[s], (it / TF_STAGES) & 1, 103, it);
+      tc_wait(&s_empty[b], ((it >> 1) & 1) ^ 1, 104, it);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t q_addr = smem_u32(smem + s * TF_STAGE_BYTES), k_addr = q_addr + TC_TILE;
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
 #pragma unroll 1
     for (int it = 0; it < n_my; ++it) {
       if (it + 1 < n_my) issue_s(it + 1);  // next window's scores overlap this window's softmax
-      mbar_wait(p_ready, it & 1);
+      tc_wait(p_ready, it & 1, 105, it);
       tc_fence_after();
       if (lane == 0) {
         const int s = it % TF_STAGES;
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
         mbar_arrive(&full[(it - 1) % TF_STAGES]);
       }
       const int s = it % TF_STAGES;
-      if (it >= TF_STAGES) mbar_wait(&stage_free[s], (it / TF_STAGES - 1) & 1);
+      if (it >= TF_STAGES) tc_wait(&stage_free[s], (it / TF_STAGES - 1) & 1, 106, it);
       const int g = blockIdx.y + it * gridDim.y;
       long long img_base; int h0, w0, em;
       geo.decode(g, img_base, h0, w0, em);
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
       const int g = blockIdx.y + it * gridDim.y;
       long long img_base; int h0, w0, emask;
       geo.decode(g, img_base, h0, w0, emask);
-      mbar_wait(&full[s], (it / TF_STAGES) & 1);
+      tc_wait(&full[s], (it / TF_STAGES) & 1, 103, it);
       const uint32_t sQ = smem_u32(smem + s * TF_STAGE_BYTES), sK = sQ + TC_TILE, sV = sK + TC_TILE;
       float m_run[2] = {-1e30f, -1e30f}, l_run[2] = {0.f, 0.f};
       float oacc[4][4];
@@ -710,6 +724,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
   T.tok = T.code + WA_ROWS;
   const char* tbl_bytes = reinterpret_cast<const char*>(T.tbl2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_OFF_BARS);
+  // timeout tags (tc_wait): 201 s_full, 202 rem_done, 203 acc_full, 204 full, 205 sdp_empty, 206 pds_ready,
+  //                         207 acc_empty, 208 stage_free
   uint64_t* full = bars;            // [2] tiles of a stage have landed                     (32 loader lanes)
   uint64_t* stage_free = bars + 2;  // [2] stage may be overwritten                          (commit + 2 remainder warps)
   uint64_t* s_full = bars + 4;      //     S and dP accumulators written                     (commit)
@@ -783,11 +799,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
 #pragma unroll
       for (int c = 0; c < 4; ++c) madd[c] = ((code_i ^ c) & emask) ? WA_MASK2 : 0.f;
 
-      mbar_wait(s_full, it & 1);
+      tc_wait(s_full, it & 1, 201, it);
       tc_fence_after();
       // P / dS buffers are free: the tensor core is done with them (this thread waited for acc_full of the previous
       // window in its drain below) and so are the remainder warps' output jobs
-      if (it > 0) mbar_wait(rem_done, (it - 1) & 1);
+      if (it > 0) tc_wait(rem_done, (it - 1) & 1, 202, it);
       if (hf == 0) {
         if (emask) tc_bwd_row<0, true>(lane_addr, sP, sdS, row, tbl_i, scale2, nlse2, negD, madd, dbacc);
         else       tc_bwd_row<0, false>(lane_addr, sP, sdS, row, tbl_i, scale2, nlse2, negD, madd, dbacc);
@@ -802,7 +818,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       if (lane == 0) mbar_arrive(pds_ready);
 
       // drain dV / dK / dQ of token `row`, head-dim columns [hf * 16, +16)
-      mbar_wait(acc_full, it & 1);
+      tc_wait(acc_full, it & 1, 203, it);
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < 3; ++t) {  // one accumulator at a time: 16 live registers next to the 72 d(bias) sums
@@ -842,8 +858,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       const int s = it & 1;
       const uint32_t q_addr = smem_u32(smem + s * TB_STAGE_BYTES);
       const uint32_t do_addr = q_addr + TC_TILE, k_addr = q_addr + 2 * TC_TILE, v_addr = q_addr + 3 * TC_TILE;
-      mbar_wait(&full[s], (it >> 1) & 1);
-      mbar_wait(sdp_empty, (it & 1) ^ 1);
+      tc_wait(&full[s], (it >> 1) & 1, 204, it);
+      tc_wait(sdp_empty, (it & 1) ^ 1, 205, it);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -855,8 +871,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
         umma_commit(s_full);
       }
       __syncwarp();
-      mbar_wait(pds_ready, it & 1);
-      mbar_wait(acc_empty, (it & 1) ^ 1);
+      tc_wait(pds_ready, it & 1, 206, it);
+      tc_wait(acc_empty, (it & 1) ^ 1, 207, it);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -886,7 +902,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
         mbar_arrive(&full[(it - 1) & 1]);
       }
       const int s = it & 1;
-      if (it >= TB_STAGES) mbar_wait(&stage_free[s], ((it >> 1) - 1) & 1);
+      if (it >= TB_STAGES) tc_wait(&stage_free[s], ((it >> 1) - 1) & 1, 208, it);
       const int g = blockIdx.y + it * gridDim.y;
       long long img_base; int h0, w0, em;
       geo.decode(g, img_base, h0, w0, em);
@@ -934,9 +950,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       const uint32_t sQ = smem_u32(smem + s * TB_STAGE_BYTES);
       const uint32_t sdO = sQ + TC_TILE, sK = sQ + 2 * TC_TILE, sV = sQ + 3 * TC_TILE;
 
-      mbar_wait(&full[s], (it >> 1) & 1);
+      tc_wait(&full[s], (it >> 1) & 1, 204, it);
       if (it > 0) {
-        mbar_wait(acc_full, (it - 1) & 1);  // the tensor core has consumed P / dS of the previous window
+        tc_wait(acc_full, (it - 1) & 1, 203, it);  // the tensor core has consumed P / dS of the previous window
         named_bar_sync(5, 64);              // ... and so has the other remainder warp
       }
 #pragma unroll
@@ -955,7 +971,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_ready);
 
-      mbar_wait(pds_ready, it & 1);  // every P / dS element of this window is in smem
+      tc_wait(pds_ready, it & 1, 206, it);  // every P / dS element of this window is in smem
       const int t_first = k == 0 ? 0 : 1, t_last = k == 0 ? 0 : 2;
       for (int type = t_first; type <= t_last; ++type) {
         float acc[4][4];
