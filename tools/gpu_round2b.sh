@@ -5,9 +5,9 @@
 mkdir -p gpurun_out
 export FIBER_WINATTN_TC=3
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:win_attn_tc_fwd -c 1 \
-    -o gpurun_out/r2b_winfwd_tc python tools/ncu_attn_case.py > gpurun_out/r2b_ncu_fwd.log 2>&1
+    -o gpurun_out/r2b_winfwd_tc python tools/ncu_attn_case.py 24 512 16 6 256 > gpurun_out/r2b_ncu_fwd.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:win_attn_tc_bwd -c 1 \
-    -o gpurun_out/r2b_winbwd_tc python tools/ncu_attn_case.py > gpurun_out/r2b_ncu_bwd.log 2>&1
+    -o gpurun_out/r2b_winbwd_tc python tools/ncu_attn_case.py 24 512 16 6 256 > gpurun_out/r2b_ncu_bwd.log 2>&1
 for f in r2b_winfwd_tc r2b_winbwd_tc; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
 done
