@@ -21,9 +21,13 @@ def concat_all_gather(tensor):
     """fiber_module.py:12-24; a single process is its own world."""
     if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
         return tensor
-    tensors_gather = [torch.ones_like(tensor) for _ in range(torch.distributed.get_world_size())]
-    torch.distributed.all_gather(tensors_gather, tensor, async_op=False)
-    return torch.cat(tensors_gather, dim=0)
+    # same result as the reference's list all_gather + cat (rank-major concatenation along dim 0), without the
+    # world_size ones_like fills and the extra cat pass over the gathered data (906 MB of raw images at 8 ranks)
+    world = torch.distributed.get_world_size()
+    tensor = tensor.contiguous()
+    out = torch.empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+    torch.distributed.all_gather_into_tensor(out, tensor)
+    return out
 
 
 def _flinear_fp32(i, o):
