@@ -340,10 +340,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
       tc_fence_after();
       uint32_t v[72];  // fp32 bit patterns: scores, then probabilities
       {
-        const uint32_t ta = lane_addr + (b ? TF_S_COL1 : TF_S_COL0) + hf * 72;
-        tmem_ld32p(ta, v);
-        tmem_ld32p(ta + 32, v + 32);
-        tmem_ld8p(ta + 64, v + 64);
+        // every load naturally aligned to its own width (columns 0 | 32 | 64 and 72 | 80 | 96 | 128)
+        const uint32_t ta = lane_addr + (b ? TF_S_COL1 : TF_S_COL0);
+        if (hf == 0) {
+          tmem_ld32p(ta, v);
+          tmem_ld32p(ta + 32, v + 32);
+          tmem_ld8p(ta + 64, v + 64);
+        } else {
+          tmem_ld8p(ta + 72, v);
+          tmem_ld16p(ta + 80, v + 8);
+          tmem_ld32p(ta + 96, v + 24);
+          tmem_ld16p(ta + 128, v + 56);
+        }
         tmem_ld_wait();
       }
       tc_fence_before();
