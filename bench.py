@@ -364,7 +364,10 @@ def _kernel_options():
     """Opt-in kernel selections in effect (fiber_set_option / FIBER_* environment); all 0 = the validated defaults."""
     try:
         from fiber_b200 import lib
-        return {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
+        from fiber_b200 import ops
+        opts = {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
+        opts["gelu_cache"] = int(ops.GELU_CACHE)
+        return opts
     except Exception as e:  # never let a label break the measurement
         return {"error": str(e)}
 

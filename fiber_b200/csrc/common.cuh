@@ -360,6 +360,44 @@ __device__ __forceinline__ void gelu_erf_grad_mul2x4(uint64_t (&g)[4], const uin
 #pragma unroll
   for (int i = 0; i < 4; ++i) g[i] = mul2(g[i], r[i]);
 }
+// x[i] <- gelu(x[i]) and g[i] <- gelu'(x[i]) on four packed pairs from ONE erfc evaluation (the same operation order
+// as gelu_erf2x4 / gelu_erf_grad_mul2x4, so both results are bit-identical to the separate functions)
+__device__ __forceinline__ void gelu_erf_both2x4(uint64_t (&x)[4], uint64_t (&g)[4]) {
+  uint64_t ax[4], r[4], sh[4], e[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0, x1;
+    upk2(x[i], x0, x1);
+    ax[i] = pk2(fabsf(x0), fabsf(x1));
+    sh[i] = pk2(copysignf(0.5f, x0), copysignf(0.5f, x1));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(x[i], x[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = mul2(e[i], FIBER_PK2C(-0.72134752044448170368f));
+  erfc_abs_scaled2x4(ax, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float e0, e1;
+    upk2(e[i], e0, e1);
+    e[i] = pk2(ex2_approx(e0), ex2_approx(e1));  // exp(-x^2 / 2)
+  }
+  uint64_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = fma2(r[i], FIBER_PK2C(-0.5f), FIBER_PK2C(0.5f));   // 0.5 (1 - r)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma2(r[i], FIBER_PK2C(-1.0f), FIBER_PK2C(1.0f));   // 1 - r
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = fma2(sh[i], r[i], FIBER_PK2C(0.5f));               // Phi(x)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = mul2(x[i], FIBER_PK2C(0.39894228040143267794f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = fma2(r[i], e[i], g[i]);                            // Phi + x phi
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = mul2(ax[i], h[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = fma2(x[i], FIBER_PK2C(0.5f), h[i]);                // 0.5 x + |x| 0.5 (1 - r)
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -131,11 +131,83 @@ __device__ __forceinline__ void epi_chunk_full(uint32_t taddr, uint8_t* box_row,
   }
 }
 
+// ---- opt-in epilogue (kernel template parameter EPI = 1; fiber_gemm_args.act 3 / 4) ---------------------------
+// act 3 (fc1): C = GELU(acc + bias) and P = GELU'(acc + bias) from ONE pass over TMEM and one erfc per element; the
+//              backward only ever needs GELU'(h), so it is stored instead of the pre-activation h.
+// act 4 (fc2 dgrad): C = acc * aux — with aux = the stored GELU'(h) this replaces the 14-instruction-per-element
+//              GELU' epilogue of act 2 by one multiply.
+// One 32-row x 32-column chunk, thread = row, all rows / columns in range (checked on the host).
+// Writes bf16 GELU into the warp's swizzled box and returns GELU' packed as bf16 pairs (gp[2 c] = columns 4c..4c+3).
+__device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box_row, int swz,
+                                                    const float* __restrict__ bias_c, bool has_bias, uint32_t (&gp)[16]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t r[16];
+    tmem_ld16(taddr + hf * 16, r);
+    float4 bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      bv[j] = has_bias ? __ldg(reinterpret_cast<const float4*>(bias_c + hf * 16 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint64_t xp[4], gq[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        xp[e] = pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+      xp[0] = add2(xp[0], pk2(bv[2 * j].x, bv[2 * j].y)); xp[1] = add2(xp[1], pk2(bv[2 * j].z, bv[2 * j].w));
+      xp[2] = add2(xp[2], pk2(bv[2 * j + 1].x, bv[2 * j + 1].y));
+      xp[3] = add2(xp[3], pk2(bv[2 * j + 1].z, bv[2 * j + 1].w));
+      gelu_erf_both2x4(xp, gq);
+      float x[8], g[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        upk2(xp[e], x[2 * e], x[2 * e + 1]);
+        upk2(gq[e], g[2 * e], g[2 * e + 1]);
+      }
+      uint4 o;
+      o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+      o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+      *reinterpret_cast<uint4*>(box_row + (((hf * 2 + j) ^ swz) << 4)) = o;
+      const int jb = hf * 2 + j;
+      gp[jb * 4 + 0] = pack_bf16(g[0], g[1]); gp[jb * 4 + 1] = pack_bf16(g[2], g[3]);
+      gp[jb * 4 + 2] = pack_bf16(g[4], g[5]); gp[jb * 4 + 3] = pack_bf16(g[6], g[7]);
+    }
+  }
+}
+// C = acc * aux for one chunk
+__device__ __forceinline__ void epi_chunk_mul_aux(uint32_t taddr, uint8_t* box_row, int swz, const bf16* __restrict__ aux_c) {
+  uint4 av[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const uint4*>(aux_c + j * 8);
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t r[16];
+    tmem_ld16(taddr + hf * 16, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[hf * 2 + j]);
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(au[e]);
+        uint64_t v = mul2(pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1])), pk2(f.x, f.y));
+        upk2(v, x[2 * e], x[2 * e + 1]);
+      }
+      uint4 o;
+      o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+      o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+      *reinterpret_cast<uint4*>(box_row + (((hf * 2 + j) ^ swz) << 4)) = o;
+    }
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-template <int BN, int MN_MAJOR>
+template <int BN, int MN_MAJOR, int EPI = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
@@ -285,6 +357,72 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* box = reinterpret_cast<uint8_t*>(staging) + ew * 2048;  // 32 rows x 64 B
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
+    if constexpr (EPI == 1) {
+      // opt-in epilogues (act 3 / 4, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
+      const int act = p.act;
+      uint8_t* box_row = box + lane * 64;
+      const int swz = (lane >> 1) & 3;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit % (p.tiles_m * p.tiles_n);
+        const int m0 = (tile / p.tiles_n) * GEMM_BM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int ncols = min(BN, p.N - n0);
+        const long long row = static_cast<long long>(m0) + q * 32 + lane;
+        const bf16* aux_r = act == 4 ? p.aux + row * p.ldaux + n0 : nullptr;
+        if (act == 4) {
+#pragma unroll
+          for (int i = 0; i < CPW; ++i) {
+            const int c0 = (cgrp * CPW + i) * 32;
+            if (c0 < ncols) prefetch_l2(aux_r + c0);
+          }
+        }
+        mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < CPW; ++i) {
+          const int c0 = (cgrp * CPW + i) * 32;
+          if (c0 >= ncols) break;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
+          __syncwarp();
+          if (act == 4) {
+            epi_chunk_mul_aux(taddr, box_row, swz, aux_r + c0);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_commit();
+            }
+          } else {
+            uint32_t gp[16];
+            epi_chunk_gelu_both(taddr, box_row, swz, p.bias + n0 + c0, p.bias != nullptr, gp);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_commit();
+              tma_store_wait_read();  // the box is reused for the second output right away
+            }
+            __syncwarp();
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb)
+              *reinterpret_cast<uint4*>(box_row + ((jb ^ swz) << 4)) =
+                  make_uint4(gp[jb * 4 + 0], gp[jb * 4 + 1], gp[jb * 4 + 2], gp[jb * 4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmP, box, n0 + c0, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc_phase ^= (1u << acc);
+        acc ^= 1;
+      }
+      if (lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
+    } else {
     const float scale = p.scale ? __ldg(p.scale) : 1.0f;
     const float* __restrict__ bias = p.bias;
     const bf16* __restrict__ residual = p.residual;
@@ -479,6 +617,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc = nacc == 2 ? acc ^ 1 : 0;
     }
     if (use_tma && lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
+    }  // EPI == 0
   }
 
   tc_fence_before();
@@ -531,10 +670,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
-template <int BN, int MN>
+template <int BN, int MN, int EPI = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                        const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, MN>;
+  auto kern = gemm_tcgen05_kernel<BN, MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -552,7 +691,17 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "bad GEMM shape %d x %d x %d", a->m, a->n, a->k);
   FIBER_CHECK(a->a_major == a->b_major, "mixed operand majors are not supported");
   FIBER_CHECK(a->out_mode >= 0 && a->out_mode <= 2, "bad out_mode");
-  FIBER_CHECK(a->act != 2 || a->aux != nullptr, "act=2 (GELU grad) needs aux");
+  FIBER_CHECK(a->act >= 0 && a->act <= 4, "bad act %d", a->act);
+  FIBER_CHECK((a->act != 2 && a->act != 4) || a->aux != nullptr, "act=2 / act=4 need aux");
+  const bool epi1 = a->act == 3 || a->act == 4;  // opt-in single-pass GELU + GELU' / multiply-by-aux epilogues
+  if (epi1) {
+    FIBER_CHECK(a->a_major == 0 && a->out_mode == 0 && a->m % GEMM_BM == 0 && a->n % 32 == 0,
+                "act=%d needs K-major operands, a bf16 output, M %% 128 == 0 and N %% 32 == 0", a->act);
+    FIBER_CHECK(a->residual == nullptr && a->scale == nullptr && a->row_scale == nullptr && a->colsum == nullptr,
+                "act=%d does not combine with residual / scale / row_scale / colsum", a->act);
+    FIBER_CHECK(a->act == 4 ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
+                "act=3 writes GELU' to preact; act=4 takes no bias / preact");
+  }
   const int mn = a->a_major;
   const int BN = (a->n > 128) ? 256 : 128;
 
@@ -616,7 +765,7 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->n % 8 == 0, "N must be a multiple of 8 (got %d)", a->n);
   FIBER_CHECK(a->residual == nullptr || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0),
               "residual rows must be 16-byte aligned");
-  FIBER_CHECK(a->act != 2 || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0),
+  FIBER_CHECK((a->act != 2 && a->act != 4) || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0),
               "aux rows must be 16-byte aligned");
   FIBER_CHECK((a->ldc * (a->out_mode == 0 ? 2 : 4)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->c) & 15) == 0,
               "output rows must be 16-byte aligned");
@@ -629,6 +778,11 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   }
   const int units = tiles * p.splits;
   const int grid = units < sms ? units : sms;
+  if (epi1) {
+    FIBER_CHECK(p.tma_store == 1, "act=%d needs the TMA-store epilogue", a->act);
+    return BN == 256 ? launch_gemm<256, 0, 1>(ta, tb, tc, tp, p, grid, stream)
+                     : launch_gemm<128, 0, 1>(ta, tb, tc, tp, p, grid, stream);
+  }
   if (BN == 256) {
     return mn ? launch_gemm<256, 1>(ta, tb, tc, tp, p, grid, stream) : launch_gemm<256, 0>(ta, tb, tc, tp, p, grid, stream);
   }

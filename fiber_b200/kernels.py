@@ -13,6 +13,9 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
+# opt-in epilogues (include/fiber_b200.h): 3 = out GELU(v), preact buffer receives GELU'(v) (one TMEM pass);
+# 4 = out = accumulator * aux.  Need M % 128 == 0, N % 32 == 0, bf16 outputs.
+ACT_GELU_CACHE, ACT_MUL_AUX = 3, 4
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 
 # Optional in-situ profiling (bench.py): when a list is installed here every GEMM launch is bracketed

@@ -16,6 +16,7 @@ Reference semantics restated here (file:line under coarse_grained/fiber/modules/
 """
 import itertools
 import math
+import os
 import weakref
 
 import torch
@@ -121,6 +122,31 @@ class _GradArena(dict):
         for n, shp in shapes.items():
             self[n] = flat[off:off + sizes[n][0]].view(shp)
             off += sizes[n][1]
+
+
+# Opt-in (FIBER_GELU_CACHE=1 or set_gelu_cache(True)): the fc1 GEMM stores GELU'(h) instead of the pre-activation h
+# as its second output (one pass over TMEM, one erfc per element) and the fc2 dgrad GEMM multiplies by it instead of
+# evaluating the exact-erf GELU' in its epilogue (gemm_sm100.cu, kernel template parameter EPI = 1).  GELU(h) itself is
+# bit-identical to the default path; the gradient sees GELU'(h) rounded to bf16 instead of h rounded to bf16.
+GELU_CACHE = os.environ.get("FIBER_GELU_CACHE", "0") == "1"
+
+
+def set_gelu_cache(on):
+    global GELU_CACHE
+    GELU_CACHE = bool(on)
+
+
+def _fc1_gelu(x, w, bias, buf):
+    """a = GELU(x W^T + b).  `buf` receives what the backward needs — h, or GELU'(h) when the opt-in epilogue applies
+    (returned flag); _fc2_dgrad_gelu takes the same flag."""
+    if GELU_CACHE and x.shape[0] % 128 == 0 and w.shape[0] % 32 == 0:
+        return K.gemm(x, w, bias=bias, act=K.ACT_GELU_CACHE, preact=buf), True
+    return K.gemm(x, w, bias=bias, act=K.ACT_GELU, preact=buf), False
+
+
+def _fc2_dgrad_gelu(dz, w2_t, buf, cached):
+    """dh = (dz W2) * GELU'(h)"""
+    return K.gemm(dz, w2_t, aux=buf, act=K.ACT_MUL_AUX if cached else K.ACT_GELU_GRAD)
 
 
 def _wgrad(dy, x, scale=None, out=None, db=None):
@@ -324,7 +350,7 @@ class SwinBlockFn(torch.autograd.Function):
         ln2, sv["mean2"], sv["rstd2"], _ = K.layernorm_fwd(x1, p["norm2.weight"], p["norm2.bias"], LN_EPS)
         w1, sv["w1_t"] = CACHE.weights((params[names.index("mlp.fc1.weight")],))
         h = torch.empty((B * T, 4 * C), device=x.device, dtype=BF16)
-        a = K.gemm(ln2, w1, bias=p["mlp.fc1.bias"], act=K.ACT_GELU, preact=h)
+        a, sv["gelu_cached"] = _fc1_gelu(ln2, w1, p["mlp.fc1.bias"], h)
         w2, sv["w2_t"] = CACHE.weights((params[names.index("mlp.fc2.weight")],))
         out = K.gemm(a, w2, bias=p["mlp.fc2.bias"], residual=x1, row_scale=s_mlp, rows_per_scale=T)
         sv.update(x2=x2, ln1=ln1, qkv=qkv, ao=ao, lse=lse, x1=x1, ln2=ln2, h=h, a=a, p=p, s=s, s_mlp=s_mlp, geom=geom,
@@ -348,7 +374,7 @@ class SwinBlockFn(torch.autograd.Function):
         # ---- MLP branch: out = x1 + s * fc2(gelu(fc1(LN2(x1)))) ----
         dz = K.scale_rows(d_out, sv["s_mlp"], T) if sv["s_mlp"] is not None else d_out
         _wgrad(dz, sv["a"], out=g["mlp.fc2.weight"], db=g["mlp.fc2.bias"])
-        dh = K.gemm(dz, sv["w2_t"], aux=sv["h"], act=K.ACT_GELU_GRAD)
+        dh = _fc2_dgrad_gelu(dz, sv["w2_t"], sv["h"], sv["gelu_cached"])
         _wgrad(dh, sv["ln2"], out=g["mlp.fc1.weight"], db=g["mlp.fc1.bias"])
         dln2 = K.gemm(dh, sv["w1_t"])
         # ---- attention branch: x1 = x + s * (z [+ alpha * y]); the LN backward also emits dZ = s * dx1 ----
@@ -493,7 +519,7 @@ class RobertaLayerFn(torch.autograd.Function):
                                                               p["attention.output.LayerNorm.bias"], eps, add=h2)
         wi, sv["wi_t"] = CACHE.weights((P["intermediate.dense.weight"],))
         hpre = torch.empty((B * L, wi.shape[0]), device=h.device, dtype=BF16)
-        inter = K.gemm(ln_a, wi, bias=p["intermediate.dense.bias"], act=K.ACT_GELU, preact=hpre)
+        inter, sv["gelu_cached"] = _fc1_gelu(ln_a, wi, p["intermediate.dense.bias"], hpre)
         wout, sv["wout_t"] = CACHE.weights((P["output.dense.weight"],))
         f = K.gemm(inter, wout, bias=p["output.dense.bias"])
         if p_h > 0:
@@ -536,7 +562,7 @@ class RobertaLayerFn(torch.autograd.Function):
             dsum = d_out
         df = K.dropout(dsum, p_h, sv["seed_f"]) if p_h > 0 else dsum
         _wgrad(df, sv["inter"], out=g["output.dense.weight"], db=g["output.dense.bias"])
-        dhpre = K.gemm(df, sv["wout_t"], aux=sv["hpre"], act=K.ACT_GELU_GRAD)
+        dhpre = _fc2_dgrad_gelu(df, sv["wout_t"], sv["hpre"], sv["gelu_cached"])
         _wgrad(dhpre, sv["ln_a"], out=g["intermediate.dense.weight"], db=g["intermediate.dense.bias"])
         dln_a = K.gemm(dhpre, sv["wi_t"], residual=dsum)
         ds1 = K.layernorm_bwd(dln_a, sv["a2"], sv["mean_a"], sv["rstd_a"], p["attention.output.LayerNorm.weight"],

@@ -163,3 +163,42 @@ def test_vocab_decoder_padded(cuda_dev):
     for name, a, r in (("dx", x.grad, xr.grad), ("dw", w.grad, wr.grad), ("db", b.grad, br.grad)):
         err = (a - r).abs().max().item()
         assert err <= 2e-2 * max(r.abs().max().item(), 1e-6), "%s: %g vs %g" % (name, err, r.abs().max().item())
+
+
+# Opt-in epilogues (kernel template parameter EPI = 1): not yet validated on hardware, run with
+# FIBER_B200_EXPERIMENTAL=1 (tools/gpu_round2a.sh).
+@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in: single-pass GELU + GELU' epilogue not yet validated on hardware")
+@pytest.mark.parametrize("m,n,k,with_bias", [(128, 128, 64, True), (256, 512, 128, True), (1024, 2048, 512, True),
+                                             (2560, 3072, 768, True), (147456 // 8, 512, 128, False),
+                                             (384, 160, 96, True)])
+def test_gemm_gelu_cache_epilogues(cuda_dev, m, n, k, with_bias):
+    from fiber_b200 import kernels as K
+    a = _mk((m, k), cuda_dev, 11)
+    b = _mk((n, k), cuda_dev, 12, k ** -0.5)
+    bias = torch.randn(n, device=cuda_dev) if with_bias else None
+    # act 3: out = GELU(v), second output = GELU'(v); GELU must be bit-identical to the default two-pass epilogue
+    gp = torch.empty((m, n), device=cuda_dev, dtype=torch.bfloat16)
+    out = K.gemm(a, b, bias=bias, act=K.ACT_GELU_CACHE, preact=gp)
+    h = torch.empty((m, n), device=cuda_dev, dtype=torch.bfloat16)
+    out_ref = K.gemm(a, b, bias=bias, act=K.ACT_GELU, preact=h)
+    assert torch.equal(out, out_ref)
+    v = (a.float() @ b.float().t() + (bias if with_bias else 0.0)).requires_grad_(True)
+    torch.nn.functional.gelu(v).sum().backward()
+    torch.testing.assert_close(gp.float(), v.grad, rtol=1e-2, atol=1e-2)
+    # act 4: dgrad through the GELU = (dz W) * GELU'(h); compare with the default act-2 path on the same operands
+    dz = _mk((m, k), cuda_dev, 13)
+    w_t = _mk((n, k), cuda_dev, 14, k ** -0.5)
+    dh = K.gemm(dz, w_t, aux=gp, act=K.ACT_MUL_AUX)
+    dh_ref = K.gemm(dz, w_t, aux=h, act=K.ACT_GELU_GRAD)
+    torch.testing.assert_close(dh.float(), (dz.float() @ w_t.float().t()) * gp.float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dh.float(), dh_ref.float(), rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1", reason="opt-in epilogues")
+def test_gemm_gelu_cache_rejects_unsupported(cuda_dev):
+    from fiber_b200 import kernels as K
+    a = _mk((100, 64), cuda_dev, 1)
+    b = _mk((128, 64), cuda_dev, 2)
+    with pytest.raises(RuntimeError):  # M % 128 != 0
+        K.gemm(a, b, act=K.ACT_GELU_CACHE, preact=torch.empty((100, 128), device=cuda_dev, dtype=torch.bfloat16))

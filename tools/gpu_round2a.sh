@@ -1,10 +1,12 @@
 #!/bin/bash
-# Round 2, first GPU call: validate the opt-in tcgen05 window attention (csrc/window_attn_tc.cu) bottom-up.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round2a.sh'
-# 1. UMMA operand-form probe (which descriptor assumption is wrong, if any)
-# 2. parity of the tcgen05 kernels against the oracle formulation, forward-only / backward-only / both
-# 3. micro-benchmark of both generations at FIBER's stage shapes, then the full bench with the option on
-# Every step runs under its own timeout; a protocol bug becomes an mbarrier-timeout trap, not a hung GPU.
+# Round 2, first GPU call: validate the opt-in kernels written at the end of round 1 (none of them has run yet).
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round2a.sh'          (~25 GPU-minutes)
+# 1. UMMA operand-form probe for the tcgen05 window attention (which descriptor assumption is wrong, if any)
+# 2. parity: tcgen05 window attention (forward-only / backward-only / both), small plain-attention configurations,
+#    single-pass GELU + GELU' GEMM epilogues, block-level parity with every option on
+# 3. window-attention micro-benchmark of both generations, then the full bench per option and with all of them
+# Every step runs under its own timeout; a protocol bug becomes an mbarrier-timeout trap that names the barrier
+# (window_attn_tc.cu: tc_wait tags), not a hung GPU.
 mkdir -p gpurun_out
 python -m fiber_b200.build > gpurun_out/r2a_build.log 2>&1
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr \
@@ -18,10 +20,15 @@ FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.
     > gpurun_out/r2a_tc_both.log 2>&1
 FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k small_cfg \
     > gpurun_out/r2a_attn_small.log 2>&1
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gemm_gpu.py -q -k gelu_cache \
+    > gpurun_out/r2a_gelu_cache.log 2>&1
+FIBER_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_blocks_gpu.py -q -k optin \
+    > gpurun_out/r2a_blocks_optin.log 2>&1
 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_mma_sync.txt 2>&1
 FIBER_WINATTN_TC=1 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc_fwd.txt 2>&1
 FIBER_WINATTN_TC=3 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc.txt 2>&1
 FIBER_ATTN_SMALL=3 timeout 900 python bench.py > gpurun_out/r2a_bench_small.json 2> gpurun_out/r2a_bench_small.err
-FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=3 timeout 900 python bench.py > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
-tail -n 4 gpurun_out/r2a_attn_small.log gpurun_out/r2a_probe.txt; grep -h "passed\|failed\|error" gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log | tail -n 6
+FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_cache.json 2> gpurun_out/r2a_bench_gelu_cache.err
+FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=3 FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
+tail -n 4 gpurun_out/r2a_attn_small.log gpurun_out/r2a_gelu_cache.log gpurun_out/r2a_blocks_optin.log gpurun_out/r2a_probe.txt; grep -h "passed\|failed\|error" gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log | tail -n 6
 cat gpurun_out/r2a_attn_mma_sync.txt gpurun_out/r2a_attn_tc.txt
