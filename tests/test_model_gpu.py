@@ -175,3 +175,52 @@ def test_merged_mlm_itm_pass_equals_separate_passes(cuda_dev):
     for k in ("mlm_loss", "itm_loss", "itc_loss"):
         assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(1.0, abs(float(b[k]))), k
     assert torch.equal(a["mlm_logits"], b["mlm_logits"]) and torch.equal(a["itm_logits"], b["itm_logits"])
+
+
+@pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in kernels not yet validated on hardware (tools/gpu_round2a.sh)")
+def test_optin_kernels_match_default_384(cuda_dev):
+    """One ITM+MLM training step at 384 px (12x12 windows, the geometry the opt-in kernels target), dropout off:
+    tcgen05 window attention + small plain-attention configurations + the GELU'-caching GEMM epilogues give the loss
+    and the gradients of the default kernels to bf16 noise.  (Both sides are checked against the oracle elsewhere;
+    this is the full-model A/B at the north-star resolution.)"""
+    from fiber_b200 import lib, ops
+    from fiber_b200.modules import objectives as OBJ
+    model, cfg, sd = _build(["itm", "mlm"], 384, 40, cuda_dev)
+    batch = _to(synth.synth_batch(4, 384, 40, seed=4321, false_image=True), cuda_dev)
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+    model.current_tasks = ["mlm", "itm"]
+    labels = torch.tensor([1.0, 0.0, 1.0, 0.0], device=cuda_dev)
+
+    def step(on):
+        ops.set_gelu_cache(on)
+        lib.set_option("winattn_tc", 3 if on else 0)
+        lib.set_option("attn_small", 3 if on else 0)
+        try:
+            before = lib.get_option("winattn_tc_launches")
+            model.zero_grad()
+            loss = OBJ.compute_mlm(model, batch)["mlm_loss"] + OBJ.compute_itm(model, batch, labels)["itm_loss"]
+            loss.backward()
+            torch.cuda.synchronize()
+            launched = lib.get_option("winattn_tc_launches") - before
+        finally:
+            ops.set_gelu_cache(False)
+            lib.set_option("winattn_tc", 0)
+            lib.set_option("attn_small", 0)
+        return loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}, launched
+
+    l0, g0, n0 = step(False)
+    l1, g1, n1 = step(True)
+    assert n0 == 0 and n1 == 2 * 2 * 24  # two passes x (forward + backward) x 24 Swin blocks
+    assert abs(l1 - l0) < 2e-3 * abs(l0), (l0, l1)
+    assert g0.keys() == g1.keys()
+    scale = max(float(v.norm()) for v in g0.values())
+    errs = sorted((_l2rel(g1[n], g0[n]), n) for n in g0 if float(g0[n].norm()) > 1e-6 * scale)
+    assert errs[len(errs) // 2][0] < 2e-2, errs[len(errs) // 2]
+    assert errs[int(len(errs) * 0.9)][0] < 5e-2, errs[int(len(errs) * 0.9)]
+    assert errs[-1][0] < 0.35, errs[-1]

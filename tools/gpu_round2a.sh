@@ -22,7 +22,7 @@ FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.
     > gpurun_out/r2a_attn_small.log 2>&1
 FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gemm_gpu.py -q -k gelu_cache \
     > gpurun_out/r2a_gelu_cache.log 2>&1
-FIBER_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_blocks_gpu.py -q -k optin \
+FIBER_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_blocks_gpu.py tests/test_model_gpu.py -q -k optin \
     > gpurun_out/r2a_blocks_optin.log 2>&1
 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_mma_sync.txt 2>&1
 FIBER_WINATTN_TC=1 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc_fwd.txt 2>&1
