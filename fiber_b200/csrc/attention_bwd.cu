@@ -439,6 +439,9 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
   }
   // opt-in: at most 48 queries and keys (RoBERTa self-attention at 40 tokens) on 3-warp CTAs, four per SM
   if (hd == 64 && p.Lq <= 48 && p.Lk <= 48 && (option_attn_small() & 1)) return launch_bwd<64, false, 3, 48>(p, stream);
+  // opt-in (bit 2): few queries, many keys (t2i: 40 text queries x 576 / 144 image keys) on the same 3-warp CTAs,
+  // walking 48-key chunks (the 48-row Q / dO tiles are re-read from L2 per chunk)
+  if (hd == 64 && p.Lq <= 48 && p.Lk > 48 && (option_attn_small() & 4)) return launch_bwd<64, false, 3, 48>(p, stream);
   // opt-in (bit 1): few keys, many queries (i2t: 576 / 144 queries x 40 text tokens) on 4-warp CTAs, three per SM
   if (hd == 32 && p.Lk <= 48 && p.Lq > 48 && (option_attn_small() & 2)) return launch_bwd<32, false, 4, 48>(p, stream);
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);

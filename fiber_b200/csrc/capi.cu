@@ -26,14 +26,15 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // environment variable FIBER_WINATTN_TC, else 0 (the mma.sync generation).
 static std::atomic<int> g_winattn_tc{-1};
 // "attn_small": bit 0 routes plain attention backward with <= 48 queries and keys (head_dim 64) to the 3-warp
-// configuration of attention_bwd.cu, bit 1 the <= 48-key / many-query case (head_dim 32) to the 4-warp one.
+// configuration of attention_bwd.cu, bit 1 the <= 48-key / many-query case (head_dim 32) to the 4-warp one, bit 2 the
+// <= 48-query / many-key case (head_dim 64, t2i) to the 3-warp one.
 // Default from FIBER_ATTN_SMALL, else 0.
 static std::atomic<int> g_attn_small{-1};
 int option_attn_small() {
   int v = g_attn_small.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_ATTN_SMALL");
-    v = e ? (atoi(e) & 3) : 0;
+    v = e ? (atoi(e) & 7) : 0;
     g_attn_small.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -139,7 +140,7 @@ int fiber_set_option(const char* name, int32_t value) {
     return 0;
   }
   if (name && strcmp(name, "attn_small") == 0) {
-    fiber::g_attn_small.store(value & 3, std::memory_order_relaxed);
+    fiber::g_attn_small.store(value & 7, std::memory_order_relaxed);
     return 0;
   }
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");

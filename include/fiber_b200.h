@@ -35,7 +35,8 @@ int64_t fiber_launch_count(void);
  * "attn_small": bit 0 routes fiber_attn_bwd (mode 0, head_dim 64, at most 48 queries and keys: RoBERTa self-attention,
  * roberta.py:256-326) to a 3-warp / four-CTAs-per-SM configuration of the same kernel, bit 1 the few-key case
  * (head_dim 32, at most 48 keys, more than 48 queries: i2t, swin_transformer.py:226-259) to a 4-warp / three-CTAs-per-SM
- * one; default 0 or FIBER_ATTN_SMALL.
+ * one, bit 2 the few-query case (head_dim 64, at most 48 queries, more than 48 keys: t2i, roberta.py:441-502) to the
+ * 3-warp one; default 0 or FIBER_ATTN_SMALL.
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
  * fiber_get_option returns the value ("winattn_tc_launches", read-only: launches of the tcgen05 generation so far). */
 int fiber_set_option(const char* name, int32_t value);

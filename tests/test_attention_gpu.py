@@ -141,10 +141,12 @@ def test_plain_attention_fwd_bwd(cuda_dev, B, nh, hd, Lq, Lk, masked):
                                                   (4, 12, 64, 33, 47, True), (256, 12, 64, 40, 40, True),
                                                   (2, 12, 64, 50, 50, True),
                                                   (2, 16, 32, 576, 40, True), (2, 32, 32, 144, 40, True),
-                                                  (3, 16, 32, 100, 48, False), (1, 4, 32, 1296, 50, True)])
+                                                  (3, 16, 32, 100, 48, False), (1, 4, 32, 1296, 50, True),
+                                                  (2, 12, 64, 40, 576, False), (2, 12, 64, 40, 144, False),
+                                                  (3, 12, 64, 33, 100, True)])
 def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked):
     from fiber_b200 import lib
-    lib.set_option("attn_small", 3)
+    lib.set_option("attn_small", 7)
     try:
         _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
         torch.cuda.synchronize()

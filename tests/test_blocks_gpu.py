@@ -134,7 +134,7 @@ def test_swin_block_optin(cuda_dev, B, H, ws, C, nh, shift, fused, variant):
     from fiber_b200 import lib, ops
     ops.set_gelu_cache(variant in ("gelu_cache", "all"))
     lib.set_option("winattn_tc", 3 if variant in ("winattn_tc", "all") else 0)
-    lib.set_option("attn_small", 3 if variant == "all" else 0)
+    lib.set_option("attn_small", 7 if variant == "all" else 0)
     try:
         test_swin_block(cuda_dev, B, H, ws, C, nh, shift, fused)
         torch.cuda.synchronize()
@@ -150,7 +150,7 @@ def test_swin_block_optin(cuda_dev, B, H, ws, C, nh, shift, fused, variant):
 def test_roberta_layer_optin(cuda_dev, li, img_tokens, img_dim, last_norm):
     from fiber_b200 import lib, ops
     ops.set_gelu_cache(True)
-    lib.set_option("attn_small", 3)
+    lib.set_option("attn_small", 7)
     try:
         test_roberta_layer(cuda_dev, li, img_tokens, img_dim, last_norm)
         torch.cuda.synchronize()

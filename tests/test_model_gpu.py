@@ -200,7 +200,7 @@ def test_optin_kernels_match_default_384(cuda_dev):
     def step(on):
         ops.set_gelu_cache(on)
         lib.set_option("winattn_tc", 3 if on else 0)
-        lib.set_option("attn_small", 3 if on else 0)
+        lib.set_option("attn_small", 7 if on else 0)
         try:
             before = lib.get_option("winattn_tc_launches")
             model.zero_grad()
