@@ -367,6 +367,7 @@ def _kernel_options():
         from fiber_b200 import ops
         opts = {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
         opts["gelu_cache"] = int(ops.GELU_CACHE)
+        opts["gelu_onepass"] = int(ops.GELU_ONEPASS)
         return opts
     except Exception as e:  # never let a label break the measurement
         return {"error": str(e)}

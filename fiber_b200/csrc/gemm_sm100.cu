@@ -137,7 +137,11 @@ __device__ __forceinline__ void epi_chunk_full(uint32_t taddr, uint8_t* box_row,
 // act 4 (fc2 dgrad): C = acc * aux — with aux = the stored GELU'(h) this replaces the 14-instruction-per-element
 //              GELU' epilogue of act 2 by one multiply.
 // One 32-row x 32-column chunk, thread = row, all rows / columns in range (checked on the host).
-// Writes bf16 GELU into the warp's swizzled box and returns GELU' packed as bf16 pairs (gp[2 c] = columns 4c..4c+3).
+// act 5 (fc1, default backward): C = GELU(acc + bias) and P = acc + bias — what act 1 + preact computes in two passes
+//              over TMEM, bit for bit, in one.
+// Writes bf16 GELU into the warp's swizzled box and returns the second output (GRAD: GELU'(v), else v) packed as
+// bf16 pairs, 16 bytes = 8 columns per group of four words.
+template <bool GRAD>
 __device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box_row, int swz,
                                                     const float* __restrict__ bias_c, bool has_bias, uint32_t (&gp)[16]) {
 #pragma unroll
@@ -158,7 +162,13 @@ __device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box
       xp[0] = add2(xp[0], pk2(bv[2 * j].x, bv[2 * j].y)); xp[1] = add2(xp[1], pk2(bv[2 * j].z, bv[2 * j].w));
       xp[2] = add2(xp[2], pk2(bv[2 * j + 1].x, bv[2 * j + 1].y));
       xp[3] = add2(xp[3], pk2(bv[2 * j + 1].z, bv[2 * j + 1].w));
-      gelu_erf_both2x4(xp, gq);
+      if (GRAD) {
+        gelu_erf_both2x4(xp, gq);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gq[e] = xp[e];  // the pre-activation itself
+        gelu_erf2x4(xp);
+      }
       float x[8], g[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -358,7 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     if constexpr (EPI == 1) {
-      // opt-in epilogues (act 3 / 4, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
+      // opt-in epilogues (act 3 / 4 / 5, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
       const int act = p.act;
       uint8_t* box_row = box + lane * 64;
       const int swz = (lane >> 1) & 3;
@@ -395,7 +405,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
             uint32_t gp[16];
-            epi_chunk_gelu_both(taddr, box_row, swz, p.bias + n0 + c0, p.bias != nullptr, gp);
+            if (act == 3) epi_chunk_gelu_both<true>(taddr, box_row, swz, p.bias + n0 + c0, p.bias != nullptr, gp);
+            else          epi_chunk_gelu_both<false>(taddr, box_row, swz, p.bias + n0 + c0, p.bias != nullptr, gp);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -691,16 +702,16 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "bad GEMM shape %d x %d x %d", a->m, a->n, a->k);
   FIBER_CHECK(a->a_major == a->b_major, "mixed operand majors are not supported");
   FIBER_CHECK(a->out_mode >= 0 && a->out_mode <= 2, "bad out_mode");
-  FIBER_CHECK(a->act >= 0 && a->act <= 4, "bad act %d", a->act);
+  FIBER_CHECK(a->act >= 0 && a->act <= 5, "bad act %d", a->act);
   FIBER_CHECK((a->act != 2 && a->act != 4) || a->aux != nullptr, "act=2 / act=4 need aux");
-  const bool epi1 = a->act == 3 || a->act == 4;  // opt-in single-pass GELU + GELU' / multiply-by-aux epilogues
+  const bool epi1 = a->act >= 3;  // opt-in single-pass GELU + GELU' (3) / GELU + pre-activation (5) / multiply-by-aux (4)
   if (epi1) {
     FIBER_CHECK(a->a_major == 0 && a->out_mode == 0 && a->m % GEMM_BM == 0 && a->n % 32 == 0,
                 "act=%d needs K-major operands, a bf16 output, M %% 128 == 0 and N %% 32 == 0", a->act);
     FIBER_CHECK(a->residual == nullptr && a->scale == nullptr && a->row_scale == nullptr && a->colsum == nullptr,
                 "act=%d does not combine with residual / scale / row_scale / colsum", a->act);
     FIBER_CHECK(a->act == 4 ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
-                "act=3 writes GELU' to preact; act=4 takes no bias / preact");
+                "act=3 / act=5 write their second output to preact; act=4 takes no bias / preact");
   }
   const int mn = a->a_major;
   const int BN = (a->n > 128) ? 256 : 128;

@@ -129,6 +129,9 @@ class _GradArena(dict):
 # evaluating the exact-erf GELU' in its epilogue (gemm_sm100.cu, kernel template parameter EPI = 1).  GELU(h) itself is
 # bit-identical to the default path; the gradient sees GELU'(h) rounded to bf16 instead of h rounded to bf16.
 GELU_CACHE = os.environ.get("FIBER_GELU_CACHE", "0") == "1"
+# Opt-in (FIBER_GELU_ONEPASS=1): same outputs as the default fc1 epilogue (GELU(h) and h), bit for bit, from one pass
+# over TMEM instead of two; the backward is unchanged.
+GELU_ONEPASS = os.environ.get("FIBER_GELU_ONEPASS", "0") == "1"
 
 
 def set_gelu_cache(on):
@@ -136,11 +139,18 @@ def set_gelu_cache(on):
     GELU_CACHE = bool(on)
 
 
+def set_gelu_onepass(on):
+    global GELU_ONEPASS
+    GELU_ONEPASS = bool(on)
+
+
 def _fc1_gelu(x, w, bias, buf):
     """a = GELU(x W^T + b).  `buf` receives what the backward needs — h, or GELU'(h) when the opt-in epilogue applies
     (returned flag); _fc2_dgrad_gelu takes the same flag."""
-    if GELU_CACHE and x.shape[0] % 128 == 0 and w.shape[0] % 32 == 0:
-        return K.gemm(x, w, bias=bias, act=K.ACT_GELU_CACHE, preact=buf), True
+    if (GELU_CACHE or GELU_ONEPASS) and x.shape[0] % 128 == 0 and w.shape[0] % 32 == 0:
+        if GELU_CACHE:
+            return K.gemm(x, w, bias=bias, act=K.ACT_GELU_CACHE, preact=buf), True
+        return K.gemm(x, w, bias=bias, act=K.ACT_GELU_ONEPASS, preact=buf), False
     return K.gemm(x, w, bias=bias, act=K.ACT_GELU, preact=buf), False
 
 

@@ -58,6 +58,7 @@ int fiber_get_option(const char* name);
  * Opt-in epilogues (K-major operands, out_mode 0, M % 128 == 0, N % 32 == 0, no scale / row_scale / residual):
  *   act == 3: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(gelu_erf'(v))   (one pass, one erfc)
  *   act == 4: c = bf16(acc * aux[row,col])          (with aux = the act-3 second output: dgrad through the GELU)
+ *   act == 5: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(v)    (act 1 + preact, bit for bit, one pass)
  */
 typedef struct fiber_gemm_args {
   const void* a;

@@ -183,6 +183,10 @@ def test_gemm_gelu_cache_epilogues(cuda_dev, m, n, k, with_bias):
     h = torch.empty((m, n), device=cuda_dev, dtype=torch.bfloat16)
     out_ref = K.gemm(a, b, bias=bias, act=K.ACT_GELU, preact=h)
     assert torch.equal(out, out_ref)
+    # act 5: both outputs of the default two-pass epilogue, bit for bit, from one pass
+    h1 = torch.empty_like(h)
+    out1 = K.gemm(a, b, bias=bias, act=K.ACT_GELU_ONEPASS, preact=h1)
+    assert torch.equal(out1, out_ref) and torch.equal(h1, h)
     v = (a.float() @ b.float().t() + (bias if with_bias else 0.0)).requires_grad_(True)
     torch.nn.functional.gelu(v).sum().backward()
     torch.testing.assert_close(gp.float(), v.grad, rtol=1e-2, atol=1e-2)

@@ -28,6 +28,7 @@ timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_mma_sync.txt 2>&
 FIBER_WINATTN_TC=1 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc_fwd.txt 2>&1
 FIBER_WINATTN_TC=3 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_attn_tc.txt 2>&1
 FIBER_ATTN_SMALL=7 timeout 900 python bench.py > gpurun_out/r2a_bench_small.json 2> gpurun_out/r2a_bench_small.err
+FIBER_GELU_ONEPASS=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_onepass.json 2> gpurun_out/r2a_bench_gelu_onepass.err
 FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_cache.json 2> gpurun_out/r2a_bench_gelu_cache.err
 FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=7 FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
 tail -n 4 gpurun_out/r2a_attn_small.log gpurun_out/r2a_gelu_cache.log gpurun_out/r2a_blocks_optin.log gpurun_out/r2a_probe.txt; grep -h "passed\|failed\|error" gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log | tail -n 6
