@@ -190,6 +190,43 @@ if __name__ == "__main__":
         gold_model("224_vqa", 224, ["vqa"], 2, 50, infer_modes=())
 
 
+def gold_itc():
+    """objectives.compute_itc of the unmodified reference (BASELINE configs[1] / [3] objective) at 224 px, B = 3:
+    the contrastive loss against the (synthetic) queues, its gradients, and the queue state after
+    _dequeue_and_enqueue.  The hard-negative draws are RNG-dependent and not part of the fixture."""
+    import torch.distributed as dist
+    from fiber.modules import objectives as ref_obj
+    if not dist.is_initialized():  # concat_all_gather (fiber_module.py:12-24) needs a process group: 1-rank gloo
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29641")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    torch.manual_seed(0)
+    B, L, size = 3, 40, 224
+    cfg = ref_shims.default_config(tasks=["itm", "mlm", "itc"], image_size=size, max_text_len=L)
+    model = FIBERTransformerSS(cfg)
+    fill(model)
+    batch = synth.synth_batch(B, size, L, seed=1234, false_image=True)
+    model.train()
+    no_dropout(model)
+    model.zero_grad()
+    torch.manual_seed(5)
+    ret, image_neg, text_neg, text_mask_neg = ref_obj.compute_itc(model, {k: v for k, v in batch.items()})
+    ret["itc_loss"].backward()
+    out = {"cfg": cfg, "B": B, "L": L, "state_keys": {k: tuple(s) for k, (s, _) in model_shapes(model).items()},
+           "itc_loss": float(ret["itc_loss"]), "grads": grad_stats(model),
+           "queue_ptr": int(model.queue_ptr), "queue_total": int(model.queue_total),
+           "image_queue_head": model.image_queue[:, :B].clone(), "text_queue_head": model.text_queue[:, :B].clone(),
+           "text_input_queue_head": model.text_input_queue[:B].clone(),
+           "neg_shapes": (tuple(image_neg.shape), tuple(text_neg.shape), tuple(text_mask_neg.shape))}
+    torch.save(out, os.path.join(GOLD, "model_224_itc.pt"))
+    print("model_224_itc.pt", "itc_loss", out["itc_loss"], "queue", out["queue_ptr"], out["queue_total"],
+          "grads", len(out["grads"]))
+
+
+if __name__ == "__main__" and "itc" in sys.argv[1:]:
+    gold_itc()
+
+
 def gold_schedule():
     """Parameter-group sizes of the reference's fiber_utils.set_schedule (name-substring rules)."""
     import types
