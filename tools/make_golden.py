@@ -223,8 +223,34 @@ def gold_itc():
           "grads", len(out["grads"]))
 
 
+def gold_itm_hardneg():
+    """objectives.compute_itm_hardneg (:78-116), the ITM objective of BASELINE configs[1] (3B-sample pass: positives,
+    (image, negative text), (negative image, text)) with deterministic negatives (the batch rolled by one)."""
+    from fiber.modules import objectives as ref_obj
+    torch.manual_seed(0)
+    B, L, size = 2, 40, 224
+    cfg = ref_shims.default_config(tasks=["itm", "mlm", "itc"], image_size=size, max_text_len=L)
+    model = FIBERTransformerSS(cfg)
+    fill(model)
+    batch = synth.synth_batch(B, size, L, seed=1234, false_image=True)
+    image_neg = batch["image"][0].roll(1, 0)
+    text_neg, text_mask_neg = batch["text_ids"].roll(1, 0), batch["text_masks"].roll(1, 0)
+    model.train()
+    no_dropout(model)
+    model.zero_grad()
+    ret = ref_obj.compute_itm_hardneg(model, {k: v for k, v in batch.items()}, image_neg, text_neg, text_mask_neg)
+    ret["itm_loss"].backward()
+    out = {"cfg": cfg, "B": B, "L": L, "state_keys": {k: tuple(s) for k, (s, _) in model_shapes(model).items()},
+           "itm_loss": float(ret["itm_loss"].detach()), "itm_logits": ret["itm_logits"].detach().clone(),
+           "grads": grad_stats(model)}
+    torch.save(out, os.path.join(GOLD, "model_224_itm_hardneg.pt"))
+    print("model_224_itm_hardneg.pt", "itm_loss", out["itm_loss"], "grads", len(out["grads"]))
+
+
 if __name__ == "__main__" and "itc" in sys.argv[1:]:
     gold_itc()
+if __name__ == "__main__" and "hardneg" in sys.argv[1:]:
+    gold_itm_hardneg()
 
 
 def gold_schedule():
