@@ -29,6 +29,7 @@ constexpr int IMG_BYTES = 192 * 1024;  // shared-memory image (operands at fixed
 //        1 O = P V    (P K-major fwd chunks x tile MN-major, N = 32, 9 steps)
 //        2 dV = P^T dO (P MN-major bwd chunks x tile MN-major, N = 32, 9 steps)
 //        3 dQ = dS K  (dS K-major bwd chunks x tile MN-major, N = 32, 9 steps)
+//        4 = form 0 with the accumulator at TMEM column 160 (the second S buffer of the forward kernel)
 __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict__ img, int form, uint32_t a_off,
                                                         uint32_t b_off, float* __restrict__ out /* [128][N] */) {
   extern __shared__ uint8_t smem_raw[];
@@ -45,17 +46,17 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(&tmem_slot, 256);
+    tmem_alloc(&tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  const int n = form == 0 ? N : HD;
+  const uint32_t tmem_base = tmem_slot + (form == 4 ? 160u : 0u);
+  const int n = (form == 0 || form == 4) ? N : HD;
   if (tid == 0) {
     const uint32_t a = smem_u32(smem) + a_off, b = smem_u32(smem) + b_off;
-    if (form == 0) {
+    if (form == 0 || form == 4) {
       const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
       for (int ks = 0; ks < 2; ++ks) umma_f16_ss(tmem_base, desc_tile_kmajor(a, ks), desc_tile_kmajor(b, ks), idesc, ks);
     } else if (form == 1) {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* __restrict
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_slot, 512);
   }
 }
 
@@ -138,12 +139,13 @@ int main() {
   CK(cudaMalloc(&d_out, 128 * N * sizeof(float)));
   CK(cudaMemcpy(d_img, img.data(), IMG_BYTES, cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IMG_BYTES + 1024));
-  const char* names[4] = {"S = X Y^T   (SW64 K-major x SW64 K-major, N=144)", "O = W Y     (SW128 K-major x SW64 MN-major, N=32)",
-                          "dV = W^T Y  (SW128 MN-major x SW64 MN-major, N=32)", "dQ = W Y    (bwd chunks K-major x SW64 MN-major)"};
+  const char* names[5] = {"S = X Y^T   (SW64 K-major x SW64 K-major, N=144)", "O = W Y     (SW128 K-major x SW64 MN-major, N=32)",
+                          "dV = W^T Y  (SW128 MN-major x SW64 MN-major, N=32)", "dQ = W Y    (bwd chunks K-major x SW64 MN-major)",
+                          "S = X Y^T   (accumulator at TMEM column 160)"};
   int bad_forms = 0;
-  for (int form = 0; form < 4; ++form) {
-    const int n = form == 0 ? N : HD;
-    const uint32_t a_off = form == 0 ? offX : (form == 1 ? offWf : offWb);
+  for (int form = 0; form < 5; ++form) {
+    const int n = (form == 0 || form == 4) ? N : HD;
+    const uint32_t a_off = (form == 0 || form == 4) ? offX : (form == 1 ? offWf : offWb);
     CK(cudaMemset(d_out, 0xFF, 128 * N * sizeof(float)));
     probe_kernel<<<1, 128, IMG_BYTES + 1024>>>(d_img, form, a_off, offY, d_out);
     CK(cudaGetLastError());
@@ -155,7 +157,7 @@ int main() {
     for (int m = 0; m < 128; ++m)
       for (int c = 0; c < n; ++c) {
         double ref = 0;
-        if (form == 0) for (int k = 0; k < HD; ++k) ref += (double)X[m * HD + k] * Y[c * HD + k];
+        if (form == 0 || form == 4) for (int k = 0; k < HD; ++k) ref += (double)X[m * HD + k] * Y[c * HD + k];
         else if (form == 2) for (int k = 0; k < N; ++k) ref += (double)W[k * N + m] * Y[k * HD + c];
         else for (int k = 0; k < N; ++k) ref += (double)W[m * N + k] * Y[k * HD + c];
         const double err = fabs(out[m * n + c] - ref);
