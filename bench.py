@@ -257,8 +257,15 @@ def run_ours(args):
         # the set of grad-less parameters is fixed per task mix => static graph
         ddp_kw = dict(static_graph=True) if os.environ.get("FIBER_DDP_STATIC", "1") == "1" else \
             dict(find_unused_parameters=True)
+        # broadcast_buffers=False: DDP's default re-broadcasts every module buffer from rank 0 at each forward, and this
+        # model's buffers include the 4096-deep ITC queues (image_input_queue alone is 4096 x 3 x 384 x 384 fp32 = 7.2 GB
+        # -> ~18-20 ms of flatten + NCCL broadcast + unflatten per step).  The queues are identical on every rank by
+        # construction (DDP syncs module state once at construction, and every rank applies the same all-gathered
+        # update, fiber_module.py:181-222; tests/test_dist_gloo.py), there is no BatchNorm, so the broadcast moves
+        # bytes without changing a value.  FIBER_DDP_BCAST_BUFFERS=1 restores the default.
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                                bucket_cap_mb=int(os.environ.get("FIBER_DDP_BUCKET_MB", "100")),
+                                                               broadcast_buffers=os.environ.get("FIBER_DDP_BCAST_BUFFERS", "0") == "1",
                                                                **ddp_kw)
     host = pin(make_batch(B, R, L, seed=1234 + rank))
     h2d = batch_bytes(host)
