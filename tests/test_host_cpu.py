@@ -173,3 +173,20 @@ def test_product_code_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(d, f)).read(), os.path.join(d, f)
+
+
+def test_rows_of_cat_equals_cat_then_index():
+    """objectives._rows_of_cat == torch.cat([batch, queue])[idx] (objectives.py:142-166 of the reference), including
+    the empty-queue case, without materialising the concatenation."""
+    import torch
+    from fiber_b200.modules.objectives import _rows_of_cat
+    g = torch.Generator().manual_seed(0)
+    for shape in ((5, 3, 4, 4), (5, 7)):
+        for qn in (0, 1, 9):
+            if len(shape) == 4:
+                a, b = torch.randn(shape, generator=g), torch.randn((qn,) + shape[1:], generator=g)
+            else:
+                a = torch.randint(0, 100, shape, generator=g)
+                b = torch.randint(0, 100, (qn,) + shape[1:], generator=g)
+            idx = torch.randint(0, shape[0] + qn, (shape[0],), generator=g)
+            assert torch.equal(_rows_of_cat(a, b, idx), torch.cat([a, b], 0)[idx])
