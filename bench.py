@@ -274,10 +274,13 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = True
 
     def step(batch):
-        out = step_model(batch)
-        loss = sum(v for k, v in out.items() if "loss" in k)
+        # clear the gradients first: at this point the GPU is still working through the previous step's backward, so
+        # the 754-parameter host loop is hidden; between forward and backward it showed up as GPU idle time
+        # (profiles/r1_step_timeline.txt: ~1.9 ms gap at the forward / backward boundary)
         for p in model.parameters():
             p.grad = None
+        out = step_model(batch)
+        loss = sum(v for k, v in out.items() if "loss" in k)
         loss.backward()
         return loss
 

@@ -34,10 +34,10 @@ batch = bench.to_device(bench.make_batch(B, R, L), dev)
 
 
 def step():
+    for p in model.parameters():  # same order as bench.py: gradients cleared while the GPU is still busy
+        p.grad = None
     out = model(batch)
     loss = sum(v for k, v in out.items() if "loss" in k)
-    for p in model.parameters():
-        p.grad = None
     loss.backward()
 
 
