@@ -225,8 +225,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem;
+  if constexpr (EPI == 1) {
+    // alignment by pointer arithmetic on the __shared__ array: the compiler keeps the address space, so the epilogue's
+    // box stores become STS.128 instead of generic ST.E.128 (to be carried over to EPI == 0 once measured)
+    smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  } else {
+    smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  }
   uint8_t* stage_base = smem;
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
