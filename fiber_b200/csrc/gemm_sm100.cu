@@ -185,11 +185,8 @@ __device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box
     }
   }
 }
-// C = acc * aux for one chunk
-__device__ __forceinline__ void epi_chunk_mul_aux(uint32_t taddr, uint8_t* box_row, int swz, const bf16* __restrict__ aux_c) {
-  uint4 av[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const uint4*>(aux_c + j * 8);
+// C = acc * aux for one chunk; av = the thread's 32 aux values (loaded by the caller one chunk ahead)
+__device__ __forceinline__ void epi_chunk_mul_aux(uint32_t taddr, uint8_t* box_row, int swz, const uint4 (&av)[4]) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
     uint32_t r[16];
@@ -385,12 +382,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ncols = min(BN, p.N - n0);
         const long long row = static_cast<long long>(m0) + q * 32 + lane;
         const bf16* aux_r = act == 4 ? p.aux + row * p.ldaux + n0 : nullptr;
-        if (act == 4) {
+        // act 4: the aux rows of chunk i + 1 are loaded into registers while chunk i is computed, and those of the
+        // first chunk before the wait for the accumulator (the act-2 epilogue stalls on exactly these loads)
+        uint4 av_next[4];
+        if (act == 4 && cgrp * CPW * 32 < ncols) {
 #pragma unroll
-          for (int i = 0; i < CPW; ++i) {
-            const int c0 = (cgrp * CPW + i) * 32;
-            if (c0 < ncols) prefetch_l2(aux_r + c0);
-          }
+          for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + cgrp * CPW * 32 + j * 8);
         }
         mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
         tc_fence_after();
@@ -402,7 +399,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
           __syncwarp();
           if (act == 4) {
-            epi_chunk_mul_aux(taddr, box_row, swz, aux_r + c0);
+            uint4 av[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[j] = av_next[j];
+            if (i + 1 < CPW && c0 + 32 < ncols) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + c0 + 32 + j * 8);
+            }
+            epi_chunk_mul_aux(taddr, box_row, swz, av);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
