@@ -378,6 +378,7 @@ def _kernel_options():
         opts = {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
         opts["gelu_cache"] = int(ops.GELU_CACHE)
         opts["gelu_onepass"] = int(ops.GELU_ONEPASS)
+        opts["gelu_grad_prefetch"] = int(ops.GELU_GRAD_PREFETCH)
         return opts
     except Exception as e:  # never let a label break the measurement
         return {"error": str(e)}

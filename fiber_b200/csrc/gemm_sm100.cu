@@ -185,7 +185,11 @@ __device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box
     }
   }
 }
-// C = acc * aux for one chunk; av = the thread's 32 aux values (loaded by the caller one chunk ahead)
+// act 7 (fc2 dgrad, default numerics): C = acc * GELU'(aux) — what act 2 computes, bit for bit, with the aux rows
+//              in registers before they are needed (below).
+// One chunk of C = acc * aux (GRAD = false, act 4) or acc * GELU'(aux) (GRAD = true, act 7); av = the thread's 32 aux
+// values, loaded by the caller one chunk ahead.
+template <bool GRAD>
 __device__ __forceinline__ void epi_chunk_mul_aux(uint32_t taddr, uint8_t* box_row, int swz, const uint4 (&av)[4]) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
@@ -196,12 +200,21 @@ __device__ __forceinline__ void epi_chunk_mul_aux(uint32_t taddr, uint8_t* box_r
     for (int j = 0; j < 2; ++j) {
       const uint32_t* au = reinterpret_cast<const uint32_t*>(&av[hf * 2 + j]);
       float x[8];
+      uint64_t xp[4], hx[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_bf16(au[e]);
-        uint64_t v = mul2(pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1])), pk2(f.x, f.y));
-        upk2(v, x[2 * e], x[2 * e + 1]);
+        xp[e] = pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+        hx[e] = pk2(f.x, f.y);
       }
+      if (GRAD) {
+        gelu_erf_grad_mul2x4(xp, hx);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xp[e] = mul2(xp[e], hx[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) upk2(xp[e], x[2 * e], x[2 * e + 1]);
       uint4 o;
       o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
       o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
@@ -371,7 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     if constexpr (EPI == 1) {
-      // opt-in epilogues (act 3 / 4 / 5, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
+      // opt-in epilogues (act 3 / 4 / 5 / 7, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
       const int act = p.act;
       uint8_t* box_row = box + lane * 64;
       const int swz = (lane >> 1) & 3;
@@ -381,11 +394,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = (tile % p.tiles_n) * BN;
         const int ncols = min(BN, p.N - n0);
         const long long row = static_cast<long long>(m0) + q * 32 + lane;
-        const bf16* aux_r = act == 4 ? p.aux + row * p.ldaux + n0 : nullptr;
+        const bool aux_mode = act == 4 || act == 7;
+        const bf16* aux_r = aux_mode ? p.aux + row * p.ldaux + n0 : nullptr;
         // act 4: the aux rows of chunk i + 1 are loaded into registers while chunk i is computed, and those of the
         // first chunk before the wait for the accumulator (the act-2 epilogue stalls on exactly these loads)
         uint4 av_next[4];
-        if (act == 4 && cgrp * CPW * 32 < ncols) {
+        if (aux_mode && cgrp * CPW * 32 < ncols) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + cgrp * CPW * 32 + j * 8);
         }
@@ -398,7 +412,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
           if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
           __syncwarp();
-          if (act == 4) {
+          if (aux_mode) {
             uint4 av[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) av[j] = av_next[j];
@@ -406,7 +420,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + c0 + 32 + j * 8);
             }
-            epi_chunk_mul_aux(taddr, box_row, swz, av);
+            if (act == 4) epi_chunk_mul_aux<false>(taddr, box_row, swz, av);
+            else          epi_chunk_mul_aux<true>(taddr, box_row, swz, av);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -712,16 +727,16 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "bad GEMM shape %d x %d x %d", a->m, a->n, a->k);
   FIBER_CHECK(a->a_major == a->b_major, "mixed operand majors are not supported");
   FIBER_CHECK(a->out_mode >= 0 && a->out_mode <= 2, "bad out_mode");
-  FIBER_CHECK(a->act >= 0 && a->act <= 5, "bad act %d", a->act);
-  FIBER_CHECK((a->act != 2 && a->act != 4) || a->aux != nullptr, "act=2 / act=4 need aux");
+  FIBER_CHECK(a->act >= 0 && a->act <= 7 && a->act != 6, "bad act %d", a->act);
+  FIBER_CHECK((a->act != 2 && a->act != 4 && a->act != 7) || a->aux != nullptr, "act=2 / 4 / 7 need aux");
   const bool epi1 = a->act >= 3;  // opt-in single-pass GELU + GELU' (3) / GELU + pre-activation (5) / multiply-by-aux (4)
   if (epi1) {
     FIBER_CHECK(a->a_major == 0 && a->out_mode == 0 && a->m % GEMM_BM == 0 && a->n % 32 == 0,
                 "act=%d needs K-major operands, a bf16 output, M %% 128 == 0 and N %% 32 == 0", a->act);
     FIBER_CHECK(a->residual == nullptr && a->scale == nullptr && a->row_scale == nullptr && a->colsum == nullptr,
                 "act=%d does not combine with residual / scale / row_scale / colsum", a->act);
-    FIBER_CHECK(a->act == 4 ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
-                "act=3 / act=5 write their second output to preact; act=4 takes no bias / preact");
+    FIBER_CHECK((a->act == 4 || a->act == 7) ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
+                "act=3 / act=5 write their second output to preact; act=4 / act=7 take no bias / preact");
   }
   const int mn = a->a_major;
   const int BN = (a->n > 128) ? 256 : 128;
@@ -786,7 +801,8 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->n % 8 == 0, "N must be a multiple of 8 (got %d)", a->n);
   FIBER_CHECK(a->residual == nullptr || (a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0),
               "residual rows must be 16-byte aligned");
-  FIBER_CHECK((a->act != 2 && a->act != 4) || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0),
+  FIBER_CHECK((a->act != 2 && a->act != 4 && a->act != 7) ||
+                  (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0),
               "aux rows must be 16-byte aligned");
   FIBER_CHECK((a->ldc * (a->out_mode == 0 ? 2 : 4)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->c) & 15) == 0,
               "output rows must be 16-byte aligned");

@@ -17,6 +17,7 @@ ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 # 4 = out = accumulator * aux.  Need M % 128 == 0, N % 32 == 0, bf16 outputs.
 ACT_GELU_CACHE, ACT_MUL_AUX = 3, 4
 ACT_GELU_ONEPASS = 5  # out GELU(v), preact buffer receives v: the results of ACT_GELU + preact, in one TMEM pass
+ACT_GELU_GRAD_PF = 7  # ACT_GELU_GRAD bit for bit, aux rows prefetched into registers one chunk ahead
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 
 # Optional in-situ profiling (bench.py): when a list is installed here every GEMM launch is bracketed

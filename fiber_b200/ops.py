@@ -134,6 +134,16 @@ GELU_CACHE = os.environ.get("FIBER_GELU_CACHE", "0") == "1"
 GELU_ONEPASS = os.environ.get("FIBER_GELU_ONEPASS", "0") == "1"
 
 
+# Opt-in (FIBER_GELU_GRAD_PREFETCH=1): the default fc2-dgrad epilogue (acc * GELU'(h)), bit for bit, with the h rows
+# loaded into registers one chunk ahead instead of after the accumulator wait.
+GELU_GRAD_PREFETCH = os.environ.get("FIBER_GELU_GRAD_PREFETCH", "0") == "1"
+
+
+def set_gelu_grad_prefetch(on):
+    global GELU_GRAD_PREFETCH
+    GELU_GRAD_PREFETCH = bool(on)
+
+
 def set_gelu_cache(on):
     global GELU_CACHE
     GELU_CACHE = bool(on)
@@ -156,7 +166,11 @@ def _fc1_gelu(x, w, bias, buf):
 
 def _fc2_dgrad_gelu(dz, w2_t, buf, cached):
     """dh = (dz W2) * GELU'(h)"""
-    return K.gemm(dz, w2_t, aux=buf, act=K.ACT_MUL_AUX if cached else K.ACT_GELU_GRAD)
+    if cached:
+        return K.gemm(dz, w2_t, aux=buf, act=K.ACT_MUL_AUX)
+    if GELU_GRAD_PREFETCH and dz.shape[0] % 128 == 0 and w2_t.shape[0] % 32 == 0:
+        return K.gemm(dz, w2_t, aux=buf, act=K.ACT_GELU_GRAD_PF)
+    return K.gemm(dz, w2_t, aux=buf, act=K.ACT_GELU_GRAD)
 
 
 def _wgrad(dy, x, scale=None, out=None, db=None):

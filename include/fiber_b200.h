@@ -59,6 +59,7 @@ int fiber_get_option(const char* name);
  *   act == 3: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(gelu_erf'(v))   (one pass, one erfc)
  *   act == 4: c = bf16(acc * aux[row,col])          (with aux = the act-3 second output: dgrad through the GELU)
  *   act == 5: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(v)    (act 1 + preact, bit for bit, one pass)
+ *   act == 7: c = bf16(acc * gelu_erf'(aux[row,col]))   (act 2, bit for bit, aux rows register-prefetched a chunk ahead)
  */
 typedef struct fiber_gemm_args {
   const void* a;

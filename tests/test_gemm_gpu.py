@@ -195,6 +195,7 @@ def test_gemm_gelu_cache_epilogues(cuda_dev, m, n, k, with_bias):
     w_t = _mk((n, k), cuda_dev, 14, k ** -0.5)
     dh = K.gemm(dz, w_t, aux=gp, act=K.ACT_MUL_AUX)
     dh_ref = K.gemm(dz, w_t, aux=h, act=K.ACT_GELU_GRAD)
+    assert torch.equal(K.gemm(dz, w_t, aux=h, act=K.ACT_GELU_GRAD_PF), dh_ref)  # act 7 == act 2, bit for bit
     torch.testing.assert_close(dh.float(), (dz.float() @ w_t.float().t()) * gp.float(), rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(dh.float(), dh_ref.float(), rtol=3e-2, atol=3e-2)
 
