@@ -379,6 +379,8 @@ def _kernel_options():
         opts["gelu_cache"] = int(ops.GELU_CACHE)
         opts["gelu_onepass"] = int(ops.GELU_ONEPASS)
         opts["gelu_grad_prefetch"] = int(ops.GELU_GRAD_PREFETCH)
+        from fiber_b200 import kernels
+        opts["res_prefetch"] = int(kernels.RES_PREFETCH)
         return opts
     except Exception as e:  # never let a label break the measurement
         return {"error": str(e)}

@@ -185,6 +185,49 @@ __device__ __forceinline__ void epi_chunk_gelu_both(uint32_t taddr, uint8_t* box
     }
   }
 }
+// act 6 (proj / fc2 forward): C = (acc + bias) * sc + residual — the default residual epilogue (act 0 + residual [+ scale /
+//              row_scale]), bit for bit, with the residual rows in registers one chunk ahead.
+template <bool BIAS, bool SCALE>
+__device__ __forceinline__ void epi_chunk_res(uint32_t taddr, uint8_t* box_row, int swz, const float* __restrict__ bias_c,
+                                              const uint4 (&rv)[4], float sc) {
+  const uint64_t sc2 = pk2(sc, sc);
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t r[16];
+    tmem_ld16(taddr + hf * 16, r);
+    float4 bv[4];
+    if (BIAS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(bias_c + hf * 16 + j * 4));
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint64_t xp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        xp[e] = pk2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+      if (BIAS) {
+        xp[0] = add2(xp[0], pk2(bv[2 * j].x, bv[2 * j].y)); xp[1] = add2(xp[1], pk2(bv[2 * j].z, bv[2 * j].w));
+        xp[2] = add2(xp[2], pk2(bv[2 * j + 1].x, bv[2 * j + 1].y));
+        xp[3] = add2(xp[3], pk2(bv[2 * j + 1].z, bv[2 * j + 1].w));
+      }
+      const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rv[hf * 2 + j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(ru[e]);
+        xp[e] = SCALE ? fma2(xp[e], sc2, pk2(f.x, f.y)) : add2(xp[e], pk2(f.x, f.y));
+      }
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) upk2(xp[e], x[2 * e], x[2 * e + 1]);
+      uint4 o;
+      o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]);
+      o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+      *reinterpret_cast<uint4*>(box_row + (((hf * 2 + j) ^ swz) << 4)) = o;
+    }
+  }
+}
 // act 7 (fc2 dgrad, default numerics): C = acc * GELU'(aux) — what act 2 computes, bit for bit, with the aux rows
 //              in registers before they are needed (below).
 // One chunk of C = acc * aux (GRAD = false, act 4) or acc * GELU'(aux) (GRAD = true, act 7); av = the thread's 32 aux
@@ -384,7 +427,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     if constexpr (EPI == 1) {
-      // opt-in epilogues (act 3 / 4 / 5 / 7, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
+      // opt-in epilogues (act 3 .. 7, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
       const int act = p.act;
       uint8_t* box_row = box + lane * 64;
       const int swz = (lane >> 1) & 3;
@@ -394,8 +437,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = (tile % p.tiles_n) * BN;
         const int ncols = min(BN, p.N - n0);
         const long long row = static_cast<long long>(m0) + q * 32 + lane;
-        const bool aux_mode = act == 4 || act == 7;
-        const bf16* aux_r = aux_mode ? p.aux + row * p.ldaux + n0 : nullptr;
+        const bool aux_mode = act == 4 || act == 6 || act == 7;  // a second bf16 [M, N] operand read per element
+        const bf16* aux_r = aux_mode ? (act == 6 ? p.residual + row * p.ldr + n0 : p.aux + row * p.ldaux + n0) : nullptr;
+        float sc = 1.0f;  // act 6: gate alpha x DropPath scale of this row's sample (as the default epilogue)
+        if (act == 6) {
+          if (p.scale) sc = __ldg(p.scale);
+          if (p.row_scale) sc *= __ldg(p.row_scale + static_cast<int>(row / p.rows_per_scale));
+        }
         // act 4: the aux rows of chunk i + 1 are loaded into registers while chunk i is computed, and those of the
         // first chunk before the wait for the accumulator (the act-2 epilogue stalls on exactly these loads)
         uint4 av_next[4];
@@ -420,8 +468,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + c0 + 32 + j * 8);
             }
-            if (act == 4) epi_chunk_mul_aux<false>(taddr, box_row, swz, av);
-            else          epi_chunk_mul_aux<true>(taddr, box_row, swz, av);
+            if (act == 4) {
+              epi_chunk_mul_aux<false>(taddr, box_row, swz, av);
+            } else if (act == 7) {
+              epi_chunk_mul_aux<true>(taddr, box_row, swz, av);
+            } else {
+              const bool scaled = p.scale != nullptr || p.row_scale != nullptr;
+              const float* bias_c = p.bias + n0 + c0;
+              if (p.bias) {
+                if (scaled) epi_chunk_res<true, true>(taddr, box_row, swz, bias_c, av, sc);
+                else        epi_chunk_res<true, false>(taddr, box_row, swz, bias_c, av, sc);
+              } else {
+                if (scaled) epi_chunk_res<false, true>(taddr, box_row, swz, bias_c, av, sc);
+                else        epi_chunk_res<false, false>(taddr, box_row, swz, bias_c, av, sc);
+              }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -727,16 +788,21 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->m > 0 && a->n > 0 && a->k > 0, "bad GEMM shape %d x %d x %d", a->m, a->n, a->k);
   FIBER_CHECK(a->a_major == a->b_major, "mixed operand majors are not supported");
   FIBER_CHECK(a->out_mode >= 0 && a->out_mode <= 2, "bad out_mode");
-  FIBER_CHECK(a->act >= 0 && a->act <= 7 && a->act != 6, "bad act %d", a->act);
+  FIBER_CHECK(a->act >= 0 && a->act <= 7, "bad act %d", a->act);
   FIBER_CHECK((a->act != 2 && a->act != 4 && a->act != 7) || a->aux != nullptr, "act=2 / 4 / 7 need aux");
   const bool epi1 = a->act >= 3;  // opt-in single-pass GELU + GELU' (3) / GELU + pre-activation (5) / multiply-by-aux (4)
   if (epi1) {
     FIBER_CHECK(a->a_major == 0 && a->out_mode == 0 && a->m % GEMM_BM == 0 && a->n % 32 == 0,
                 "act=%d needs K-major operands, a bf16 output, M %% 128 == 0 and N %% 32 == 0", a->act);
-    FIBER_CHECK(a->residual == nullptr && a->scale == nullptr && a->row_scale == nullptr && a->colsum == nullptr,
-                "act=%d does not combine with residual / scale / row_scale / colsum", a->act);
-    FIBER_CHECK((a->act == 4 || a->act == 7) ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
-                "act=3 / act=5 write their second output to preact; act=4 / act=7 take no bias / preact");
+    if (a->act == 6) {
+      FIBER_CHECK(a->residual != nullptr && a->preact == nullptr && a->aux == nullptr && a->colsum == nullptr,
+                  "act=6 needs residual and takes no preact / aux / colsum");
+    } else {
+      FIBER_CHECK(a->residual == nullptr && a->scale == nullptr && a->row_scale == nullptr && a->colsum == nullptr,
+                  "act=%d does not combine with residual / scale / row_scale / colsum", a->act);
+      FIBER_CHECK((a->act == 4 || a->act == 7) ? (a->preact == nullptr && a->bias == nullptr) : a->preact != nullptr,
+                  "act=3 / act=5 write their second output to preact; act=4 / act=7 take no bias / preact");
+    }
   }
   const int mn = a->a_major;
   const int BN = (a->n > 128) ? 256 : 128;

@@ -55,10 +55,12 @@ int fiber_get_option(const char* name);
  *   if (scale) v *= *scale;  if (row_scale) v *= row_scale[row / rows_per_scale];
  *   if (residual) v += residual[row,col];
  *   out_mode 0: c = bf16(v); 1: c = f32(v); 2: atomicAdd(f32 c, v) (split-K allowed).
- * Opt-in epilogues (K-major operands, out_mode 0, M % 128 == 0, N % 32 == 0, no scale / row_scale / residual):
+ * Opt-in epilogues (K-major operands, out_mode 0, M % 128 == 0, N % 32 == 0; no scale / row_scale / residual except act 6):
  *   act == 3: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(gelu_erf'(v))   (one pass, one erfc)
  *   act == 4: c = bf16(acc * aux[row,col])          (with aux = the act-3 second output: dgrad through the GELU)
  *   act == 5: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(v)    (act 1 + preact, bit for bit, one pass)
+ *   act == 6: the default epilogue with residual (bias, scale, row_scale as above; no preact / aux), bit for bit, residual
+ *             rows register-prefetched a chunk ahead
  *   act == 7: c = bf16(acc * gelu_erf'(aux[row,col]))   (act 2, bit for bit, aux rows register-prefetched a chunk ahead)
  */
 typedef struct fiber_gemm_args {

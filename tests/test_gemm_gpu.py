@@ -207,3 +207,31 @@ def test_gemm_gelu_cache_rejects_unsupported(cuda_dev):
     b = _mk((128, 64), cuda_dev, 2)
     with pytest.raises(RuntimeError):  # M % 128 != 0
         K.gemm(a, b, act=K.ACT_GELU_CACHE, preact=torch.empty((100, 128), device=cuda_dev, dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1", reason="opt-in epilogues")
+@pytest.mark.parametrize("m,n,k", [(256, 512, 512), (1152, 512, 2048), (9216, 128, 128), (2560, 768, 3072), (384, 160, 96)])
+@pytest.mark.parametrize("with_bias,with_scale,with_rows", [(True, False, False), (True, True, True), (False, False, True),
+                                                            (False, True, False)])
+def test_gemm_residual_prefetch_is_bit_identical(cuda_dev, m, n, k, with_bias, with_scale, with_rows):
+    """act 6 (ACT_RES_PF, opt-in) == the default residual epilogue, bit for bit."""
+    from fiber_b200 import kernels as K
+    a = _mk((m, k), cuda_dev, 21)
+    b = _mk((n, k), cuda_dev, 22, k ** -0.5)
+    res = _mk((m, n), cuda_dev, 23)
+    kw = dict(residual=res)
+    if with_bias:
+        kw["bias"] = torch.randn(n, device=cuda_dev)
+    if with_scale:
+        kw["scale"] = torch.tensor([0.7], device=cuda_dev)
+    if with_rows:
+        rps = 128
+        kw["row_scale"] = torch.rand(m // rps, device=cuda_dev) + 0.5
+        kw["rows_per_scale"] = rps
+    ref = K.gemm(a, b, **kw)
+    K.set_res_prefetch(True)
+    try:
+        out = K.gemm(a, b, **kw)
+    finally:
+        K.set_res_prefetch(False)
+    assert torch.equal(out, ref)

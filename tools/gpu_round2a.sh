@@ -20,7 +20,7 @@ FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.
     > gpurun_out/r2a_tc_both.log 2>&1
 FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -k small_cfg \
     > gpurun_out/r2a_attn_small.log 2>&1
-FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gemm_gpu.py -q -k gelu_cache \
+FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gemm_gpu.py -q -k "gelu_cache or prefetch" \
     > gpurun_out/r2a_gelu_cache.log 2>&1
 FIBER_B200_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_blocks_gpu.py tests/test_model_gpu.py -q -k optin \
     > gpurun_out/r2a_blocks_optin.log 2>&1
@@ -30,9 +30,9 @@ FIBER_WINATTN_TC=3 timeout 300 python tools/bench_attn.py 64 > gpurun_out/r2a_at
 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_default.json 2> gpurun_out/r2a_bench_default.err
 FIBER_ATTN_SMALL=7 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_small.json 2> gpurun_out/r2a_bench_small.err
 FIBER_GELU_ONEPASS=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_onepass.json 2> gpurun_out/r2a_bench_gelu_onepass.err
-FIBER_GELU_ONEPASS=1 FIBER_GELU_GRAD_PREFETCH=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_exact.json 2> gpurun_out/r2a_bench_gelu_exact.err
+FIBER_GELU_ONEPASS=1 FIBER_GELU_GRAD_PREFETCH=1 FIBER_GEMM_RES_PREFETCH=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_exact.json 2> gpurun_out/r2a_bench_gelu_exact.err
 FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_gelu_cache.json 2> gpurun_out/r2a_bench_gelu_cache.err
-FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=7 FIBER_GELU_CACHE=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
+FIBER_WINATTN_TC=3 FIBER_ATTN_SMALL=7 FIBER_GELU_CACHE=1 FIBER_GEMM_RES_PREFETCH=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_tc.json 2> gpurun_out/r2a_bench_tc.err
 tail -n 4 gpurun_out/r2a_attn_small.log gpurun_out/r2a_gelu_cache.log gpurun_out/r2a_blocks_optin.log gpurun_out/r2a_probe.txt; grep -h "passed\|failed\|error" gpurun_out/r2a_tc_fwd.log gpurun_out/r2a_tc_bwd.log gpurun_out/r2a_tc_both.log | tail -n 6
 cat gpurun_out/r2a_attn_mma_sync.txt gpurun_out/r2a_attn_tc.txt
 for f in default small gelu_onepass gelu_exact gelu_cache tc; do echo "$f: $(cut -c1-120 gpurun_out/r2a_bench_$f.json)"; done
