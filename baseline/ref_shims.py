@@ -1,21 +1,42 @@
-"""Import shims that let the UNMODIFIED reference package (/root/reference/coarse_grained/fiber)
-be imported in the build container, where timm 0.4.12, pytorch_lightning 1.3.2 and sacred are not
-installed and transformers is 5.x instead of the pinned 4.6.0.
+"""Import shims that let the UNMODIFIED reference package (coarse_grained/fiber) be imported in this
+image, where timm 0.4.12, pytorch_lightning 1.3.2 and sacred are not installed and transformers is
+5.x instead of the pinned 4.6.0.
 
-Used ONLY by tools/make_golden.py (golden-vector generation; runs where /root/reference exists).
-Nothing under fiber_b200/, tests/ (at run time on the GPU box), bench.py or __graft_entry__.py
-imports this module.  The shims restate the third-party semantics the reference relies on
-(SURVEY.md §8c): timm PatchEmbed/Mlp/DropPath/trunc_normal_/_init_vit_weights, the
-LightningModule attributes objectives.py touches, HF 4.6 get_extended_attention_mask (-10000).
+The package is looked up in baseline/_ref/ first (an untouched copy made by baseline/install_ref.py;
+git-ignored, so it never enters history, but it travels to the GPU box with the snapshot) and in
+/root/reference/coarse_grained otherwise (build container only).
+
+Users: tools/make_golden.py (golden vectors), bench.py's reference arms (`--impl reference`,
+`eager_gpu_baseline`), tests/test_reference_on_top.py (the reference's own objectives driven over
+the fiber_b200 module).  Nothing under fiber_b200/ imports this module.  The shims restate the
+third-party semantics the reference relies on: timm PatchEmbed/Mlp/DropPath/
+trunc_normal_/_init_vit_weights, the LightningModule attributes objectives.py touches, HF 4.6
+get_extended_attention_mask (-10000).
 """
-import math
+import os
 import sys
 import types
 
 import torch
 import torch.nn as nn
 
-REF_ROOT = "/root/reference/coarse_grained"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = (os.path.join(_HERE, "_ref"), "/root/reference/coarse_grained")
+
+
+def ref_root():
+    """Directory holding the reference's `fiber` package, or None."""
+    for c in _CANDIDATES:
+        if os.path.isfile(os.path.join(c, "fiber", "modules", "fiber_module.py")):
+            return c
+    return None
+
+
+def available():
+    return ref_root() is not None
+
+
+_INSTALLED = None
 
 
 def _mod(name):
@@ -25,6 +46,12 @@ def _mod(name):
 
 
 def install():
+    global _INSTALLED
+    if _INSTALLED is not None:
+        return _INSTALLED
+    REF_ROOT = ref_root()
+    if REF_ROOT is None:
+        raise RuntimeError("reference package not found (baseline/_ref/fiber or /root/reference/coarse_grained/fiber)")
     import transformers  # noqa: F401  (must be imported before a fake `timm` exists)
     import transformers.modeling_utils as mu
     import transformers.file_utils as fu
@@ -246,7 +273,8 @@ def install():
         return model_cls(**kwargs)
 
     ref_swin.swin_build_model_with_cfg = swin_build_model_with_cfg
-    return ref_swin, ref_roberta
+    _INSTALLED = (ref_swin, ref_roberta)
+    return _INSTALLED
 
 
 def default_config(**over):

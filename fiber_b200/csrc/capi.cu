@@ -22,19 +22,20 @@ void set_last_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu).  Default from the
-// environment variable FIBER_WINATTN_TC, else 0 (the mma.sync generation).
+// "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu) for the geometries it
+// covers (12x12 windows, shift 0 / 6); 0 = the mma.sync generation everywhere.  Default 3 (validated on B200 in round 2:
+// gpurun_out/r2a_*), overridable by FIBER_WINATTN_TC; fiber_set_option(name, -1) returns to the default.
 static std::atomic<int> g_winattn_tc{-1};
 // "attn_small": bit 0 routes plain attention backward with <= 48 queries and keys (head_dim 64) to the 3-warp
 // configuration of attention_bwd.cu, bit 1 the <= 48-key / many-query case (head_dim 32) to the 4-warp one, bit 2 the
 // <= 48-query / many-key case (head_dim 64, t2i) to the 3-warp one.
-// Default from FIBER_ATTN_SMALL, else 0.
+// Default 7 (validated on B200 in round 2), overridable by FIBER_ATTN_SMALL.
 static std::atomic<int> g_attn_small{-1};
 int option_attn_small() {
   int v = g_attn_small.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_ATTN_SMALL");
-    v = e ? (atoi(e) & 7) : 0;
+    v = e ? (atoi(e) & 7) : 7;
     g_attn_small.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -45,7 +46,7 @@ int option_winattn_tc() {
   int v = g_winattn_tc.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_WINATTN_TC");
-    v = e ? (atoi(e) & 3) : 0;
+    v = e ? (atoi(e) & 3) : 3;
     g_winattn_tc.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -136,11 +137,11 @@ int64_t fiber_launch_count(void) { return fiber::g_launches.load(); }
 
 int fiber_set_option(const char* name, int32_t value) {
   if (name && strcmp(name, "winattn_tc") == 0) {
-    fiber::g_winattn_tc.store(value & 3, std::memory_order_relaxed);
+    fiber::g_winattn_tc.store(value < 0 ? -1 : (value & 3), std::memory_order_relaxed);
     return 0;
   }
   if (name && strcmp(name, "attn_small") == 0) {
-    fiber::g_attn_small.store(value & 7, std::memory_order_relaxed);
+    fiber::g_attn_small.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
     return 0;
   }
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");

@@ -124,11 +124,11 @@ class _GradArena(dict):
             off += sizes[n][1]
 
 
-# Opt-in (FIBER_GELU_CACHE=1 or set_gelu_cache(True)): the fc1 GEMM stores GELU'(h) instead of the pre-activation h
+# Default (FIBER_GELU_CACHE=0 or set_gelu_cache(False) restores the h-saving epilogues): the fc1 GEMM stores GELU'(h) instead of the pre-activation h
 # as its second output (one pass over TMEM, one erfc per element) and the fc2 dgrad GEMM multiplies by it instead of
 # evaluating the exact-erf GELU' in its epilogue (gemm_sm100.cu, kernel template parameter EPI = 1).  GELU(h) itself is
 # bit-identical to the default path; the gradient sees GELU'(h) rounded to bf16 instead of h rounded to bf16.
-GELU_CACHE = os.environ.get("FIBER_GELU_CACHE", "0") == "1"
+GELU_CACHE = os.environ.get("FIBER_GELU_CACHE", "1") == "1"
 # Opt-in (FIBER_GELU_ONEPASS=1): same outputs as the default fc1 epilogue (GELU(h) and h), bit for bit, from one pass
 # over TMEM instead of two; the backward is unchanged.
 GELU_ONEPASS = os.environ.get("FIBER_GELU_ONEPASS", "0") == "1"

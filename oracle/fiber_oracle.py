@@ -7,7 +7,7 @@ reference's parameter names.  Only tests/, __graft_entry__.smoke() and bench.py'
 
 Parity pinning: the reference ships no tests or golden vectors, so this oracle is
 pinned against OUTPUTS OF THE REFERENCE ITSELF: tools/make_golden.py imports the unmodified
-reference in the build container (under the import shims of tools/ref_shims.py), runs it on
+reference in the build container (under the import shims of baseline/ref_shims.py), runs it on
 seeded inputs/weights (oracle/synth.py) and commits the results under tests/golden/;
 tests/test_oracle_golden.py checks this file against those fixtures on CPU.
 

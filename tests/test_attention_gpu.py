@@ -32,15 +32,13 @@ def test_window_attention_fwd_bwd(cuda_dev, B, H, ws, shift, nh):
     _window_case(cuda_dev, B, H, ws, shift, nh)
 
 
-# The tcgen05 generation (csrc/window_attn_tc.cu) is opt-in until it has been validated on a B200: run with
-# FIBER_B200_EXPERIMENTAL=1 (tools/gpu_round2a.sh does).  Cases it does not cover (ws != 12, odd shifts) must
-# fall through to the mma.sync kernels with the option set, so every case runs; the 12x12 ones must launch it.
+# The tcgen05 generation (csrc/window_attn_tc.cu) is the default for 12x12 windows (option "winattn_tc" = 3).  Cases it
+# does not cover (ws != 12, odd shifts) must fall through to the mma.sync kernels with the option set, so every case
+# runs; the 12x12 ones must launch it.  Mode 0 keeps the mma.sync generation under test for every geometry.
 TC_CASES = WINDOW_CASES + [(64, 12, 12, 0, 32), (5, 96, 12, 6, 4), (3, 24, 12, 6, 16), (1, 48, 12, 0, 8)]
 
 
-@pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: tcgen05 window attention not yet validated on hardware (FIBER_B200_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("mode", [1, 2, 3], ids=["tcfwd", "tcbwd", "tcboth"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["mmasync", "tcfwd", "tcbwd", "tcboth"])
 @pytest.mark.parametrize("B,H,ws,shift,nh", TC_CASES)
 def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
     from fiber_b200 import lib
@@ -50,7 +48,7 @@ def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
         _window_case(cuda_dev, B, H, ws, shift, nh, diag=True)
         torch.cuda.synchronize()
     finally:
-        lib.set_option("winattn_tc", 0)
+        lib.set_option("winattn_tc", -1)  # back to the default
     launched = lib.get_option("winattn_tc_launches") - before
     covered = ws == 12 and shift in (0, 6)
     assert launched == ((mode & 1) + (mode >> 1) if covered else 0)
@@ -134,9 +132,8 @@ def test_plain_attention_fwd_bwd(cuda_dev, B, nh, hd, Lq, Lk, masked):
     _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
 
 
-# Opt-in 3-warp configuration of the plain backward for <= 48 queries and keys (option "attn_small").
-@pytest.mark.skipif(os.environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: small-sequence backward configuration not yet validated on hardware")
+# Small-CTA configurations of the plain backward (option "attn_small", default 7) and the generic kernel (0).
+@pytest.mark.parametrize("small", [7, 0], ids=["small", "generic"])
 @pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", [(3, 12, 64, 40, 40, True), (2, 12, 64, 48, 48, False),
                                                   (4, 12, 64, 33, 47, True), (256, 12, 64, 40, 40, True),
                                                   (2, 12, 64, 50, 50, True),
@@ -144,14 +141,14 @@ def test_plain_attention_fwd_bwd(cuda_dev, B, nh, hd, Lq, Lk, masked):
                                                   (3, 16, 32, 100, 48, False), (1, 4, 32, 1296, 50, True),
                                                   (2, 12, 64, 40, 576, False), (2, 12, 64, 40, 144, False),
                                                   (3, 12, 64, 33, 100, True)])
-def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked):
+def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked, small):
     from fiber_b200 import lib
-    lib.set_option("attn_small", 7)
+    lib.set_option("attn_small", small)
     try:
         _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
         torch.cuda.synchronize()
     finally:
-        lib.set_option("attn_small", 0)
+        lib.set_option("attn_small", -1)
 
 
 def _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked):

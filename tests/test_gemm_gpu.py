@@ -167,8 +167,6 @@ def test_vocab_decoder_padded(cuda_dev):
 
 # Opt-in epilogues (kernel template parameter EPI = 1): not yet validated on hardware, run with
 # FIBER_B200_EXPERIMENTAL=1 (tools/gpu_round2a.sh).
-@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in: single-pass GELU + GELU' epilogue not yet validated on hardware")
 @pytest.mark.parametrize("m,n,k,with_bias", [(128, 128, 64, True), (256, 512, 128, True), (1024, 2048, 512, True),
                                              (2560, 3072, 768, True), (147456 // 8, 512, 128, False),
                                              (384, 160, 96, True)])
@@ -200,7 +198,6 @@ def test_gemm_gelu_cache_epilogues(cuda_dev, m, n, k, with_bias):
     torch.testing.assert_close(dh.float(), dh_ref.float(), rtol=3e-2, atol=3e-2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1", reason="opt-in epilogues")
 def test_gemm_gelu_cache_rejects_unsupported(cuda_dev):
     from fiber_b200 import kernels as K
     a = _mk((100, 64), cuda_dev, 1)
@@ -209,7 +206,6 @@ def test_gemm_gelu_cache_rejects_unsupported(cuda_dev):
         K.gemm(a, b, act=K.ACT_GELU_CACHE, preact=torch.empty((100, 128), device=cuda_dev, dtype=torch.bfloat16))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FIBER_B200_EXPERIMENTAL", "0") != "1", reason="opt-in epilogues")
 @pytest.mark.parametrize("m,n,k", [(256, 512, 512), (1152, 512, 2048), (9216, 128, 128), (2560, 768, 3072), (384, 160, 96)])
 @pytest.mark.parametrize("with_bias,with_scale,with_rows", [(True, False, False), (True, True, True), (False, False, True),
                                                             (False, True, False)])

@@ -8,8 +8,8 @@
 # Every step runs under its own timeout; a protocol bug becomes an mbarrier-timeout trap that names the barrier
 # (window_attn_tc.cu: tc_wait tags), not a hung GPU.
 mkdir -p gpurun_out
-python -m fiber_b200.build > gpurun_out/r2a_build.log 2>&1
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr \
+[ -f fiber_b200/libfiber_b200.so ] || python -m fiber_b200.build > gpurun_out/r2a_build.log 2>&1
+[ -f tools/umma_probe.bin ] || /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr \
     -o tools/umma_probe.bin tools/umma_probe.cu >> gpurun_out/r2a_build.log 2>&1
 timeout 120 tools/umma_probe.bin > gpurun_out/r2a_probe.txt 2>&1; echo "probe exit $?" >> gpurun_out/r2a_probe.txt
 FIBER_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_attention_gpu.py -q -s -k tcfwd \

@@ -10,5 +10,6 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:win_
     -o gpurun_out/r2b_winbwd_tc python tools/ncu_attn_case.py 24 512 16 6 256 > gpurun_out/r2b_ncu_bwd.log 2>&1
 for f in r2b_winfwd_tc r2b_winbwd_tc; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
+  ncu -i gpurun_out/$f.ncu-rep --page source --csv > gpurun_out/$f.source.csv 2>/dev/null
 done
 tail -n 3 gpurun_out/r2b_ncu_fwd.log gpurun_out/r2b_ncu_bwd.log

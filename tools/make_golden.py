@@ -1,7 +1,7 @@
 """Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on seeded inputs.
 
 Run in the build container only (`python tools/make_golden.py`): the reference is imported through
-tools/ref_shims.py, its parameters are overwritten with oracle/synth.py's name-seeded values, and
+baseline/ref_shims.py, its parameters are overwritten with oracle/synth.py's name-seeded values, and
 small slices / statistics of its outputs and gradients are saved.  tests/test_oracle_golden.py
 then pins oracle/fiber_oracle.py against these files on CPU, anywhere.
 """
@@ -13,9 +13,8 @@ import torch.nn as nn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-import ref_shims  # noqa: E402
+from baseline import ref_shims  # noqa: E402
 from oracle import synth  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
