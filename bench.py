@@ -141,8 +141,67 @@ def batch_bytes(batch):
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference algorithm on the host cores
+# reference arm / cpu_baseline: the UNMODIFIED reference (baseline/_ref, driven through its own
+# FIBERTransformerSS.training_step by baseline/ref_harness.py) on the host cores; the oracle port of the
+# same algorithm only when the reference package is not installed next to this file
 # ---------------------------------------------------------------------------------------------
+def fill_queues(model, seed=4321):
+    """Steady-state ITC queues (what every run reaches after 4096 / global-batch steps, fiber_module.py:181-222):
+    unit-norm feature columns, valid token ids, queue_total = queue_size — so that every N and both arms time the
+    same work (hard negatives drawn from batch + a full queue)."""
+    if not hasattr(model, "image_queue"):
+        return
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for q in (model.image_queue, model.text_queue):
+            v = torch.randn(q.shape, generator=g)
+            q.copy_((v / v.norm(dim=0, keepdim=True)).to(q.device))
+        n, L = model.text_input_queue.shape
+        ids = torch.randint(3, 50264, (n, L), generator=g)
+        ids[:, 0], ids[:, -1] = 0, 2
+        model.text_input_queue.copy_(ids.to(model.text_input_queue.device))
+        model.text_input_mask_queue.fill_(1)
+        model.queue_total.fill_(n)
+        model.queue_ptr.fill_(0)
+
+
+def reference_available():
+    try:
+        from baseline import ref_harness
+        return ref_harness.available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def ref_cpu_step_seconds(B, image_size, L, steps, warmup, threads):
+    """fwd+bwd of the ITM+ITC+MLM step of the unmodified reference (fp32, CPU, all host threads)."""
+    from baseline import ref_harness
+    torch.set_num_threads(threads)
+    st = ref_harness.RefStep(["itm", "itc", "mlm"], image_size, L, "cpu")
+    batch = make_batch(B, image_size, L, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        st(batch)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    st.close()
+    return sum(times) / len(times)
+
+
+def cpu_baseline_record(B, image_size, L, steps, warmup):
+    threads = os.cpu_count() or 1
+    if reference_available():
+        sec = ref_cpu_step_seconds(B, image_size, L, steps, warmup, threads)
+        kind, what = "reference", "unmodified reference (baseline/_ref, FIBERTransformerSS.training_step + backward)"
+    else:
+        sec = cpu_step_seconds(B, image_size, L, steps, warmup, threads)
+        kind, what = "port", "oracle port of the reference algorithm (reference package not installed)"
+    return sec, {"value": B / sec, "unit": "pairs/s", "cores": threads, "kind": kind,
+                 "sample": "B=%d pairs/step, %d timed step(s) of the same ITM+ITC+MLM %dpx workload, fp32, torch %d threads; %s"
+                           % (B, steps, image_size, threads, what)}
+
+
 def cpu_step_seconds(B, image_size, L, steps, warmup, threads):
     """fwd+bwd of the ITM+ITC+MLM step through oracle/fiber_oracle.py (fp32, CPU)."""
     from oracle import fiber_oracle as O
@@ -172,24 +231,29 @@ def cpu_step_seconds(B, image_size, L, steps, warmup, threads):
     return sum(times) / len(times)
 
 
+def bench_config(args, world):
+    """The `config` object, identical for both arms (what is measured, not how)."""
+    return {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "image_size": args.image_size, "text_len": args.text_len, "parallelism": "dp%d" % world,
+            "itc_queue": "full (4096 entries, steady state)",
+            "l2": "per-step activations (>10 GB) exceed the 126 MB L2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    B = args.cpu_batch if args.steps <= 10 else 1  # bounded sample: keep K steps within a few minutes
-    sec = cpu_step_seconds(B, args.image_size, args.text_len, args.steps, min(args.warmup, 1), threads)
+    B = args.cpu_batch  # bounded sample of the workload: B pairs per step (one step is a few seconds on 16 cores)
+    sec, rec = cpu_baseline_record(B, args.image_size, args.text_len, args.steps, args.warmup)
     v = B / sec
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": 64, "image_size": args.image_size, "text_len": args.text_len,
-                   "reference_arm": "the reference's algorithm (oracle port; the reference package itself needs "
-                                    "pytorch_lightning/timm/sacred and cannot run on the GPU box) on all host cores, "
-                                    "bounded sample of B=%d pairs per step" % B},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": "B=%d pairs/step, %d timed steps, fp32, torch %d threads" % (B, args.steps, threads)},
+        "config": bench_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+        "reference_arm": "the reference's own CPU implementation of the path on all host cores (kind '%s'); each step is a "
+                         "bounded sample of B=%d pairs of the workload" % (rec["kind"], B),
+        "cpu_baseline": rec,
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -249,6 +313,7 @@ def run_ours(args):
         for n, p in model.named_parameters():
             if n.endswith(("alpha_i2t", "alpha_t2i")):
                 p.fill_(0.5)
+    fill_queues(model)  # steady-state ITC queues: every N and both arms time the same work
     model.train()
     fiber_utils.set_task(model)
     ops.set_dropout_seed(1234 + rank)
@@ -335,10 +400,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image_size": R, "text_len": L,
-                   "parallelism": "dp%d" % world, "l2": "per-step activations (>10 GB) exceed the 126 MB L2",
-                   "last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1),
-                   "kernel_options": _kernel_options()},
+        "config": bench_config(args, world),
+        "value_per_gpu": value / world,
+        "run_info": {"last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1), "kernel_options": _kernel_options(),
+                     "note": "`value` is the whole-job aggregate over n_gpus (contract); value_per_gpu is the metric's "
+                             "per-GPU figure"},
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -359,15 +425,65 @@ def run_ours(args):
                           "note": "whole step per GPU: pairs/s x 1636.23 GFLOP/pair"},
         "gemm_breakdown": gemm_stats["top"],
     }
+    if world == 1 and args.eager_baseline:
+        # the north-star's denominator: the reference PyTorch-eager GPU path, timed in this process after our arm
+        del step_model, model, dev_batch
+        line["eager_gpu_baseline"] = eager_gpu_baseline(args, dev, host, value)
     if args.cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        sec = cpu_step_seconds(args.cpu_batch, R, L, 1, 0, threads)
-        line["cpu_baseline"] = {"value": args.cpu_batch / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                "sample": "B=%d pairs, 1 step of the same ITM+ITC+MLM 384px workload, fp32 oracle port"
-                                          % args.cpu_batch}
+        _, line["cpu_baseline"] = cpu_baseline_record(args.cpu_batch, R, L, 1, 0)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def eager_gpu_baseline(args, dev, host, our_value):
+    """The UNMODIFIED reference (baseline/_ref) as PyTorch eager on this GPU under bf16 autocast — same workload, same
+    synthetic batch schema, full ITC queue, dropout / DropPath on, optimizer excluded — at the largest per-GPU batch of
+    64 / 32 / 16 / 8 that fits (the reference materialises every score matrix; SURVEY.md §7 'Eager baseline at B=64')."""
+    import gc
+    if not reference_available():
+        return {"unavailable": "reference package not installed (baseline/_ref missing)"}
+    from baseline import ref_harness
+    R, L = args.image_size, args.text_len
+    tried = []
+    for B in (args.batch, 32, 16, 8):
+        if B > args.batch or B in tried:
+            continue
+        tried.append(B)
+        gc.collect()
+        torch.cuda.empty_cache()
+        st = None
+        try:
+            st = ref_harness.RefStep(["itm", "itc", "mlm"], R, L, dev, autocast=torch.bfloat16)
+            batch = to_device(make_batch(B, R, L, seed=1234), dev, non_blocking=False)
+            for _ in range(2):
+                st(batch)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 3
+            e0.record()
+            for _ in range(n):
+                loss = st(batch)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            v = B / ms * 1e3
+            mem = torch.cuda.max_memory_allocated() / 2 ** 30
+            st.close()
+            return {"value": v, "unit": "pairs/s", "per_gpu_batch": B, "ms_per_step": ms, "dtype": "bf16 autocast",
+                    "impl": "unmodified reference (baseline/_ref), FIBERTransformerSS.training_step + backward, PyTorch eager",
+                    "steps": n, "warmup": 2, "last_loss": float(loss), "peak_mem_gib": round(mem, 1),
+                    "batches_tried": tried, "ours_over_eager": our_value / v}
+        except torch.cuda.OutOfMemoryError:
+            if st is not None:
+                st.close()
+            st = None
+            continue
+        except Exception as e:  # noqa: BLE001  (a label must never break the measurement)
+            if st is not None:
+                st.close()
+            return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:300]), "batches_tried": tried}
+    return {"unavailable": "out of memory at every batch size tried", "batches_tried": tried}
 
 
 def _kernel_options():
@@ -397,6 +513,7 @@ def main():
     ap.add_argument("--text-len", type=int, default=40)
     ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-eager-baseline", dest="eager_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,7 +23,8 @@ void set_last_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // "winattn_tc": bit 0 = tcgen05 window-attention forward, bit 1 = backward (window_attn_tc.cu) for the geometries it
-// covers (12x12 windows, shift 0 / 6); 0 = the mma.sync generation everywhere.  Default 3 (validated on B200 in round 2:
+// covers (12x12 windows, shift 0 / 6); 0 = the mma.sync generation everywhere; bit 2 / bit 3 select the fourth
+// generation (TMA-fed, quadrant token order) for the forward / backward.  Default 3 (validated on B200 in round 2:
 // gpurun_out/r2a_*), overridable by FIBER_WINATTN_TC; fiber_set_option(name, -1) returns to the default.
 static std::atomic<int> g_winattn_tc{-1};
 // "attn_small": bit 0 routes plain attention backward with <= 48 queries and keys (head_dim 64) to the 3-warp
@@ -46,11 +47,14 @@ int option_winattn_tc() {
   int v = g_winattn_tc.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_WINATTN_TC");
-    v = e ? (atoi(e) & 3) : 3;
+    v = e ? (atoi(e) & 15) : 3;
     g_winattn_tc.store(v, std::memory_order_relaxed);
   }
   return v;
 }
+
+static std::atomic<int> g_tq_trace{0};  // debug: event trace of the fourth-generation window backward (tools/tq_trace.py)
+int option_tq_trace() { return g_tq_trace.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached[64] = {0};
@@ -137,11 +141,15 @@ int64_t fiber_launch_count(void) { return fiber::g_launches.load(); }
 
 int fiber_set_option(const char* name, int32_t value) {
   if (name && strcmp(name, "winattn_tc") == 0) {
-    fiber::g_winattn_tc.store(value < 0 ? -1 : (value & 3), std::memory_order_relaxed);
+    fiber::g_winattn_tc.store(value < 0 ? -1 : (value & 15), std::memory_order_relaxed);
     return 0;
   }
   if (name && strcmp(name, "attn_small") == 0) {
     fiber::g_attn_small.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
+    return 0;
+  }
+  if (name && strcmp(name, "tq_trace") == 0) {
+    fiber::g_tq_trace.store(value > 0 ? 1 : 0, std::memory_order_relaxed);
     return 0;
   }
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");

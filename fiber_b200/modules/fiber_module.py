@@ -99,7 +99,7 @@ class FIBERTransformerSS(LightningModule):
             self.rank_output.bias.data = self.itm_score.fc.bias.data[1:]
 
         if config["load_path"] != "" and not config["test_only"]:
-            self._load(config["load_path"])
+            self._load(config["load_path"], adapt=True)
         if ln["vqa"] > 0:
             vs = config["vqav2_label_size"]
             self.vqa_classifier = nn.Sequential(nn.Linear(hs * 2, hs * 2), nn.LayerNorm(hs * 2), nn.GELU(),
@@ -111,11 +111,17 @@ class FIBERTransformerSS(LightningModule):
         if config["load_path"] != "" and config["test_only"]:
             self._load(config["load_path"])
 
-    def _load(self, path):
+    def _load(self, path, adapt=False):
+        """fiber_module.py:139-148 (fine-tuning start: relative-position tables resized from resolution_before to
+        image_size, e.g. the 384-px pre-training checkpoint at 576 px for VQA) and :174-180 (test_only: as is)."""
         state_dict = torch.load(path, map_location="cpu")["state_dict"]
         for key in ["image_queue", "text_queue", "queue_ptr", "queue_total", "image_input_queue", "text_input_queue",
                     "text_input_mask_queue"]:
             state_dict.pop(key, None)
+        if adapt:
+            state_dict = swin_transformer.swin_adapt_position_encoding(
+                state_dict, before=self.config.get("resolution_before", self.config["image_size"]),
+                after=self.config["image_size"])
         self.load_state_dict(state_dict, strict=False)
 
     @torch.no_grad()
@@ -248,9 +254,27 @@ class FIBERTransformerSS(LightningModule):
         output = self(batch)
         return sum([v for k, v in output.items() if "loss" in k])
 
+    def training_epoch_end(self, outs):
+        fiber_utils.epoch_wrapup(self)
+
     def validation_step(self, batch, batch_idx):
         fiber_utils.set_task(self)
-        return self(batch)
+        self(batch)  # returns None like the reference (:483-485): PL keeps step outputs for the whole epoch otherwise
+
+    def validation_epoch_end(self, outs):
+        fiber_utils.epoch_wrapup(self)
+
+    def test_step(self, batch, batch_idx):
+        """fiber_module.py:490-505 minus the captioning branch (out of scope)."""
+        fiber_utils.set_task(self)
+        output = self(batch)
+        ret = dict()
+        if self.config["loss_names"]["vqa"] > 0:
+            ret.update(objectives.vqa_test_step(self, batch, output))
+        return ret
+
+    def test_epoch_end(self, outs):
+        fiber_utils.epoch_wrapup(self)
 
     def configure_optimizers(self):
         return fiber_utils.set_schedule(self)

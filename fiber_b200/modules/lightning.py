@@ -51,32 +51,43 @@ class Metric(nn.Module):
         self.acc.zero_()
         self.total.zero_()
 
+    def batch_state(self, *a):
+        """(numerator, denominator) contributed by one batch."""
+        raise NotImplementedError
+
+    def update(self, *a):
+        num, den = self.batch_state(*a)
+        self.acc += num
+        self.total += den
+
     def forward(self, *a):
-        self.update(*a)
-        return self.compute()
+        """PL Metric.forward semantics (compute_on_step): accumulate the batch into the epoch state and return the value
+        of THIS batch — what the objectives log per step; the epoch value comes from compute() in epoch_wrapup."""
+        num, den = self.batch_state(*a)
+        self.acc += num
+        self.total += den
+        return num / den
 
 
 class Accuracy(Metric):  # gadgets/my_metrics.py:5-29
-    def update(self, logits, target):
+    def batch_state(self, logits, target):
         logits, target = logits.detach(), target.detach()
         preds = logits.argmax(dim=-1)
         keep = target != -100
         # same sums as the reference's boolean-mask indexing, without its two device->host syncs per update
         # (the mask is applied arithmetically; an all-ignored batch adds 0 / 0 exactly like the early return)
-        self.acc += ((preds == target) & keep).sum()
-        self.total += keep.sum()
+        return ((preds == target) & keep).sum().float(), keep.sum().float()
 
 
 class Scalar(Metric):  # gadgets/my_metrics.py:32-47
-    def update(self, scalar):
-        self.acc += scalar.detach().float() if isinstance(scalar, torch.Tensor) else float(scalar)
-        self.total += 1
+    def batch_state(self, scalar):
+        v = scalar.detach().float() if isinstance(scalar, torch.Tensor) else torch.tensor(float(scalar), device=self.acc.device)
+        return v, torch.ones((), device=self.acc.device)
 
 
 class VQAScore(Metric):  # gadgets/my_metrics.py:50-69
-    def update(self, logits, target):
+    def batch_state(self, logits, target):
         logits, target = logits.detach().float(), target.detach().float()
         idx = logits.max(1)[1]
         one_hots = torch.zeros_like(target).scatter_(1, idx.view(-1, 1), 1)
-        self.acc += (one_hots * target).sum()
-        self.total += len(idx)
+        return (one_hots * target).sum(), torch.tensor(float(len(idx)), device=self.acc.device)

@@ -173,3 +173,15 @@ def compute_vqa(pl_module, batch):
     pl_module.log(f"vqa/{phase}/loss", loss)
     pl_module.log(f"vqa/{phase}/score", score)
     return ret
+
+
+def vqa_test_step(pl_module, batch, output):
+    """objectives.py:652-668: argmax answers of a test batch (the id -> answer table lives in the datamodule)."""
+    try:
+        id2answer = pl_module.trainer.datamodule.dm_dicts["vqa_trainval"].id2answer if "vqa_trainval" in \
+            pl_module.trainer.datamodule.dm_dicts else pl_module.trainer.datamodule.dm_dicts["vqa"].id2answer
+    except Exception:  # noqa: BLE001  (no datamodule attached: return the label ids)
+        id2answer = None
+    vqa_preds = output["vqa_logits"].argmax(dim=-1)
+    vqa_preds = [id2answer[p.item()] if id2answer is not None else p.item() for p in vqa_preds]
+    return {"qids": batch.get("qid"), "preds": vqa_preds}

@@ -201,10 +201,33 @@ class RobertaModel(nn.Module):
 
     @classmethod
     def from_pretrained(cls, name, *a, **k):
-        """No network in this environment: builds roberta-base's architecture with fresh weights;
-        real weights arrive through load_state_dict of a FIBER checkpoint."""
-        assert name == "roberta-base", "FIBER-Base uses roberta-base"
-        return cls(RobertaConfig())
+        """HF `from_pretrained("roberta-base")` (fiber_module.py:88) without network access: the roberta-base weights
+        are read from a local file — FIBER_ROBERTA_WEIGHTS=/path/to/pytorch_model.bin (an HF RobertaModel /
+        RobertaForMaskedLM state_dict; `name` may also be a directory holding pytorch_model.bin).  Without one the
+        model keeps its random initialisation and says so LOUDLY: that is only right when a FIBER checkpoint is
+        loaded afterwards (config["load_path"]) or for synthetic benchmarks."""
+        import os
+        import warnings
+        if os.path.basename(str(name).rstrip("/")) not in ("roberta-base",) and not os.path.isdir(str(name)):
+            raise ValueError("FIBER-Base pairs Swin-B with roberta-base; got tokenizer/model name %r" % (name,))
+        model = cls(RobertaConfig())
+        path = os.environ.get("FIBER_ROBERTA_WEIGHTS", "")
+        if not path and os.path.isdir(str(name)) and os.path.exists(os.path.join(str(name), "pytorch_model.bin")):
+            path = os.path.join(str(name), "pytorch_model.bin")
+        if path and os.path.exists(path):
+            sd = torch.load(path, map_location="cpu")
+            sd = {(k[len("roberta."):] if k.startswith("roberta.") else k): v for k, v in sd.items()}
+            sd = {k: v for k, v in sd.items() if not k.startswith("lm_head.") and not k.endswith("position_ids")}
+            missing, unexpected = model.load_state_dict(sd, strict=False)
+            bad = [k for k in missing if "t2i" not in k and not k.endswith("position_ids")]
+            if bad:
+                raise RuntimeError("FIBER_ROBERTA_WEIGHTS lacks encoder tensors: %s ..." % bad[:5])
+        else:
+            warnings.warn("fiber_b200: RobertaModel.from_pretrained(%r) found no local weights (FIBER_ROBERTA_WEIGHTS is "
+                          "unset / missing and there is no network): the text tower is RANDOMLY INITIALISED. Load a FIBER "
+                          "checkpoint (load_path) or point FIBER_ROBERTA_WEIGHTS at roberta-base's pytorch_model.bin before "
+                          "training from scratch." % (name,), RuntimeWarning, stacklevel=2)
+        return model
 
     def get_extended_attention_mask(self, attention_mask, input_shape=None, device=None):
         """transformers 4.6.0 semantics: (1 - mask[:, None, None, :]) * -10000.0"""

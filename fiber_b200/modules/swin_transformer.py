@@ -283,12 +283,50 @@ def _init_vit_weights(m):
         nn.init.ones_(m.weight)
 
 
+def swin_adapt_position_encoding(state_dict, before=384, patch_size=32, after=384,
+                                 suffix="relative_position_bias_table"):
+    """swin_helpers.py:20-44 — a checkpoint trained at `before` pixels loaded at `after` pixels: window = size / 32, so
+    every (2w-1)^2-row relative-position table is resized bicubically to the new (2w'-1)^2 grid and the resolution-
+    dependent buffers (attn_mask, relative_position_index) are dropped from the dict (the model rebuilds them).
+    Mutates and returns `state_dict`."""
+    if after == before:
+        return state_dict
+    side_before, side_after = 2 * int(before / 32) - 1, 2 * int(after / 32) - 1
+    tables = [k for k in state_dict if k.endswith(suffix)]
+    if not tables:
+        raise AssertionError("no %s entries in the checkpoint" % suffix)
+    for k in tables:
+        t = state_dict[k]                                               # [(2w-1)^2, heads]
+        grid = t.t().reshape(1, -1, side_before, side_before)            # heads as channels
+        grid = torch.nn.functional.interpolate(grid, size=(side_after, side_after), mode="bicubic")
+        state_dict[k] = grid[0].permute(1, 2, 0).reshape(side_after * side_after, -1).contiguous()
+    for k in [k for k in state_dict if k.endswith(("attn_mask", "relative_position_index"))]:
+        del state_dict[k]
+    return state_dict
+
+
 def _create(pretrained=False, **kwargs):
     config = kwargs.pop("config")
-    if pretrained:
-        raise RuntimeError("pretrained Swin weights need network access; load a checkpoint with load_state_dict")
     kwargs.pop("num_classes", None)
-    return SwinTransformer(img_size=config["image_size"], **kwargs)
+    model = SwinTransformer(img_size=config["image_size"], **kwargs)
+    if pretrained:
+        # timm downloads the ImageNet-22k weights here (swin_helpers.py:183-261); this image has no network, so they
+        # must be supplied as a local file (a timm / official Swin checkpoint: {"model": state_dict} or a bare dict)
+        import os
+        path = os.environ.get("FIBER_SWIN_WEIGHTS", "")
+        if not path or not os.path.exists(path):
+            raise RuntimeError("pretrained_vit=True needs the Swin-B weights as a local file: set FIBER_SWIN_WEIGHTS=/path/to/"
+                               "swin_base_patch4_window12_384_22k.pth (no network access to download them)")
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("model", sd)
+        sd = {k: v for k, v in sd.items() if not k.startswith("head.")}
+        ckpt_res = 32 * ((int(round(sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape[0] ** 0.5)) + 1) // 2)
+        sd = swin_adapt_position_encoding(sd, before=ckpt_res, after=config["image_size"])
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        bad = [k for k in missing if "i2t" not in k and not k.endswith(("attn_mask", "relative_position_index"))]
+        if bad:
+            raise RuntimeError("FIBER_SWIN_WEIGHTS lacks backbone tensors: %s ..." % bad[:5])
+    return model
 
 
 def swin_base_patch4_window12_384_in22k(pretrained=False, **kwargs):

@@ -28,17 +28,31 @@ F32 = torch.float32
 LN_EPS = 1e-5
 
 _seed_counter = itertools.count(1)
-_base_seed = 0x5EED
+_base_seed = None  # resolved lazily: torch's seed (torch.manual_seed / pl.seed_everything) and the distributed rank
 
 
 def set_dropout_seed(seed):
+    """Pin the dropout / DropPath-independent hash stream explicitly (benchmarks, tests)."""
     global _base_seed, _seed_counter
     _base_seed = int(seed)
     _seed_counter = itertools.count(1)
 
 
+def _resolve_base_seed():
+    """Dropout masks come from counter-based hashes (not torch's Philox stream).  Their base seed follows
+    torch.initial_seed() — so torch.manual_seed / pl.seed_everything select the mask sequence — and differs per
+    data-parallel rank (identical masks on every rank would correlate the replicas' gradients)."""
+    global _base_seed
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    _base_seed = (int(torch.initial_seed()) * 2654435761 + 0x9E3779B97F4A7C15 * (rank + 1)) & 0x7FFFFFFF
+    return _base_seed
+
+
 def _next_seed():
-    return (_base_seed * 1000003 + next(_seed_counter)) & 0x7FFFFFFFFFFF
+    base = _base_seed if _base_seed is not None else _resolve_base_seed()
+    return (base * 1000003 + next(_seed_counter)) & 0x7FFFFFFFFFFF
 
 
 # ---------------------------------------------------------------------------------------------
@@ -47,11 +61,22 @@ def _next_seed():
 class _WeightCache:
     """bf16 [N,K] and transposed [K,N] copies of (packed) fp32 Linear weights; packed fp32 biases.
     Refreshed whenever any source parameter's in-place version counter changes (optimizer step,
-    load_state_dict)."""
+    load_state_dict).  NOTE: writes through `param.data` (EMA, manual clipping via p.data.mul_) do not bump the version
+    counter — call CACHE.clear() after such an update.  Entries whose parameters have been garbage-collected are
+    evicted whenever the cache grows (models come and go in tests / sweeps)."""
 
     def __init__(self):
         self._w = {}
         self._b = {}
+        self._sweep_at = 256
+
+    def _sweep(self):
+        if len(self._w) + len(self._b) < self._sweep_at:
+            return
+        for d, ri in ((self._w, 3), (self._b, 2)):
+            for key in [k for k, v in d.items() if any(r() is None for r in v[ri])]:
+                del d[key]
+        self._sweep_at = max(256, 2 * (len(self._w) + len(self._b)))
 
     @staticmethod
     def _key(ps):
@@ -83,6 +108,7 @@ class _WeightCache:
                 K.cast_transpose(m, w[n0:n0 + n], None if wt is None else wt[:, n0:n0 + n])
                 n0 += n
         self._w[ids] = (vers, w, wt, tuple(weakref.ref(p) for p in ps))
+        self._sweep()
         return w, wt
 
     def bias(self, ps):
@@ -95,6 +121,7 @@ class _WeightCache:
         with torch.no_grad():
             b = torch.cat([p.detach() for p in ps])
         self._b[ids] = (vers, b, tuple(weakref.ref(p) for p in ps))
+        self._sweep()
         return b
 
     def clear(self):

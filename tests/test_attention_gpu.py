@@ -38,7 +38,8 @@ def test_window_attention_fwd_bwd(cuda_dev, B, H, ws, shift, nh):
 TC_CASES = WINDOW_CASES + [(64, 12, 12, 0, 32), (5, 96, 12, 6, 4), (3, 24, 12, 6, 16), (1, 48, 12, 0, 8)]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3], ids=["mmasync", "tcfwd", "tcbwd", "tcboth"])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5, 7, 11, 15],
+                         ids=["mmasync", "tcfwd", "tcbwd", "tcboth", "tqfwd", "tqfwd_tcbwd", "tcfwd_tqbwd", "tqboth"])
 @pytest.mark.parametrize("B,H,ws,shift,nh", TC_CASES)
 def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
     from fiber_b200 import lib
@@ -51,7 +52,7 @@ def test_window_attention_tcgen05(cuda_dev, B, H, ws, shift, nh, mode):
         lib.set_option("winattn_tc", -1)  # back to the default
     launched = lib.get_option("winattn_tc_launches") - before
     covered = ws == 12 and shift in (0, 6)
-    assert launched == ((mode & 1) + (mode >> 1) if covered else 0)
+    assert launched == ((mode & 1) + ((mode >> 1) & 1) if covered else 0)
 
 
 def _diag(name, got, ref, src, N, hd):
