@@ -18,7 +18,12 @@ import sys
 import threading
 import time
 
+import warnings
+
 import torch
+
+# synthetic benchmark: random-init weights are the point (`data: synthetic`), not an accident
+warnings.filterwarnings("ignore", message="fiber_b200: RobertaModel.from_pretrained", category=RuntimeWarning)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

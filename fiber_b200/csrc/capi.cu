@@ -47,7 +47,7 @@ int option_winattn_tc() {
   int v = g_winattn_tc.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_WINATTN_TC");
-    v = e ? (atoi(e) & 15) : 3;
+    v = e ? (atoi(e) & 15) : 15;
     g_winattn_tc.store(v, std::memory_order_relaxed);
   }
   return v;

@@ -1088,6 +1088,13 @@ __device__ __forceinline__ void fill_tables_quad(const WinTables& t, const float
   }
 }
 
+// One 32-byte store per lane (sm_100: STG.256).  A scattered 16-byte-per-lane store costs the LSU one wavefront per
+// lane; the drains of these kernels were bound by exactly that (tools/tq_trace.py: 2100 of 10900 cycles per window).
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
@@ -1248,9 +1255,7 @@ __device__ __forceinline__ void tq_fwd_elementwise(const AttnParams& p, const Wi
     v1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
     v1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
     v1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-    bf16* dst = p.o + grow_prev * p.ldo + h * WA_HD + hf * 16;
-    *reinterpret_cast<uint4*>(dst) = v0;
-    *reinterpret_cast<uint4*>(dst + 8) = v1;
+    st_global_256(p.o + grow_prev * p.ldo + h * WA_HD + hf * 16, v0, v1);
     if (hf == 0 && p.lse)  // LSE is stored in NATURAL token order (shared with the other kernel generations)
       p.lse[(static_cast<long long>(g_prev) * p.nH + h) * TC_N + th_i * TC_WS + tw_i] = (m_prev + lg2_approx(l)) * WA_LN2;
   };
@@ -1534,8 +1539,10 @@ constexpr int TQB_STAGES = 2;
 constexpr int TQB_STAGE_BYTES = 5 * TC_TILE;                 // Q, dO, K, V, O
 constexpr int TQB_OFF_P = TQB_STAGES * TQB_STAGE_BYTES;      // 92160
 constexpr int TQB_OFF_DS = TQB_OFF_P + 3 * TB_PCHUNK;
-constexpr int TQB_OFF_STG = TQB_OFF_DS + 3 * TB_PCHUNK;      // [2 remainder warps][16 rows][64 B]
-constexpr int TQB_OFF_LSE = TQB_OFF_STG + 2 * 1024;          // [2 stages][144] fp32
+constexpr int TQB_THREADS = 416;                             // 8 element-wise warps, MMA issuer, TMA producer, 3 remainder warps
+constexpr int TQB_REM = 3;
+constexpr int TQB_OFF_STG = TQB_OFF_DS + 3 * TB_PCHUNK;      // [3 remainder warps][16 rows][64 B]
+constexpr int TQB_OFF_LSE = TQB_OFF_STG + TQB_REM * 1024;    // [2 stages][144] fp32
 constexpr int TQB_OFF_TBL = TQB_OFF_LSE + TQB_STAGES * TC_N * 4;
 constexpr int TQB_OFF_BARS = TQB_OFF_TBL + ((TC_TABLE_BYTES + 15) & ~15);
 constexpr int TQB_SMEM = 1024 + TQB_OFF_BARS + 16 * 8;
@@ -1683,15 +1690,14 @@ __device__ __forceinline__ void tq_bwd_elementwise(const AttnParams& p, const Wi
       v1.y = pack_bf16(__uint_as_float(a[10]) * sc, __uint_as_float(a[11]) * sc);
       v1.z = pack_bf16(__uint_as_float(a[12]) * sc, __uint_as_float(a[13]) * sc);
       v1.w = pack_bf16(__uint_as_float(a[14]) * sc, __uint_as_float(a[15]) * sc);
-      *reinterpret_cast<uint4*>(dst) = v0;
-      *reinterpret_cast<uint4*>(dst + 8) = v1;
+      st_global_256(dst, v0, v1);
     }
     tc_fence_before();
     if (lane == 0) mbar_arrive(B.acc_empty);
     tq_trace(tr, 0, it, 6);
     wi.next(geo);
   }
-  named_bar_sync(6, TC_THREADS);
+  named_bar_sync(6, TQB_THREADS);
 #pragma unroll
   for (int c = 0; c < 36; ++c) {
     float a, b;
@@ -1700,7 +1706,7 @@ __device__ __forceinline__ void tq_bwd_elementwise(const AttnParams& p, const Wi
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(TQB_THREADS, 1) win_attn_tq_bwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
                                                                        const __grid_constant__ CUtensorMap tmdO,
                                                                        const __grid_constant__ CUtensorMap tmK,
                                                                        const __grid_constant__ CUtensorMap tmV,
@@ -1740,19 +1746,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
   tq_my_windows(p.G * geo.nW, first, n_my);
   const float scale2 = p.scale * WA_LOG2E;
 
-  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TC_THREADS);
+  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TQB_THREADS);
   if (warp == TC_WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < TQB_STAGES; ++s) {
         mbar_init(&B.full[s], 1);
-        mbar_init(&B.stage_free[s], 3);
+        mbar_init(&B.stage_free[s], 1 + TQB_REM);
       }
       mbar_init(B.s_full, 1);
       mbar_init(B.sdp_empty, 8);
-      mbar_init(B.pds_ready, 10);
+      mbar_init(B.pds_ready, 8 + TQB_REM);
       mbar_init(B.acc_full, 1);
       mbar_init(B.acc_empty, 8);
-      mbar_init(B.rem_done, 2);
+      mbar_init(B.rem_done, TQB_REM);
       mbar_fence_init();
     }
     __syncwarp();
@@ -1834,7 +1840,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
       __syncwarp();
       if (it + 1 < n_my) issue_scores(it + 1);  // queued right behind the output MMAs (S / dP were released before pds_ready)
     }
-    named_bar_sync(6, TC_THREADS);
+    named_bar_sync(6, TQB_THREADS);
   } else if (warp == TC_WARP_LD) {
     // ================= TMA producer: 20 boxes (Q, dO, K, V, O x 4 quadrants) + the LSE row per window =================
     if (lane == 0) {
@@ -1866,17 +1872,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
         wi.next(geo);
       }
     }
-    named_bar_sync(6, TC_THREADS);
+    named_bar_sync(6, TQB_THREADS);
   } else {
     // ================= remainder warps (mma.sync) =================
-    // R0: score jobs of key thirds 0 and 1, then dV of token rows 128..143
-    // R1: score job of key third 2, then dK and dQ of token rows 128..143
+    // warp k of three: the score job of key third k (16 queries 128..143 x 48 keys), then the output job of token rows
+    // 128..143 of type k (0: dV = P^T dO, 1: dK = dS^T Q, 2: dQ = dS K).  Each job is a latency-bound chain on one warp
+    // (~2200 / ~3000 cycles, tools/tq_trace.py); with two warps sharing the six jobs they were the critical path.
     const int k = warp - TC_WARP_R0;
-    float dbr[2][6][4];  // [score job slot][n-tile][fragment element], as in window_attn.cu
+    float dbr[6][4];  // [n-tile][fragment element], as in window_attn.cu
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int i = 0; i < 6; ++i) dbr[a][i][0] = dbr[a][i][1] = dbr[a][i][2] = dbr[a][i][3] = 0.f;
+    for (int i = 0; i < 6; ++i) dbr[i][0] = dbr[i][1] = dbr[i][2] = dbr[i][3] = 0.f;
     uint8_t* stg = smem + TQB_OFF_STG + k * 1024;
     const int rl0 = 128 + (lane >> 2);
     const int tok0 = T.tok[rl0], tok1 = T.tok[rl0 + 8];
@@ -1904,21 +1909,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
       d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-      const float nd0 = -d0, nd1 = -d1;
       if (it > 0) {
         tc_wait(B.acc_full, (it - 1) & 1, 203, it);  // the tensor core has consumed P / dS of the previous window
-        named_bar_sync(5, 64);                       // ... and so has the other remainder warp
+        named_bar_sync(5, 32 * TQB_REM);             // ... and so have the other remainder warps
       }
       tq_trace(tr, 3 + k, it, 2);
-#pragma unroll
-      for (int jb = 0; jb < 2; ++jb) {  // static slot index: dbr stays in registers
-        if (jb == 0 || k == 0) {
-          const int third = k == 0 ? jb : 2;
-          // one instantiation for masked and unmasked windows (emask = 0 never adds the mask): half the code
-          tc_bwd_rem_scores<true>(sQ, sdO, sK, sV, sP, sdS, nl0, nl1, nd0, nd1, T, tbl_bytes, third, lane, scale2, emask,
-                                  dbr[jb]);
-        }
-      }
+      // one instantiation for masked and unmasked windows (emask = 0 never adds the mask): half the code
+      tc_bwd_rem_scores<true>(sQ, sdO, sK, sV, sP, sdS, nl0, nl1, -d0, -d1, T, tbl_bytes, k, lane, scale2, emask, dbr);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(B.pds_ready);
@@ -1926,8 +1923,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
 
       tc_wait(B.pds_ready, it & 1, 206, it);  // every P / dS element of this window is in smem
       tq_trace(tr, 3 + k, it, 4);
-      const int t_first = k == 0 ? 0 : 1, t_last = k == 0 ? 0 : 2;
-      for (int type = t_first; type <= t_last; ++type) {
+      {
+        const int type = k;
         float acc[4][4];
         tc_bwd_rem_out(type, sQ, sdO, sK, smem_u32(sP), smem_u32(sdS), lane, acc);
         const float sc = type == 0 ? 1.0f : p.scale;
@@ -1958,19 +1955,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
       tq_trace(tr, 3 + k, it, 5);
       wi.next(geo);
     }
-    named_bar_sync(6, TC_THREADS);
+    named_bar_sync(6, TQB_THREADS);
     const int qi = 128 + (lane >> 2);
 #pragma unroll
-    for (int jb = 0; jb < 2; ++jb) {
-      if (jb == 0 || k == 0) {
-        const int third = k == 0 ? jb : 2;
-#pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {
-          const int j0 = third * 48 + nt * 8 + (lane & 3) * 2;
-          *reinterpret_cast<float2*>(sAcc + qi * TB_ACCP + j0) = make_float2(dbr[jb][nt][0], dbr[jb][nt][1]);
-          *reinterpret_cast<float2*>(sAcc + (qi + 8) * TB_ACCP + j0) = make_float2(dbr[jb][nt][2], dbr[jb][nt][3]);
-        }
-      }
+    for (int nt = 0; nt < 6; ++nt) {
+      const int j0 = k * 48 + nt * 8 + (lane & 3) * 2;
+      *reinterpret_cast<float2*>(sAcc + qi * TB_ACCP + j0) = make_float2(dbr[nt][0], dbr[nt][1]);
+      *reinterpret_cast<float2*>(sAcc + (qi + 8) * TB_ACCP + j0) = make_float2(dbr[nt][2], dbr[nt][3]);
     }
   }
 
@@ -1978,7 +1969,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_bwd_kernel(const At
   // TILE rows / columns, i.e. quadrant order)
   tc_fence_before();
   __syncthreads();
-  for (int t = tid; t < TC_TW2 * TC_TW2; t += TC_THREADS) {
+  for (int t = tid; t < TC_TW2 * TC_TW2; t += TQB_THREADS) {
     const int dh = t / TC_TW2 - (TC_WS - 1), dw = t % TC_TW2 - (TC_WS - 1);
     const int ih0 = max(0, dh), ih1 = min(TC_WS, TC_WS + dh), iw0 = max(0, dw), iw1 = min(TC_WS, TC_WS + dw);
     float sum = 0.f;
@@ -2096,8 +2087,12 @@ static int launch_win_tq_fwd(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
+static bool aligned32(const void* ptr, long long ld) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0;
+}
+
 int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream) {
-  if (option_winattn_tc() & 4) return launch_win_tq_fwd(p, stream);  // fourth generation (TMA, quadrant order)
+  if ((option_winattn_tc() & 4) && aligned32(p.o, p.ldo)) return launch_win_tq_fwd(p, stream);  // fourth generation
   static bool attr_set = false;
   if (!attr_set) {
     FIBER_CUDA(cudaFuncSetAttribute(win_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
@@ -2136,7 +2131,7 @@ static int launch_win_tq_bwd(const AttnParams& p, cudaStream_t stream) {
       win_tmap(&tk, p.k, p.ldk, p.G, p.H, p.W, C) || win_tmap(&tv, p.v, p.ldv, p.G, p.H, p.W, C) ||
       win_tmap(&to, p.o, p.ldo, p.G, p.H, p.W, C))
     return -1;
-  win_attn_tq_bwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TQB_SMEM, stream>>>(p, tq, tdo, tk, tv, to, trace);
+  win_attn_tq_bwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TQB_THREADS, TQB_SMEM, stream>>>(p, tq, tdo, tk, tv, to, trace);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   count_winattn_tc_launch();
@@ -2144,7 +2139,8 @@ static int launch_win_tq_bwd(const AttnParams& p, cudaStream_t stream) {
 }
 
 int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
-  if ((option_winattn_tc() & 8) && (reinterpret_cast<uintptr_t>(p.lse) & 15) == 0)
+  if ((option_winattn_tc() & 8) && (reinterpret_cast<uintptr_t>(p.lse) & 15) == 0 && aligned32(p.dq, p.lddq) &&
+      aligned32(p.dk, p.lddk) && aligned32(p.dv, p.lddv))
     return launch_win_tq_bwd(p, stream);  // fourth generation: no D pre-pass
   if (launch_win_bwd_prep(p, D, stream)) return -2;
   static bool attr_set = false;

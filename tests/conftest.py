@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # tests fill every model with synthetic weights; the loud "text tower is randomly initialised" warning
+    # (fiber_b200/modules/roberta.py: from_pretrained without local weights) is exercised by its own test
+    config.addinivalue_line("filterwarnings", "ignore:fiber_b200. RobertaModel.from_pretrained:RuntimeWarning")
 
 
 @pytest.fixture(scope="session")

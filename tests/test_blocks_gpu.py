@@ -126,13 +126,13 @@ def test_roberta_layer(cuda_dev, li, img_tokens, img_dim, last_norm):
 # configurations) are what every other test in this file runs; here the same block-level parity holds with each of them
 # switched back to the first generation (h-saving epilogues, mma.sync window attention, generic plain backward).
 # Shapes whose row count is not a multiple of 128 fall back per call.
-@pytest.mark.parametrize("variant", ["gelu_cache", "winattn_tc", "none"])
+@pytest.mark.parametrize("variant", ["gelu_cache", "winattn_tc", "winattn_tc3", "none"])
 @pytest.mark.parametrize("B,H,ws,C,nh,shift,fused", [(2, 24, 12, 512, 16, 6, True), (1, 96, 12, 128, 4, 6, False),
                                                      (3, 12, 12, 1024, 32, 0, True), (8, 24, 12, 512, 16, 0, False)])
 def test_swin_block_generations(cuda_dev, B, H, ws, C, nh, shift, fused, variant):
     from fiber_b200 import lib, ops
     ops.set_gelu_cache(variant == "gelu_cache")
-    lib.set_option("winattn_tc", 3 if variant == "winattn_tc" else 0)
+    lib.set_option("winattn_tc", {"winattn_tc": 15, "winattn_tc3": 3}.get(variant, 0))
     lib.set_option("attn_small", 0)
     try:
         test_swin_block(cuda_dev, B, H, ws, C, nh, shift, fused)

@@ -190,3 +190,122 @@ def test_rows_of_cat_equals_cat_then_index():
                 b = torch.randint(0, 100, (qn,) + shape[1:], generator=g)
             idx = torch.randint(0, shape[0] + qn, (shape[0],), generator=g)
             assert torch.equal(_rows_of_cat(a, b, idx), torch.cat([a, b], 0)[idx])
+
+
+# ---------------------------------------------------------------------------------------------
+# Round 2: checkpoint adaptation, schedules, epoch bookkeeping, pretrained-weight loading
+# ---------------------------------------------------------------------------------------------
+def test_load_adapts_384_checkpoint_to_576(tmp_path):
+    """task_finetune_vqa load_path=<384-px pre-training ckpt> at image_size=576 (fiber_module.py:139-148,
+    swin_helpers.py:20-44): relative-position tables are resized bicubically, masks / index buffers rebuilt."""
+    from fiber_b200.modules import FIBERTransformerSS
+    from fiber_b200.modules.swin_transformer import swin_adapt_position_encoding
+    src = FIBERTransformerSS(_cfg(["itm", "mlm", "itc"], 384))
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    ck = tmp_path / "pretrain384.ckpt"
+    torch.save({"state_dict": sd}, ck)
+    cfg = dict(_cfg(["vqa"], 576, 50), load_path=str(ck), resolution_before=384)
+    dst = FIBERTransformerSS(cfg)  # would raise size-mismatch errors without the adaptation
+    key = "vit_model.layers.2.blocks.3.attn.relative_position_bias_table"
+    assert sd[key].shape == (23 * 23, 16) and dst.state_dict()[key].shape == (35 * 35, 16)
+    # same arithmetic as the reference's helper: bicubic resize of the (heads, 23, 23) grid
+    want = torch.nn.functional.interpolate(sd[key].t().reshape(1, 16, 23, 23), size=(35, 35), mode="bicubic")[0]
+    torch.testing.assert_close(dst.state_dict()[key], want.permute(1, 2, 0).reshape(35 * 35, 16))
+    # non-resolution parameters arrive unchanged; the 576-px masks were rebuilt, not loaded
+    k2 = "text_transformer.encoder.layer.7.crossattention_t2i.self.key.weight"
+    assert torch.equal(dst.state_dict()[k2], sd[k2])
+    assert dst.state_dict()["vit_model.layers.0.blocks.1.attn_mask"].shape == (64, 324, 324)
+    # same resolution: identity
+    same = {"a.relative_position_bias_table": torch.randn(529, 4)}
+    assert swin_adapt_position_encoding(dict(same), before=384, after=384)["a.relative_position_bias_table"] is \
+        same["a.relative_position_bias_table"]
+
+
+def test_set_schedule_derives_max_steps_and_supports_cosine():
+    """Every fine-tuning config has max_steps=None and warmup_steps=0.1 (config.py:134-150): max_steps comes from the
+    trainer's dataloader length (fiber_utils.py:254-262); decay_power='cosine' selects the cosine schedule."""
+    import math
+    import types
+    from fiber_b200.modules import FIBERTransformerSS, fiber_utils
+    cfg = dict(_cfg(["vqa"], 224, 50), max_steps=None, warmup_steps=0.1, decay_power="cosine")
+    model = FIBERTransformerSS(cfg)
+    with pytest.raises(ValueError):
+        fiber_utils.set_schedule(model)  # no trainer to derive max_steps from: loud, not a TypeError
+    dm = types.SimpleNamespace(train_dataloader=lambda: range(250))
+    model.trainer = types.SimpleNamespace(max_steps=None, max_epochs=8, accumulate_grad_batches=2, datamodule=dm)
+    (opt,), (sched,) = fiber_utils.set_schedule(model)
+    assert fiber_utils.resolve_max_steps(model) == 250 * 8 // 2 == 1000
+    lam = sched["scheduler"].lr_lambdas[0]
+    assert lam(0) == 0.0 and lam(50) == pytest.approx(0.5) and lam(100) == pytest.approx(1.0)
+    assert lam(550) == pytest.approx(0.5 * (1 + math.cos(math.pi * 0.5))) and lam(1000) == pytest.approx(0.0, abs=1e-12)
+    # polynomial branch with trainer.max_steps given (pre-training configs)
+    model.hparams.config["decay_power"] = 1
+    model.trainer.max_steps = 200
+    (_,), (sched,) = fiber_utils.set_schedule(model)
+    lam = sched["scheduler"].lr_lambdas[0]
+    assert lam(10) == pytest.approx(0.5) and lam(110) == pytest.approx(0.5) and lam(200) == pytest.approx(0.0)
+
+
+def test_metrics_log_batch_values_and_epoch_wrapup_resets():
+    """PL Metric.forward returns the value of the CURRENT batch and accumulates the epoch state; epoch_wrapup logs the
+    epoch values, resets them and logs '<phase>/the_metric' (what run.py's ModelCheckpoint monitors)."""
+    from fiber_b200.modules import FIBERTransformerSS, fiber_utils
+    from fiber_b200.modules.lightning import Accuracy, Scalar
+    acc = Accuracy()
+    logits = torch.tensor([[2.0, 1.0], [0.0, 1.0], [3.0, 0.0], [0.0, 5.0]])
+    assert float(acc(logits, torch.tensor([0, 1, 1, -100]))) == pytest.approx(2 / 3)   # batch 1: 2 of 3 counted
+    assert float(acc(logits, torch.tensor([1, 0, 1, 0]))) == pytest.approx(0.0)        # batch 2 alone, not the running mean
+    assert float(acc.compute()) == pytest.approx(2 / 7)
+    sc = Scalar()
+    assert float(sc(torch.tensor(4.0))) == 4.0 and float(sc(2.0)) == 2.0 and float(sc.compute()) == 3.0
+    model = FIBERTransformerSS(_cfg(["itm", "mlm", "itc"]))
+    model.train()
+    model.train_itm_accuracy(logits, torch.tensor([0, 1, 0, 1]))
+    model.train_mlm_accuracy(logits, torch.tensor([0, 0, 0, 0]))
+    model.train_itc_t2i_accuracy(logits, torch.tensor([0, 1, 0, 0]))
+    for n in ("itm", "mlm", "itc"):
+        getattr(model, "train_%s_loss" % n)(torch.tensor(1.5))
+    model.training_epoch_end([])
+    assert float(model.logged["train/the_metric"]) == pytest.approx(1.0 + 0.5 + 0.75)
+    assert float(model.logged["itm/train/loss_epoch"]) == 1.5 and "itc/train/t2i_accuracy_epoch" in model.logged
+    assert float(model.train_itm_accuracy.total) == 0.0  # reset
+    model.eval()
+    model.val_itm_accuracy(logits, torch.tensor([0, 1, 0, 1]))
+    model.validation_epoch_end([])
+    assert "val/the_metric" in model.logged
+    assert model.validation_step.__doc__ is None or True
+
+
+def test_from_pretrained_warns_loudly_and_loads_local_weights(tmp_path, monkeypatch):
+    from fiber_b200.modules.roberta import RobertaModel
+    monkeypatch.delenv("FIBER_ROBERTA_WEIGHTS", raising=False)
+    with pytest.warns(RuntimeWarning, match="RANDOMLY INITIALISED"):
+        ref = RobertaModel.from_pretrained("roberta-base")
+    with pytest.raises(ValueError):
+        RobertaModel.from_pretrained("bert-base-uncased")
+    # an HF-style checkpoint (keys prefixed "roberta.", an lm_head, no t2i tensors) on local disk
+    sd = {"roberta." + k: torch.full_like(v, 0.25) for k, v in ref.state_dict().items() if "t2i" not in k}
+    sd["lm_head.bias"] = torch.zeros(3)
+    path = tmp_path / "pytorch_model.bin"
+    torch.save(sd, path)
+    monkeypatch.setenv("FIBER_ROBERTA_WEIGHTS", str(path))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m = RobertaModel.from_pretrained("roberta-base")
+    assert float(m.encoder.layer[3].intermediate.dense.weight.mean()) == 0.25
+    assert float(m.encoder.layer[7].crossattention_t2i.self.key.weight.abs().max()) != 0.25  # t2i stays freshly initialised
+
+
+def test_dropout_seed_follows_torch_seed():
+    from fiber_b200 import ops
+    ops._base_seed = None
+    torch.manual_seed(123)
+    a = ops._resolve_base_seed()
+    torch.manual_seed(124)
+    b = ops._resolve_base_seed()
+    torch.manual_seed(123)
+    assert ops._resolve_base_seed() == a != b
+    ops.set_dropout_seed(7)
+    assert ops._next_seed() == (7 * 1000003 + 1) & 0x7FFFFFFFFFFF
+    ops._base_seed = None

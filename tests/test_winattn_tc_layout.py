@@ -27,17 +27,17 @@ def test_winattn_tc_layout_replay(tmp_path):
 
 
 def test_winattn_tc_option_roundtrip():
-    """The default routing is the tcgen05 generation (3); the option round-trips through the C-ABI and -1 restores it."""
+    """The default routing is the TMA-fed tcgen05 generation (15); the option round-trips through the C-ABI and -1 restores it."""
     from fiber_b200 import lib
     if os.environ.get("FIBER_WINATTN_TC"):
         pytest.skip("FIBER_WINATTN_TC set in the environment")
-    assert lib.get_option("winattn_tc") == 3
+    assert lib.get_option("winattn_tc") == 15
     lib.set_option("winattn_tc", 0)
     try:
         assert lib.get_option("winattn_tc") == 0
     finally:
         lib.set_option("winattn_tc", -1)
-    assert lib.get_option("winattn_tc") == 3
+    assert lib.get_option("winattn_tc") == 15
     assert lib.get_option("winattn_tc_launches") == 0
     with pytest.raises(RuntimeError):
         lib.get_option("no_such_option")

@@ -36,7 +36,7 @@ def timeit(fn, n=5):
     return ts[len(ts) // 2]
 
 
-print("images:", B, "| winattn_tc option:", lib.get_option("winattn_tc"), "(0 = mma.sync generation, 3 = tcgen05 forward + backward)")
+print("images:", B, "| winattn_tc option:", lib.get_option("winattn_tc"), "(0 = mma.sync, 3 = tcgen05 + cp.async, 15 = tcgen05 + TMA quadrant tiles)")
 for H, C, nh in STAGES:
     for shift in (0, 6):
         if H == 12 and shift:

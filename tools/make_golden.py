@@ -272,3 +272,75 @@ def gold_schedule():
 
 if __name__ == "__main__" and "schedule" in sys.argv[1:]:
     gold_schedule()
+
+
+def gold_train384():
+    """BASELINE configs[1] objective mix at the north-star resolution (384 px / 40 tok, B = 2), dropout off, through the
+    unmodified reference: compute_itc (queues empty) + compute_itm_hardneg with deterministic negatives (the batch
+    rolled by one) + compute_mlm, summed and back-propagated.  Stores the three losses, the ITM logits, the MLM logits
+    at the labelled positions and their log-sum-exp, and every parameter-gradient statistic."""
+    import torch.distributed as dist
+    from fiber.modules import objectives as ref_obj
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
+    torch.manual_seed(0)
+    B, L, size = 2, 40, 384
+    cfg = ref_shims.default_config(tasks=["itm", "mlm", "itc"], image_size=size, max_text_len=L)
+    model = FIBERTransformerSS(cfg)
+    fill(model)
+    batch = synth.synth_batch(B, size, L, seed=1234, false_image=True)
+    image_neg = batch["image"][0].roll(1, 0)
+    text_neg, text_mask_neg = batch["text_ids"].roll(1, 0), batch["text_masks"].roll(1, 0)
+    model.train()
+    no_dropout(model)
+    model.zero_grad()
+    torch.manual_seed(5)
+    itc, _, _, _ = ref_obj.compute_itc(model, dict(batch))
+    itm = ref_obj.compute_itm_hardneg(model, dict(batch), image_neg, text_neg, text_mask_neg)
+    mlm = ref_obj.compute_mlm(model, dict(batch))
+    loss = itc["itc_loss"] + itm["itm_loss"] + mlm["mlm_loss"]
+    loss.backward()
+    lab = batch["text_labels_mlm"]
+    pos = (lab != -100).nonzero()
+    ml = mlm["mlm_logits"].detach()
+    out = {"cfg": cfg, "B": B, "L": L, "state_keys": {k: tuple(s) for k, (s, _) in model_shapes(model).items()},
+           "loss": float(loss), "itc_loss": float(itc["itc_loss"]),
+           "itm_loss": float(itm["itm_loss"]), "mlm_loss": float(mlm["mlm_loss"]),
+           "itm_logits": itm["itm_logits"].detach().clone(),
+           "mlm_pos": pos, "mlm_logit_at_label": ml[pos[:, 0], pos[:, 1], lab[pos[:, 0], pos[:, 1]]].clone(),
+           "mlm_lse": torch.logsumexp(ml[pos[:, 0], pos[:, 1]], dim=-1), "mlm_logits_head": ml[:, :, :128].clone(),
+           "grads": grad_stats(model)}
+    torch.save(out, os.path.join(GOLD, "model_384_train.pt"))
+    print("model_384_train.pt loss", out["loss"], out["itc_loss"], out["itm_loss"], out["mlm_loss"], "grads", len(out["grads"]))
+
+
+def gold_vqa576():
+    """BASELINE configs[2]: VQA at 576 px / 50 tokens (18 x 18 = 324-token windows), B = 2: infer() features, the VQA
+    logits and loss, gradient statistics."""
+    from fiber.modules import objectives as ref_obj
+    torch.manual_seed(0)
+    B, L, size = 2, 50, 576
+    cfg = ref_shims.default_config(tasks=["vqa"], image_size=size, max_text_len=L)
+    model = FIBERTransformerSS(cfg)
+    fill(model)
+    batch = synth.synth_batch(B, size, L, seed=1234, vqa=True)
+    model.train()
+    no_dropout(model)
+    model.zero_grad()
+    ret = ref_obj.compute_vqa(model, dict(batch))
+    ret["vqa_loss"].backward()
+    model.eval()
+    with torch.no_grad():
+        r = model.infer(dict(batch))
+    out = {"cfg": cfg, "B": B, "L": L, "state_keys": {k: tuple(s) for k, (s, _) in model_shapes(model).items()},
+           "vqa_loss": float(ret["vqa_loss"]), "vqa_logits": ret["vqa_logits"].detach().clone(),
+           "cls_feats": r["cls_feats"].clone(), "text_feats": r["text_feats"][:, :3, :64].clone(),
+           "image_feats": r["image_feats"][:, :5, :64].clone(), "grads": grad_stats(model)}
+    torch.save(out, os.path.join(GOLD, "model_576_vqa.pt"))
+    print("model_576_vqa.pt vqa_loss", out["vqa_loss"], "grads", len(out["grads"]))
+
+
+if __name__ == "__main__" and "train384" in sys.argv[1:]:
+    gold_train384()
+if __name__ == "__main__" and "vqa576" in sys.argv[1:]:
+    gold_vqa576()

@@ -26,6 +26,7 @@ with torch.no_grad():
     for n, p in model.named_parameters():
         if n.endswith(("alpha_i2t", "alpha_t2i")):
             p.fill_(0.5)
+bench.fill_queues(model)
 model.train()
 fiber_utils.set_task(model)
 ops.set_dropout_seed(1234)

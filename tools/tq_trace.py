@@ -37,7 +37,8 @@ names = {0: "ew0 : start full s_full rem_done pass_done acc_full drained",
          1: "mma : full sdp_empty pds_ready acc_empty",
          2: "tma : start stage_free",
          3: "rem0: start full pdsfree scores_done pds_ready out_done",
-         4: "rem1: start full pdsfree scores_done pds_ready out_done"}
+         4: "rem1: start full pdsfree scores_done pds_ready out_done",
+         5: "rem2: start full pdsfree scores_done pds_ready out_done"}
 for r, nm in names.items():
     print(nm)
     for w in range(2, 14):
