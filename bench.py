@@ -337,6 +337,11 @@ def run_ours(args):
                                                                bucket_cap_mb=int(os.environ.get("FIBER_DDP_BUCKET_MB", "100")),
                                                                broadcast_buffers=os.environ.get("FIBER_DDP_BCAST_BUFFERS", "0") == "1",
                                                                **ddp_kw)
+        if os.environ.get("FIBER_DDP_BF16", "1") == "1":
+            # gradient buckets travel as bf16 (0.56 GB instead of 1.13 GB per step) and are accumulated back into the fp32
+            # .grad views; the all-reduce itself still sums in the wire dtype (NCCL), as SURVEY.md §7 step 7 plans
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            step_model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     host = pin(make_batch(B, R, L, seed=1234 + rank))
     h2d = batch_bytes(host)
 

@@ -126,23 +126,60 @@ class FIBERTransformerSS(LightningModule):
 
     @torch.no_grad()
     def _dequeue_and_enqueue(self, image_feat, text_feat, image_input, text_input, text_input_mask):
-        """fiber_module.py:181-222 (ring buffer with wrap-around)."""
-        image_feats = concat_all_gather(image_feat)
-        text_feats = concat_all_gather(text_feat)
-        image_input = concat_all_gather(image_input)
-        text_input = concat_all_gather(text_input)
-        text_input_mask = concat_all_gather(text_input_mask)
-        n = image_feats.shape[0]
+        """fiber_module.py:181-222 (ring buffer with wrap-around).
+
+        Multi-GPU: the reference runs its five all_gathers synchronously in the middle of the step — at 8 ranks the raw
+        images alone are 0.9 GB gathered per step.  Nothing reads the queues again before the NEXT step's compute_itc, so
+        here the gathers and the queue writes run on a side stream (FIBER_ITC_ASYNC_QUEUE=0 disables it) while the
+        compute stream goes on with the hard-negative ITM pass and the backward; `queue_sync()` — called by forward(),
+        compute_itc, queue_counters() and state_dict() — makes the compute stream wait for the update before any read.
+        Every rank issues the collectives at the same point of its step, so their order on the communicator is the same
+        everywhere.  The queue contents are bit-identical to the synchronous update."""
+        world = torch.distributed.get_world_size() if (torch.distributed.is_available()
+                                                       and torch.distributed.is_initialized()) else 1
+        overlap = (world > 1 and image_feat.is_cuda and os.environ.get("FIBER_ITC_ASYNC_QUEUE", "1") != "0")
+        self.queue_sync()  # a previous update still in flight writes the same buffers
         ptr, total = self.queue_counters()
-        idx = (ptr + torch.arange(n, device=image_feats.device)) % self.queue_size
-        self.image_queue[:, idx] = image_feats.T.float()
-        self.text_queue[:, idx] = text_feats.T.float()
-        self.image_input_queue[idx] = image_input
-        self.text_input_queue[idx] = text_input
-        self.text_input_mask_queue[idx] = text_input_mask
-        self.queue_ptr[0] = (ptr + n) % self.queue_size
-        self.queue_total[0] = total + n
+        n = image_feat.shape[0] * world
+        if overlap:
+            cur = torch.cuda.current_stream()
+            side = self.__dict__.get("_queue_stream")
+            if side is None:
+                side = self.__dict__["_queue_stream"] = torch.cuda.Stream()
+            side.wait_stream(cur)
+            for t in (image_feat, text_feat, image_input, text_input, text_input_mask):
+                t.record_stream(side)
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            image_feats = concat_all_gather(image_feat)
+            text_feats = concat_all_gather(text_feat)
+            image_input = concat_all_gather(image_input)
+            text_input = concat_all_gather(text_input)
+            text_input_mask = concat_all_gather(text_input_mask)
+            idx = (ptr + torch.arange(n, device=image_feats.device)) % self.queue_size
+            self.image_queue[:, idx] = image_feats.T.float()
+            self.text_queue[:, idx] = text_feats.T.float()
+            self.image_input_queue[idx] = image_input
+            self.text_input_queue[idx] = text_input
+            self.text_input_mask_queue[idx] = text_input_mask
+            self.queue_ptr[0] = (ptr + n) % self.queue_size
+            self.queue_total[0] = total + n
+            if overlap:
+                self.__dict__["_queue_event"] = side.record_event()
         self._queue_host = ((ptr + n) % self.queue_size, total + n, self.queue_ptr._version, self.queue_total._version)
+
+    def queue_sync(self):
+        """Order the current stream after an ITC queue update that is still running on the side stream."""
+        ev = self.__dict__.pop("_queue_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def state_dict(self, *a, **k):
+        self.queue_sync()
+        return super().state_dict(*a, **k)
 
     def queue_counters(self):
         """(queue_ptr, queue_total) as Python ints.  The reference reads both device buffers with int(...) every
@@ -150,6 +187,8 @@ class FIBERTransformerSS(LightningModule):
         _dequeue_and_enqueue are mirrored on the host and re-read from the device only when somebody else
         modified the buffers (load_state_dict, manual reset), detected through their version counters."""
         h = getattr(self, "_queue_host", None)
+        if h is None:
+            self.queue_sync()
         if h is None or h[2] != self.queue_ptr._version or h[3] != self.queue_total._version:
             h = (int(self.queue_ptr), int(self.queue_total), self.queue_ptr._version, self.queue_total._version)
             self._queue_host = h
@@ -224,6 +263,7 @@ class FIBERTransformerSS(LightningModule):
                 "text_labels": text_labels, "text_ids": text_ids, "text_masks": text_masks, "image": img}
 
     def forward(self, batch):
+        self.queue_sync()
         ret = dict()
         if len(self.current_tasks) == 0:
             ret.update(self.infer(batch))

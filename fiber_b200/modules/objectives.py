@@ -117,6 +117,8 @@ def _rows_of_cat(first, second, idx):
 
 
 def compute_itc(pl_module, batch):
+    if hasattr(pl_module, "queue_sync"):
+        pl_module.queue_sync()  # the previous step's queue update may still be running on its side stream
     with torch.no_grad():
         pl_module.temp.clamp_(0.001, 1.0)
     infer_image = pl_module.infer(batch, mask_image=False, mask_text=False, image_only=True)
