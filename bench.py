@@ -111,6 +111,60 @@ def make_batch(B, image_size, L, seed=1234, vocab=50265):
     return batch
 
 
+# Other BASELINE.json configs, measured as EXTRA keys of the N = 1 line (never the headline): name -> (tasks, image
+# size, text length, per-GPU batch, fwd+bwd GFLOP per pair from SURVEY.md §8a)
+EXTRA_CONFIGS = {
+    "vqa576": (["vqa"], 576, 50, 32, 771.02e9),   # configs[2]: VQAv2 fine-tuning, 18 x 18 = 324-token windows
+    "itc384": (["itc"], 384, 50, 64, 309.02e9),   # configs[3]: ITC-only retrieval fine-tuning, 64 x (64 + 4096) sims
+}
+
+
+def measure_extra_config(name, dev, steps=3, warmup=3):
+    """fwd+bwd pairs/s of one extra config on this GPU (device-resident synthetic batch, CUDA events)."""
+    from fiber_b200 import ops
+    from fiber_b200.modules import FIBERTransformerSS, fiber_utils
+    tasks, R, L, B, flops = EXTRA_CONFIGS[name]
+    torch.manual_seed(1234)
+    model = FIBERTransformerSS(config(tasks, R, L)).to(dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith(("alpha_i2t", "alpha_t2i")):
+                p.fill_(0.5)
+    fill_queues(model)
+    model.train()
+    fiber_utils.set_task(model)
+    ops.set_dropout_seed(1234)
+    batch = make_batch(B, R, L, seed=1234)
+    if "vqa" in tasks:
+        g = torch.Generator(device="cpu").manual_seed(99)
+        batch["vqa_labels"] = [[int(torch.randint(0, 3129, (1,), generator=g))] for _ in range(B)]
+        batch["vqa_scores"] = [[1.0] for _ in range(B)]
+    batch = to_device(batch, dev, non_blocking=False)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        out = model(batch)
+        loss = sum(v for k, v in out.items() if "loss" in k)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    v = B / ms * 1e3
+    return {"value": v, "unit": "pairs/s", "ms_per_step": ms, "per_gpu_batch": B, "image_size": R, "text_len": L,
+            "tasks": tasks, "steps": steps, "warmup": warmup, "tflops": v * flops / 1e12, "last_loss": float(loss.detach()),
+            "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+
+
 def to_device(batch, dev, non_blocking=True):
     out = {}
     for k, v in batch.items():
@@ -296,6 +350,82 @@ def profile_gemms(step, batch):
                      "gbs": round(d[2] / d[3] / 1e6)} for k, d in top]}
 
 
+def gpu_speed_probe(dev, world):
+    """How uniform are the GPUs of this job?  Every rank times the same 20 launches of the step's largest GEMM
+    (147456 x 512 x 2048, no communication) after the timed region; the per-rank TFLOP/s are gathered.  A data-parallel
+    step runs at the pace of its slowest rank (the ranks meet in the ITC all_gathers and in the gradient all-reduce),
+    so the spread printed here is a floor for the scaling loss that no overlap scheme can recover."""
+    from fiber_b200 import kernels as K
+    a = torch.randn(147456, 2048, device=dev).to(torch.bfloat16)
+    b = torch.randn(512, 2048, device=dev).to(torch.bfloat16)
+    for _ in range(5):
+        K.gemm(a, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 40
+    for _ in range(n):
+        K.gemm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    tf = 2.0 * 147456 * 512 * 2048 * n / (e0.elapsed_time(e1) / 1e3) / 1e12
+    if world == 1:
+        return {"gemm_tflops_per_rank": [round(tf, 1)]}
+    t = torch.tensor([tf], device=dev)
+    out = torch.empty(world, device=dev)
+    torch.distributed.all_gather_into_tensor(out, t)
+    v = [round(float(x), 1) for x in out.tolist()]
+    return {"gemm_tflops_per_rank": v, "slowest_over_fastest": round(min(v) / max(v), 4),
+            "slowest_over_rank0": round(min(v) / v[0], 4)}
+
+
+def profile_timeline(step, batch, out_path):
+    """One more (untimed) step under torch.profiler on every rank (the step contains collectives); the rank that is
+    given a path writes the kernel timeline summary: totals per kernel, NCCL kernel spans, busy / idle time of the
+    compute stream and of the union of all streams."""
+    from collections import defaultdict
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        step(batch)
+        torch.cuda.synchronize()
+    if out_path is None:
+        return
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+    t0, t1 = ks[0][0], max(k[1] for k in ks)
+
+    def union(iv):
+        busy, end = 0.0, None
+        for s_, e_ in sorted(iv):
+            if end is None or s_ > end:
+                busy += e_ - s_
+                end = e_
+            elif e_ > end:
+                busy += e_ - end
+                end = e_
+        return busy
+
+    nccl = [(s_, e_, n) for s_, e_, n in ks if "nccl" in n.lower()]
+    comp = [(s_, e_, n) for s_, e_, n in ks if "nccl" not in n.lower()]
+    agg = defaultdict(lambda: [0, 0.0])
+    for s_, e_, n in ks:
+        n = n.split("(")[0].replace("void ", "")
+        agg[n][0] += 1
+        agg[n][1] += e_ - s_
+    lines = ["span %.3f ms, %d kernels; compute kernels busy %.3f ms (sum %.3f ms), NCCL kernels busy %.3f ms in %d launches, "
+             "all streams busy %.3f ms" % ((t1 - t0) / 1e3, len(ks), union([(a, b) for a, b, _ in comp]) / 1e3,
+                                           sum(b - a for a, b, _ in comp) / 1e3, union([(a, b) for a, b, _ in nccl]) / 1e3,
+                                           len(nccl), union([(a, b) for a, b, _ in ks]) / 1e3)]
+    lines.append("NCCL kernels (start ms, duration ms, name):")
+    for s_, e_, n in nccl:
+        if e_ - s_ > 50:
+            lines.append("  %8.2f %8.3f  %s" % ((s_ - t0) / 1e3, (e_ - s_) / 1e3, n[:90]))
+    lines.append("%-86s %6s %10s %9s" % ("kernel", "count", "ms", "avg us"))
+    for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        lines.append("%-86s %6d %10.3f %9.1f" % (n[:86], c, us / 1e3, us / c))
+    with open(out_path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
 def run_ours(args):
     from fiber_b200 import lib, ops
     from fiber_b200.modules import FIBERTransformerSS, fiber_utils
@@ -337,9 +467,10 @@ def run_ours(args):
                                                                bucket_cap_mb=int(os.environ.get("FIBER_DDP_BUCKET_MB", "100")),
                                                                broadcast_buffers=os.environ.get("FIBER_DDP_BCAST_BUFFERS", "0") == "1",
                                                                **ddp_kw)
-        if os.environ.get("FIBER_DDP_BF16", "1") == "1":
-            # gradient buckets travel as bf16 (0.56 GB instead of 1.13 GB per step) and are accumulated back into the fp32
-            # .grad views; the all-reduce itself still sums in the wire dtype (NCCL), as SURVEY.md §7 step 7 plans
+        if os.environ.get("FIBER_DDP_BF16", "0") == "1":
+            # opt-in: gradient buckets travel as bf16 (0.56 GB instead of 1.13 GB per step).  Measured at N = 8
+            # (profiles/r2_scaling_ab.txt): 2386 pairs/s with, 2388 without — the fp32 all-reduce is already hidden
+            # behind the backward, so the default keeps the reference's fp32 gradient averaging
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             step_model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     host = pin(make_batch(B, R, L, seed=1234 + rank))
@@ -392,6 +523,31 @@ def run_ours(args):
     ms_e2e, _, last_loss = timed(args.steps, True)
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
     gemm_stats = profile_gemms(step, dev_batch)  # every rank runs it: the step contains DDP collectives
+    rank_probe = gpu_speed_probe(dev, world)
+    # the same step followed by the optimizer (fused multi-tensor AdamW, one launch; the bf16 weight
+    # copies are re-cast by the next forward) — reported next to the fwd+bwd metric, not instead of it
+    (optimizer,), (sched,) = fiber_utils.set_schedule(model)
+
+    def full_step(batch):
+        loss = step(batch)
+        optimizer.step()
+        sched["scheduler"].step()
+        return loss
+
+    for _ in range(2):
+        full_step(dev_batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_opt = max(3, args.steps // 2)
+    for _ in range(n_opt):
+        full_step(dev_batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_opt = e0.elapsed_time(e1) / n_opt
+    del optimizer
+    if args.profile_out:
+        profile_timeline(step, dev_batch, args.profile_out if rank == 0 else None)
 
     if rank != 0:
         return
@@ -413,6 +569,9 @@ def run_ours(args):
         "config": bench_config(args, world),
         "value_per_gpu": value / world,
         "run_info": {"last_loss": last_loss, "peak_mem_gib": round(peak_mem, 1), "kernel_options": _kernel_options(),
+                     "gpu_speed_probe": rank_probe,
+                     "with_optimizer": {"ms_per_step": ms_opt, "pairs_per_s": B * world / ms_opt * 1e3, "steps": n_opt,
+                                        "optimizer": "fiber_b200.optim.FusedAdamW (HF AdamW order, one launch) + LR schedule"},
                      "note": "`value` is the whole-job aggregate over n_gpus (contract); value_per_gpu is the metric's "
                              "per-GPU figure"},
         "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -435,9 +594,25 @@ def run_ours(args):
                           "note": "whole step per GPU: pairs/s x 1636.23 GFLOP/pair"},
         "gemm_breakdown": gemm_stats["top"],
     }
+    if world == 1 and (args.eager_baseline or args.extra_configs):
+        del step_model, model, dev_batch
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if world == 1 and args.extra_configs:
+        # BASELINE.json configs[2] / [3] on the same kernels (extra keys, not the headline)
+        line["extra_configs"] = {}
+        for name in EXTRA_CONFIGS:
+            try:
+                torch.cuda.reset_peak_memory_stats()
+                line["extra_configs"][name] = measure_extra_config(name, dev)
+            except Exception as e:  # noqa: BLE001  (never let an extra break the headline line)
+                line["extra_configs"][name] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
     if world == 1 and args.eager_baseline:
         # the north-star's denominator: the reference PyTorch-eager GPU path, timed in this process after our arm
-        del step_model, model, dev_batch
         line["eager_gpu_baseline"] = eager_gpu_baseline(args, dev, host, value)
     if args.cpu_baseline and world == 1:
         _, line["cpu_baseline"] = cpu_baseline_record(args.cpu_batch, R, L, 1, 0)
@@ -507,12 +682,16 @@ def _kernel_options():
         opts["gelu_grad_prefetch"] = int(ops.GELU_GRAD_PREFETCH)
         from fiber_b200 import kernels
         opts["res_prefetch"] = int(kernels.RES_PREFETCH)
+        opts["ddp_bf16_buckets"] = int(os.environ.get("FIBER_DDP_BF16", "0") == "1")
+        opts["itc_async_queue"] = int(os.environ.get("FIBER_ITC_ASYNC_QUEUE", "0") == "1")
         return opts
     except Exception as e:  # never let a label break the measurement
         return {"error": str(e)}
 
 
 def main():
+    # NCCL prints its version banner (NCCL_DEBUG >= VERSION) to stdout by default; ONE JSON line on stdout is the contract
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -524,6 +703,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="pairs per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-eager-baseline", dest="eager_baseline", action="store_false")
+    ap.add_argument("--no-extra-configs", dest="extra_configs", action="store_false",
+                    help="skip the VQA-576 / ITC-only extra measurements of the N = 1 line")
+    ap.add_argument("--profile-out", default="", help="write a torch.profiler kernel-timeline summary of one extra step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

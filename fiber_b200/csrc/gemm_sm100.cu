@@ -47,13 +47,19 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 576;  // TMA warp, MMA warp, 16 epilogue warps
 
-template <int BN>
+// EPI = 1 (two-output GELU epilogues, aux / residual epilogues): these GEMMs move 1.2 - 1.4 GB per launch and were
+// bound by the epilogue waiting, four times per tile and warp, for the TMA unit to finish READING the warp's only box
+// before the next result could be staged (6.6 us per tile against 2.3 us of MMAs).  They trade one operand stage for a
+// second box per warp: the two outputs of a chunk (and consecutive chunks) alternate boxes, and a box is rewritten
+// only when the store issued two stores ago has been read (cp.async.bulk.wait_group.read 1).
+template <int BN, int EPI = 0>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? (EPI == 1 ? 3 : 4) : (EPI == 1 ? 5 : 6);
+  static constexpr int BOXES = EPI == 1 ? 2 : 1;
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t STAGING_BYTES = 16 * 2048;  // 16 epilogue warps x (32 rows x 64 B) TMA-store box
+  static constexpr uint32_t STAGING_BYTES = 16 * 2048 * BOXES;  // 16 epilogue warps x BOXES x (32 rows x 64 B) TMA-store box
   static constexpr uint32_t SMEM_BYTES =
       1024 /*align slack*/ + STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem;
@@ -423,14 +429,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;     // TMEM lane quadrant this warp may access
     const int cgrp = ew >> 2;   // which quarter of the BN columns
     constexpr int CPW = BN / 128;  // 32-column chunks per warp
-    uint8_t* box = reinterpret_cast<uint8_t*>(staging) + ew * 2048;  // 32 rows x 64 B
+    uint8_t* box = reinterpret_cast<uint8_t*>(staging) + ew * 2048 * Cfg::BOXES;  // BOXES x (32 rows x 64 B)
     int acc = 0;
     uint32_t acc_phase = 0;  // bit a = phase of accumulator a
     if constexpr (EPI == 1) {
       // opt-in epilogues (act 3 .. 7, see epi_chunk_gelu_both): full tiles, bf16 outputs through the TMA-store box
       const int act = p.act;
-      uint8_t* box_row = box + lane * 64;
       const int swz = (lane >> 1) & 3;
+      int bsel = 0;  // which of the warp's two boxes the next result goes to
+      auto wait_box = [&] {  // the store issued two stores ago (the last user of box `bsel`) has been read
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+      };
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         const int tile = unit % (p.tiles_m * p.tiles_n);
         const int m0 = (tile / p.tiles_n) * GEMM_BM;
@@ -438,18 +448,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ncols = min(BN, p.N - n0);
         const long long row = static_cast<long long>(m0) + q * 32 + lane;
         const bool aux_mode = act == 4 || act == 6 || act == 7;  // a second bf16 [M, N] operand read per element
-        const bf16* aux_r = aux_mode ? (act == 6 ? p.residual + row * p.ldr + n0 : p.aux + row * p.ldaux + n0) : nullptr;
         float sc = 1.0f;  // act 6: gate alpha x DropPath scale of this row's sample (as the default epilogue)
         if (act == 6) {
           if (p.scale) sc = __ldg(p.scale);
           if (p.row_scale) sc *= __ldg(p.row_scale + static_cast<int>(row / p.rows_per_scale));
         }
-        // act 4: the aux rows of chunk i + 1 are loaded into registers while chunk i is computed, and those of the
-        // first chunk before the wait for the accumulator (the act-2 epilogue stalls on exactly these loads)
+        // The second operand (aux / residual) of a 32 x 32 chunk is loaded COALESCED — lane l fetches the 16-byte piece
+        // l % 4 of rows l / 4 + 8 i, i = 0..3: eight 64-byte rows per instruction = 8 LSU wavefronts, where the
+        // thread-per-row form (64 contiguous bytes per lane) costs 32 — one chunk ahead into registers, and is
+        // transposed to thread-per-row through the warp's (still idle) output box.  The per-row loads were what bound
+        // these epilogues: 4096 wavefronts per 128 x 256 tile, as many cycles as the tile's MMAs.
+        const bf16* aux_base = nullptr;
+        long long aux_ld = 0;
+        if (aux_mode) {
+          aux_base = act == 6 ? p.residual : p.aux;
+          aux_ld = act == 6 ? p.ldr : p.ldaux;
+          aux_base += (static_cast<long long>(m0) + q * 32 + (lane >> 2)) * aux_ld + n0 + (lane & 3) * 8;
+        }
         uint4 av_next[4];
         if (aux_mode && cgrp * CPW * 32 < ncols) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + cgrp * CPW * 32 + j * 8);
+          for (int j = 0; j < 4; ++j)
+            av_next[j] = *reinterpret_cast<const uint4*>(aux_base + static_cast<long long>(8 * j) * aux_ld + cgrp * CPW * 32);
         }
         mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
         tc_fence_after();
@@ -458,15 +478,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int c0 = (cgrp * CPW + i) * 32;
           if (c0 >= ncols) break;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
-          if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
-          __syncwarp();
+          wait_box();
+          uint8_t* bx = box + bsel * 2048;
+          uint8_t* box_row = bx + lane * 64;
           if (aux_mode) {
+            // registers (piece l % 4 of rows l / 4 + 8 j) -> box -> this thread's row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = (lane >> 2) + 8 * j;
+              *reinterpret_cast<uint4*>(bx + r * 64 + ((((lane & 3) ^ ((r >> 1) & 3))) << 4)) = av_next[j];
+            }
+            __syncwarp();
             uint4 av[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) av[j] = av_next[j];
+            for (int j = 0; j < 4; ++j) av[j] = *reinterpret_cast<const uint4*>(box_row + ((j ^ swz) << 4));
+            __syncwarp();  // every lane has read its row: the box may take the outputs
             if (i + 1 < CPW && c0 + 32 < ncols) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) av_next[j] = *reinterpret_cast<const uint4*>(aux_r + c0 + 32 + j * 8);
+              for (int j = 0; j < 4; ++j)
+                av_next[j] = *reinterpret_cast<const uint4*>(aux_base + static_cast<long long>(8 * j) * aux_ld + c0 + 32);
             }
             if (act == 4) {
               epi_chunk_mul_aux<false>(taddr, box_row, swz, av);
@@ -486,9 +516,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_2d(&tmC, bx, n0 + c0, m0 + q * 32);
               tma_store_commit();
             }
+            bsel ^= 1;
           } else {
             uint32_t gp[16];
             if (act == 3) epi_chunk_gelu_both<true>(taddr, box_row, swz, p.bias + n0 + c0, p.bias != nullptr, gp);
@@ -496,21 +527,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_2d(&tmC, bx, n0 + c0, m0 + q * 32);
               tma_store_commit();
-              tma_store_wait_read();  // the box is reused for the second output right away
             }
-            __syncwarp();
+            bsel ^= 1;
+            wait_box();  // the second output goes to the other box
+            uint8_t* bx2 = box + bsel * 2048;
 #pragma unroll
             for (int jb = 0; jb < 4; ++jb)
-              *reinterpret_cast<uint4*>(box_row + ((jb ^ swz) << 4)) =
+              *reinterpret_cast<uint4*>(bx2 + lane * 64 + ((jb ^ swz) << 4)) =
                   make_uint4(gp[jb * 4 + 0], gp[jb * 4 + 1], gp[jb * 4 + 2], gp[jb * 4 + 3]);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmP, box, n0 + c0, m0 + q * 32);
+              tma_store_2d(&tmP, bx2, n0 + c0, m0 + q * 32);
               tma_store_commit();
             }
+            bsel ^= 1;
           }
         }
         tc_fence_before();
@@ -774,10 +807,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   static bool attr_set = false;
   if (!attr_set) {
     FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmCfg<BN>::SMEM_BYTES));
+                                    GemmCfg<BN, EPI>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, p);
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN, EPI>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, p);
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

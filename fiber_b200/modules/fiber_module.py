@@ -130,14 +130,16 @@ class FIBERTransformerSS(LightningModule):
 
         Multi-GPU: the reference runs its five all_gathers synchronously in the middle of the step — at 8 ranks the raw
         images alone are 0.9 GB gathered per step.  Nothing reads the queues again before the NEXT step's compute_itc, so
-        here the gathers and the queue writes run on a side stream (FIBER_ITC_ASYNC_QUEUE=0 disables it) while the
-        compute stream goes on with the hard-negative ITM pass and the backward; `queue_sync()` — called by forward(),
-        compute_itc, queue_counters() and state_dict() — makes the compute stream wait for the update before any read.
+        with FIBER_ITC_ASYNC_QUEUE=1 the gathers and the queue writes run on a side stream while the compute stream goes
+        on with the hard-negative ITM pass and the backward; `queue_sync()` — called by forward(), compute_itc,
+        queue_counters() and state_dict() — makes the compute stream wait for the update before any read.  Opt-in: at
+        N = 8 it measured 2386 pairs/s against 2388 for the synchronous update (profiles/r2_scaling_ab.txt) — the
+        gathers take ~1.5 ms on NVSwitch; the scaling loss is the spread between the GPUs (bench.py gpu_speed_probe).
         Every rank issues the collectives at the same point of its step, so their order on the communicator is the same
         everywhere.  The queue contents are bit-identical to the synchronous update."""
         world = torch.distributed.get_world_size() if (torch.distributed.is_available()
                                                        and torch.distributed.is_initialized()) else 1
-        overlap = (world > 1 and image_feat.is_cuda and os.environ.get("FIBER_ITC_ASYNC_QUEUE", "1") != "0")
+        overlap = (world > 1 and image_feat.is_cuda and os.environ.get("FIBER_ITC_ASYNC_QUEUE", "0") == "1")
         self.queue_sync()  # a previous update still in flight writes the same buffers
         ptr, total = self.queue_counters()
         n = image_feat.shape[0] * world

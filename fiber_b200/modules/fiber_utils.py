@@ -96,16 +96,21 @@ def resolve_max_steps(pl_module):
 
 
 def set_schedule(pl_module):
-    """fiber_utils.py:156-287.  Optimizer: torch.optim.AdamW stands in for transformers.AdamW (4.6.0).  Both are
-    decoupled-weight-decay Adam; they differ in two second-order details — HF adds eps to sqrt(v) BEFORE the bias
-    correction and applies the decay after the Adam update, torch adds eps after the correction and decays first —
-    which change an update by O(lr * wd * lr) and O(eps), below fp32 resolution of the parameters at FIBER's settings."""
+    """fiber_utils.py:156-287.  Optimizer: on the GPU, fiber_b200.optim.FusedAdamW — transformers.AdamW (4.6.0)'s update
+    in its exact operation order as one multi-tensor kernel.  For CPU-resident modules (host-side tests) torch.optim.AdamW
+    stands in; the two differ in second-order details only (HF adds eps to sqrt(v) before the bias correction and
+    decays after the Adam update, torch adds eps after the correction and decays first)."""
     import math
     cfg = pl_module.hparams.config
     groups = param_groups(pl_module)
     lr = cfg["learning_rate"]
     if cfg["optim_type"] == "adamw":
-        optimizer = torch.optim.AdamW(groups, lr=lr, eps=1e-8, betas=(0.9, 0.98))
+        on_gpu = all(p.is_cuda for g in groups for p in g["params"]) and any(len(g["params"]) for g in groups)
+        if on_gpu:  # one fused launch per step with HF AdamW's exact update order (fiber_b200/optim.py, csrc/optim.cu)
+            from ..optim import FusedAdamW
+            optimizer = FusedAdamW(groups, lr=lr, eps=1e-8, betas=(0.9, 0.98))
+        else:       # host-side construction (tests, group bookkeeping): same groups, torch's AdamW
+            optimizer = torch.optim.AdamW(groups, lr=lr, eps=1e-8, betas=(0.9, 0.98))
     elif cfg["optim_type"] == "adam":
         optimizer = torch.optim.Adam(groups, lr=lr)
     elif cfg["optim_type"] == "sgd":

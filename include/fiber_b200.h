@@ -201,6 +201,25 @@ int fiber_embed_gather(const int64_t* ids, int32_t batch, int32_t len, int32_t c
 int fiber_embed_scatter(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const void* dsum,
                         int64_t ldd, float* dword, float* dpos, fiber_stream_t stream);
 
+/* ---- fused multi-tensor AdamW ----------------------------------------------
+ * Replaces transformers.AdamW.step over the six parameter groups of fiber_utils.set_schedule
+ * (coarse_grained/fiber/modules/fiber_utils.py:156-252): per element, in HF 4.6 order,
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps);  p -= lr wd p.
+ * `tensors` is a DEVICE array of fiber_adamw_tensor (one per parameter; lr / wd carry its group), `chunks` a DEVICE array
+ * of n_chunks (tensor index, chunk index) int32 pairs covering every tensor in pieces of chunk_elems elements
+ * (a multiple of 1024).  step counts from 1.  p_bf16 (nullable) receives a bf16 copy of the updated parameter. */
+typedef struct fiber_adamw_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  void* p_bf16;
+  int64_t n;
+  float lr, wd;
+} fiber_adamw_tensor;
+int fiber_adamw_multi(const void* tensors, const void* chunks, int32_t n_chunks, int32_t chunk_elems, float beta1, float beta2,
+                      float eps, int32_t step, fiber_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

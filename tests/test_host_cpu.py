@@ -309,3 +309,24 @@ def test_dropout_seed_follows_torch_seed():
     ops.set_dropout_seed(7)
     assert ops._next_seed() == (7 * 1000003 + 1) & 0x7FFFFFFFFFFF
     ops._base_seed = None
+
+
+def test_fused_adamw_tables_cover_every_element():
+    """Host half of the fused multi-tensor AdamW (fiber_b200/optim.py): table layout == the header's struct, chunks tile
+    every tensor exactly once."""
+    import numpy as np
+    from fiber_b200 import optim
+    text = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
+    body = re.search(r"typedef struct fiber_adamw_tensor \{(.*?)\} fiber_adamw_tensor;", text, re.S).group(1)
+    assert re.findall(r"(\w+)\s*[;,]", body) == ["p", "g", "m", "v", "p_bf16", "n", "lr", "wd"]
+    sizes = [1, 1023, 65536, 65537, 3 * 65536 + 5]
+    t, ch = optim.build_tables((8 * i, 16 * i, 24 * i, 32 * i, 0, n, 1e-5 * (i + 1), 0.01 * (i % 2)) for i, n in enumerate(sizes))
+    assert t.dtype.itemsize == 56 and list(t["n"]) == sizes and t["lr"][2] == np.float32(3e-5)
+    covered = {i: 0 for i in range(len(sizes))}
+    for ti, ci in ch:
+        covered[int(ti)] += min(optim.CHUNK, sizes[ti] - ci * optim.CHUNK)
+    assert covered == dict(enumerate(sizes)) and len(ch) == 1 + 1 + 1 + 2 + 4
+    with pytest.raises(RuntimeError):  # no CPU path
+        p = torch.nn.Parameter(torch.zeros(4))
+        p.grad = torch.ones(4)
+        optim.FusedAdamW([p], lr=1e-3).step()

@@ -147,3 +147,40 @@ def test_layernorm_bwd_scaled_second_output(cuda_dev, rows, C):
     dx, dxs = K.layernorm_bwd(dy, x, mean, rstd, g, dres=dres, dgamma=dg, dbeta=db, row_scale=s, rows_per_scale=rps)
     assert torch.equal(dx, dx0)
     _close(dxs, dx0.float() * s.repeat_interleave(rps)[:, None], 1e-2, "dx_scaled")
+
+
+def test_fused_adamw_matches_hf_update(cuda_dev):
+    """fiber_adamw_multi against a plain restatement of transformers 4.6 AdamW.step (fiber_utils.py:247 uses it with
+    betas (0.9, 0.98), eps 1e-8): three steps over tensors of awkward sizes in two groups, one with weight decay."""
+    from fiber_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(3)
+    sizes = [(5,), (1023,), (257, 129), (65536 + 3,), (768, 768)]
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(cuda_dev)) for s in sizes]
+    ref = [p.detach().double().clone() for p in ps]
+    m = [torch.zeros_like(r) for r in ref]
+    v = [torch.zeros_like(r) for r in ref]
+    groups = [{"params": ps[:3], "weight_decay": 0.01, "lr": 1e-3}, {"params": ps[3:], "weight_decay": 0.0, "lr": 5e-3}]
+    opt = FusedAdamW(groups, lr=1e-3, betas=(0.9, 0.98), eps=1e-8)
+    b1, b2, eps = 0.9, 0.98, 1e-8
+    for step in range(1, 4):
+        for i, p in enumerate(ps):
+            p.grad = torch.randn(p.shape, generator=g).to(cuda_dev) * (0.1 * step)
+        opt.step()
+        for i, p in enumerate(ps):
+            lr, wd = (1e-3, 0.01) if i < 3 else (5e-3, 0.0)
+            gr = p.grad.double()
+            m[i] = b1 * m[i] + (1 - b1) * gr
+            v[i] = b2 * v[i] + (1 - b2) * gr * gr
+            step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+            ref[i] = ref[i] - step_size * m[i] / (v[i].sqrt() + eps)
+            ref[i] = ref[i] - lr * wd * ref[i]
+    for i, p in enumerate(ps):
+        torch.testing.assert_close(p.detach().double(), ref[i], rtol=2e-6, atol=2e-7)
+        torch.testing.assert_close(opt.state[p]["exp_avg_sq"].double(), v[i], rtol=1e-5, atol=1e-12)
+    # a parameter without gradient is skipped; LR schedulers rewrite group["lr"] and the next step sees it
+    ps[0].grad = None
+    before = ps[0].detach().clone()
+    opt.param_groups[0]["lr"] = 0.0
+    p1 = ps[1].detach().clone()
+    opt.step()
+    assert torch.equal(ps[0].detach(), before) and torch.equal(ps[1].detach(), p1 * (1 - 0.0 * 0.01))
