@@ -79,10 +79,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
+// After a few failed polls the warp backs off with nanosleep: a spinning warp (the MMA issuer waiting for the epilogue,
+// the producer waiting for a free slot, ...) otherwise takes issue slots from the working warps of its scheduler —
+// ncu on the GELU GEMM counted ~35 % of all issued instructions in such loops (profiles/r2_gemm_gelu_cache_ncu.txt).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+#ifndef FIBER_NO_BACKOFF
+    if (++spins > 4) __nanosleep(spins > 64 ? 256 : 32);
+#else
+    ++spins;
+#endif
+    if (spins > (1u << 22)) {
       printf("fiber_b200: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -91,7 +91,12 @@ __device__ __noinline__ void tc_wait_timeout(int tag, uint32_t parity, int it) {
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int tag, int it) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) tc_wait_timeout(tag, parity, it);
+#ifndef FIBER_NO_BACKOFF
+    if (++spins > 4) __nanosleep(spins > 64 ? 256 : 32);  // do not take issue slots from the working warps (common.cuh)
+#else
+    ++spins;
+#endif
+    if (spins > (1u << 22)) tc_wait_timeout(tag, parity, it);
   }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

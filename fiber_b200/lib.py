@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfiber_b200.so")
+LIB_PATH = os.environ.get("FIBER_B200_LIB") or os.path.join(_HERE, "libfiber_b200.so")  # env: A/B builds (tools)
 
 _lib = None
 

@@ -41,6 +41,7 @@ def main():
             ("qkv", x, 3 * C, {}),
             ("proj+res", x, C, {"residual": res}),
             ("fc1+gelu+preact", x, 4 * C, {"act": K.ACT_GELU, "preact": True}),
+            ("fc1+gelu+gelu' (act3)", x, 4 * C, {"act": K.ACT_GELU_CACHE, "preact": True}),
             ("fc2+res", x4, C, {"residual": res}),
             ("plain N=4C", x, 4 * C, {}),
         ):
@@ -57,6 +58,12 @@ def main():
             out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             us = timeit(lambda: K.gemm(a, w, bias=bias if name != "plain N=4C" else None, out=out, **kw))
             report(tag + " " + name, M, N, Kd, us, M * Kd * 2 + N * Kd * 2 + M * N * 2 + extra)
+        # fc2 dgrad through the cached GELU' (act 4): dh[M, 4C] = (dz[M, C] W2^T) * aux
+        w2 = torch.randn(4 * C, C, device=dev).to(torch.bfloat16)
+        out4 = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+        us = timeit(lambda: K.gemm(x, w2, aux=x4, act=K.ACT_MUL_AUX, out=out4))
+        report(tag + " fc2 dgrad * aux (act4)", M, 4 * C, C, us, M * C * 2 + 4 * C * C * 2 + 2 * M * 4 * C * 2)
+        del w2, out4
         # wgrad: dW[N, K] = dY[M, N]^T X[M, K]
         for name, N, Kd in (("wgrad qkv", 3 * C, C), ("wgrad fc1", 4 * C, C), ("wgrad fc2", C, 4 * C)):
             dy = torch.randn(M, N, device=dev).to(torch.bfloat16)

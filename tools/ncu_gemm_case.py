@@ -1,5 +1,5 @@
 """A few launches of one GEMM shape / epilogue for an `ncu --set full` capture.
-    python tools/ncu_gemm_case.py MODE [M N K]      MODE in plain | bias | gelu | gelu_grad | res | wgrad"""
+    python tools/ncu_gemm_case.py MODE [M N K]      MODE in plain | bias | gelu | gelu_grad | res | wgrad | gelu_cache | mul_aux | res_pf"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fiber_b200 import kernels as K, lib
@@ -26,6 +26,12 @@ for _ in range(3):
         K.gemm(x, w, bias=bias, preact=pre, act=K.ACT_GELU, out=out)
     elif mode == "gelu_grad":
         K.gemm(x, w, aux=res, act=K.ACT_GELU_GRAD, out=out)
+    elif mode == "gelu_cache":   # act 3: GELU + GELU' in one pass (the default fc1 epilogue)
+        K.gemm(x, w, bias=bias, preact=pre, act=K.ACT_GELU_CACHE, out=out)
+    elif mode == "mul_aux":      # act 4: acc * aux (the default fc2-dgrad epilogue)
+        K.gemm(x, w, aux=res, act=K.ACT_MUL_AUX, out=out)
+    elif mode == "res_pf":       # act 6: residual epilogue on the two-box path
+        K.gemm(x, w, bias=bias, residual=res, act=K.ACT_RES_PF, out=out)
     elif mode == "wgrad":  # dW[N, Kd] = dY[M, N]^T X[M, Kd] with the fused bias gradient
         K.gemm(res, x, mn_major=True, accumulate=True, out=dw, colsum=db)
 torch.cuda.synchronize()
