@@ -29,16 +29,19 @@ int fiber_version(void);
 int fiber_init(void);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t fiber_launch_count(void);
-/* Process-wide kernel selection.  "winattn_tc": bit 0 / bit 1 route the forward / backward of 12x12-window
- * attention (fiber_attn_fwd / fiber_attn_bwd, mode 1, head_dim 32) to the tcgen05 generation
- * (csrc/window_attn_tc.cu) instead of the mma.sync one; default 0, or the FIBER_WINATTN_TC environment variable.
+/* Process-wide kernel selection (value -1 restores the default).
+ * "winattn_tc": routes the forward (bit 0) / backward (bit 1) of 12x12-window attention (fiber_attn_fwd / fiber_attn_bwd,
+ * mode 1, head_dim 32, shift 0 or 6) to the tcgen05 kernels of csrc/window_attn_tc.cu instead of the mma.sync ones; bit 2 /
+ * bit 3 select their fourth generation (TMA-fed quadrant-order tiles) for the forward / backward.  Default 15, or the
+ * FIBER_WINATTN_TC environment variable.
  * "attn_small": bit 0 routes fiber_attn_bwd (mode 0, head_dim 64, at most 48 queries and keys: RoBERTa self-attention,
  * roberta.py:256-326) to a 3-warp / four-CTAs-per-SM configuration of the same kernel, bit 1 the few-key case
  * (head_dim 32, at most 48 keys, more than 48 queries: i2t, swin_transformer.py:226-259) to a 4-warp / three-CTAs-per-SM
  * one, bit 2 the few-query case (head_dim 64, at most 48 queries, more than 48 keys: t2i, roberta.py:441-502) to the
- * 3-warp one; default 0 or FIBER_ATTN_SMALL.
+ * 3-warp one; default 7 or FIBER_ATTN_SMALL.
+ * "tq_trace" (debug): 1 makes the fourth-generation window backward record an event trace of one CTA (tools/tq_trace.py).
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
- * fiber_get_option returns the value ("winattn_tc_launches", read-only: launches of the tcgen05 generation so far). */
+ * fiber_get_option returns the value ("winattn_tc_launches", read-only: launches of the tcgen05 generations so far). */
 int fiber_set_option(const char* name, int32_t value);
 int fiber_get_option(const char* name);
 
@@ -55,8 +58,9 @@ int fiber_get_option(const char* name);
  *   if (scale) v *= *scale;  if (row_scale) v *= row_scale[row / rows_per_scale];
  *   if (residual) v += residual[row,col];
  *   out_mode 0: c = bf16(v); 1: c = f32(v); 2: atomicAdd(f32 c, v) (split-K allowed).
- * Opt-in epilogues (K-major operands, out_mode 0, M % 128 == 0, N % 32 == 0; no scale / row_scale / residual except act 6):
- *   act == 3: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(gelu_erf'(v))   (one pass, one erfc)
+ * Single-pass epilogues (K-major operands, out_mode 0, M % 128 == 0, N % 32 == 0; no scale / row_scale / residual except
+ * act 6; two TMA-store boxes per warp).  act 3 / act 4 are what the FIBER path uses for fc1 / fc2 dgrad:
+ *   act == 3: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(gelu_erf'(v))   (one pass, one exponential)
  *   act == 4: c = bf16(acc * aux[row,col])          (with aux = the act-3 second output: dgrad through the GELU)
  *   act == 5: v += bias[col]; c = bf16(gelu_erf(v)); preact[row,col] = bf16(v)    (act 1 + preact, bit for bit, one pass)
  *   act == 6: the default epilogue with residual (bias, scale, row_scale as above; no preact / aux), bit for bit, residual
