@@ -278,9 +278,20 @@ int launch_win_fwd(const AttnParams& p, cudaStream_t stream);  // window_attn.cu
 bool win_attn_tc_supported(const AttnParams& p, int hd, bool bwd);  // window_attn_tc.cu
 int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream);    // window_attn_tc.cu
 int option_winattn_tc();                                            // capi.cu
+bool attn_sk_supported(const AttnParams& p, int hd);                // attention_sk.cu
+int launch_attn_sk_fwd(const AttnParams& p, int hd, cudaStream_t stream);
+int option_attn_sk();                                               // capi.cu
+void count_attn_sk_launch();
 
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
+  // tcgen05 + TMA forward for at most 64 keys per group.  Bit 0: where a 128-query tile is mostly full (image -> text:
+  // 576 / 144 / 1296 queries per sample; measured 0.255 -> 0.158 ms at stage 2) — the default; bit 2 also routes short
+  // query sequences (RoBERTa self-attention, 40 of 128 tile rows used: 0.041 -> 0.062 ms, slower than mma.sync)
+  if (attn_sk_supported(p, hd) && (((option_attn_sk() & 1) && p.Lq >= 96) || (option_attn_sk() & 4))) {
+    count_attn_sk_launch();
+    return launch_attn_sk_fwd(p, hd, stream);
+  }
   if ((option_winattn_tc() & 1) && win_attn_tc_supported(p, hd, false)) return launch_win_tc_fwd(p, stream);  // opt-in
   if (win_attn_supported(p, hd)) return launch_win_fwd(p, stream);  // ws*ws <= 144 tokens, head_dim 32
   if (hd == 32) {

@@ -1,0 +1,376 @@
+// fiber_b200 — plain ("mode 0") attention with at most 64 keys per group on tcgen05: the image->text cross attention of
+// the fused Swin blocks (swin_transformer.py:226-259: 576 / 144 / 1296 image queries per sample against <= 50 text
+// tokens, head_dim 32, additive text mask) and RoBERTa self-attention (roberta.py:256-326: <= 50 x <= 50, head_dim 64,
+// -10000 padding mask, probability dropout).  The mma.sync kernels of attention_{fwd,bwd}.cu remain for everything
+// else (text->image with 576 / 144 keys, 324-token windows) and as the generation to compare against ("attn_sk" option).
+//
+// Forward.  Work item = (group, head, tile of 128 queries).  Per item: Q [128][hd], K [64][hd], V [64][hd] arrive as
+// three TMA boxes (2-D maps over the row-major activations; rows past the tensor end are zero-filled, rows of the next
+// group are finite garbage that the key mask / the row predicate neutralise); S = Q K^T is ONE tcgen05.mma chain
+// (M = 128, N = 64) into TMEM; thread = query row turns its 64 scores into probabilities (scale + mask in the log2 domain,
+// row maximum and sum without shuffles, optional dropout) and writes them as bf16 into one SWIZZLE_128B chunk;
+// O = P V is a second chain (M = 128, N = hd, K = 64) whose accumulator is drained one item later (O double-buffered).
+// Six warps (4 element-wise, MMA issuer, TMA producer), 256 TMEM columns, ~80 KB of shared memory: two CTAs per SM
+// overlap each other's bubbles.
+#include "attention.cuh"
+#include "window_tc_layout.cuh"
+#include "../../include/fiber_b200.h"
+
+#include <mutex>
+
+namespace fiber {
+
+void count_launch(int n = 1);
+
+namespace {
+
+using namespace tcl;
+
+constexpr float SK_LOG2E = 1.4426950408889634f;
+constexpr float SK_LN2 = 0.6931471805599453f;
+constexpr int SK_THREADS = 192;
+constexpr int SK_WARP_MMA = 4, SK_WARP_LD = 5;
+constexpr int SK_KEYS = 64;
+
+__device__ __forceinline__ void sk_wait_timeout(int tag, uint32_t parity, int it) {
+  printf("fiber_b200 attention_sk: mbarrier timeout tag %d parity %u item %d block %d warp %d lane %d\n", tag, parity, it,
+         blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31);
+  __trap();
+}
+__device__ __forceinline__ void sk_wait(uint64_t* bar, uint32_t parity, int tag, int it) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 4) __nanosleep(spins > 64 ? 256 : 32);
+    if (spins > (1u << 22)) sk_wait_timeout(tag, parity, it);
+  }
+}
+__device__ __forceinline__ float sk_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sk_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// operand descriptors of a [rows][HD] bf16 tile with HD * 2-byte rows: SWIZZLE_64B for HD = 32, SWIZZLE_128B for HD = 64
+template <int HD>
+__device__ __forceinline__ uint64_t sk_desc_kmajor(uint32_t tile, int ks) {  // K = head dim, step = 16 elements = 32 B
+  if constexpr (HD == 32) return desc_tile_kmajor(tile, ks);
+  else return umma_desc_sw128(tile + ks * 32, 16, 1024);
+}
+template <int HD>
+__device__ __forceinline__ uint64_t sk_desc_mnmajor(uint32_t tile, int kk) {  // K = rows (tokens), step = 16 rows
+  if constexpr (HD == 32) return desc_tile_mnmajor(tile, kk);
+  else return umma_desc_sw128(tile + kk * 2048, 8192, 1024);  // the wgrad GEMM's MN-major form (one 128-byte MN chunk)
+}
+
+template <int HD>
+struct SkFwdCfg {
+  static constexpr int Q_BYTES = 128 * HD * 2, KV_BYTES = SK_KEYS * HD * 2;
+  static constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int OFF_P = STAGES * STAGE_BYTES;       // [128][64] bf16, 128-byte rows, SWIZZLE_128B
+  static constexpr int OFF_MSK = OFF_P + 128 * 128;        // [2 stages][64] fp32: additive key mask, log2 domain
+  static constexpr int OFF_BARS = OFF_MSK + 2 * SK_KEYS * 4;
+  static constexpr int SMEM = 1024 + OFF_BARS + 16 * 8;
+  static constexpr uint32_t S_COL0 = 0, S_COL1 = 64, O_COL0 = 128, O_COL1 = 192;
+};
+
+template <int HD, bool DROPOUT>
+__global__ void __launch_bounds__(SK_THREADS, 2) attn_sk_fwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV, int ntiles,
+                                                                   int n_items) {
+  using Cfg = SkFwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem + Cfg::OFF_P;
+  float* sMsk = reinterpret_cast<float*>(smem + Cfg::OFF_MSK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+  // timeout tags: 301 s_full, 302 o_full, 303 full, 304 s_empty, 305 p_ready, 306 stage_free, 307 o_empty
+  uint64_t* full = bars;            // [2] TMA boxes of a stage have landed     (expect_tx)
+  uint64_t* stage_free = bars + 2;  // [2] stage may be overwritten             (tcgen05.commit)
+  uint64_t* s_full = bars + 4;      // [2] S written                            (tcgen05.commit)
+  uint64_t* s_empty = bars + 6;     // [2] S read                               (4 element-wise warps)
+  uint64_t* p_ready = bars + 8;     //     P in smem                            (4 element-wise warps)
+  uint64_t* o_full = bars + 9;      // [2] O written, P consumed                (tcgen05.commit)
+  uint64_t* o_empty = bars + 11;    // [2] O drained                            (4 element-wise warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const float scale2 = p.scale * SK_LOG2E;
+
+  if (warp == SK_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&stage_free[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&s_empty[s], 4);
+        mbar_init(&o_full[s], 1);
+        mbar_init(&o_empty[s], 4);
+      }
+      mbar_init(p_ready, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  if (warp == SK_WARP_LD && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    // ================= element-wise warps: thread = query row of the tile =================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint8_t* p_row = sP + row * 128;
+    const int xr = row & 7;
+    const float keep_inv = DROPOUT ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    float m_prev = 0.f, l_prev = 1.f;
+    long long orow_prev = -1;   // global output row of the previous item (-1: row not valid)
+    long long lse_prev = 0;
+    int h_prev = 0;
+
+    auto epilogue = [&](int itp) {
+      const int bp = itp & 1;
+      sk_wait(&o_full[bp], (itp >> 1) & 1, 302, itp);
+      tc_fence_after();
+      uint32_t o[HD];
+      if constexpr (HD == 64) {
+        tmem_ld32(lane_addr + (bp ? Cfg::O_COL1 : Cfg::O_COL0), reinterpret_cast<uint32_t(&)[32]>(o[0]));
+        tmem_ld32(lane_addr + (bp ? Cfg::O_COL1 : Cfg::O_COL0) + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
+      } else {
+        tmem_ld32(lane_addr + (bp ? Cfg::O_COL1 : Cfg::O_COL0), reinterpret_cast<uint32_t(&)[32]>(o[0]));
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&o_empty[bp]);
+      if (orow_prev >= 0) {
+        const float inv = 1.0f / l_prev;
+        bf16* dst = p.o + orow_prev * p.ldo + h_prev * HD;
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c) = v;
+        }
+        if (p.lse) p.lse[lse_prev] = (m_prev + sk_lg2(l_prev)) * SK_LN2;
+      }
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int t = item % ntiles, gh = item / ntiles;
+      const int h = gh % p.nH, g = gh / p.nH;
+      const int b = it & 1;
+      const int qi = t * 128 + row;
+      // additive key mask of this group in the log2 domain; keys past Lk (rows of the next group) are switched off
+      if (row < SK_KEYS) {
+        float mk = -1e30f;
+        if (row < p.Lk) mk = p.key_mask ? p.key_mask[static_cast<long long>(g) * p.Lk + row] * SK_LOG2E : 0.f;
+        sMsk[b * SK_KEYS + row] = mk;
+      }
+      sk_bar_sync(1, 128);
+
+      sk_wait(&s_full[b], (it >> 1) & 1, 301, it);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld32(lane_addr + (b ? Cfg::S_COL1 : Cfg::S_COL0), reinterpret_cast<uint32_t(&)[32]>(v[0]));
+      tmem_ld32(lane_addr + (b ? Cfg::S_COL1 : Cfg::S_COL0) + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+      float mx = -1e30f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 mk = *reinterpret_cast<const float4*>(sMsk + b * SK_KEYS + j);
+        const float x0 = fmaf(__uint_as_float(v[j]), scale2, mk.x), x1 = fmaf(__uint_as_float(v[j + 1]), scale2, mk.y);
+        const float x2 = fmaf(__uint_as_float(v[j + 2]), scale2, mk.z), x3 = fmaf(__uint_as_float(v[j + 3]), scale2, mk.w);
+        v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
+        v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+        mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+      }
+      if (it > 0) sk_wait(&o_full[b ^ 1], ((it - 1) >> 1) & 1, 302, it);  // P V of the previous item has consumed P
+      float sum = 0.f;
+      const unsigned long long didx0 = DROPOUT ? ((static_cast<unsigned long long>(g) * p.nH + h) * p.Lq + qi) * p.Lk : 0ull;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        float pr[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pr[e] = ex2_approx(__uint_as_float(v[c8 * 8 + e]) - mx);
+          sum += pr[e];
+          if (DROPOUT) pr[e] = dropout_keep(p.seed, didx0 + c8 * 8 + e, p.drop_p) ? pr[e] * keep_inv : 0.f;
+        }
+        uint4 o;
+        o.x = pack_bf16(pr[0], pr[1]); o.y = pack_bf16(pr[2], pr[3]);
+        o.z = pack_bf16(pr[4], pr[5]); o.w = pack_bf16(pr[6], pr[7]);
+        *reinterpret_cast<uint4*>(p_row + ((c8 ^ xr) << 4)) = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      if (it > 0) epilogue(it - 1);
+      m_prev = mx;
+      l_prev = sum;
+      h_prev = h;
+      orow_prev = qi < p.Lq ? static_cast<long long>(g) * p.Lq + qi : -1;
+      lse_prev = (static_cast<long long>(g) * p.nH + h) * p.Lq + qi;
+      // (the mask row of stage b is rewritten two items later, behind the barrier of the item in between)
+    }
+    if (n_my > 0) epilogue(n_my - 1);
+  } else if (warp == SK_WARP_MMA) {
+    // ================= tcgen05.mma issuer =================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, SK_KEYS, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+    auto issue_s = [&](int it) {
+      const int s = it & 1;
+      sk_wait(&full[s], (it >> 1) & 1, 303, it);
+      sk_wait(&s_empty[s], ((it >> 1) & 1) ^ 1, 304, it);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + s * Cfg::STAGE_BYTES), k_addr = q_addr + Cfg::Q_BYTES;
+        const uint32_t d = tmem_base + (s ? Cfg::S_COL1 : Cfg::S_COL0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(d, sk_desc_kmajor<HD>(q_addr, ks), sk_desc_kmajor<HD>(k_addr, ks), idesc_s, ks);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) issue_s(0);
+#pragma unroll 1
+    for (int it = 0; it < n_my; ++it) {
+      if (it + 1 < n_my) issue_s(it + 1);
+      const int b = it & 1;
+      sk_wait(p_ready, it & 1, 305, it);
+      sk_wait(&o_empty[b], ((it >> 1) & 1) ^ 1, 307, it);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t v_addr = smem_u32(smem + b * Cfg::STAGE_BYTES + Cfg::Q_BYTES + Cfg::KV_BYTES), p_addr = smem_u32(sP);
+        const uint32_t d = tmem_base + (b ? Cfg::O_COL1 : Cfg::O_COL0);
+#pragma unroll
+        for (int kk = 0; kk < SK_KEYS / 16; ++kk)
+          umma_f16_ss(d, umma_desc_sw128(p_addr + kk * 32, 16, 1024), sk_desc_mnmajor<HD>(v_addr, kk), idesc_o, kk);
+        umma_commit(&o_full[b]);
+        umma_commit(&stage_free[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= TMA producer =================
+    if (lane == 0) {
+#pragma unroll 1
+      for (int it = 0; it < n_my; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int t = item % ntiles, gh = item / ntiles;
+        const int h = gh % p.nH, g = gh / p.nH;
+        const int s = it & 1;
+        if (it >= 2) sk_wait(&stage_free[s], ((it >> 1) - 1) & 1, 306, it);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_2d(st, &tmQ, &full[s], h * HD, g * p.Lq + t * 128);
+        tma_load_2d(st + Cfg::Q_BYTES, &tmK, &full[s], h * HD, g * p.Lk);
+        tma_load_2d(st + Cfg::Q_BYTES + Cfg::KV_BYTES, &tmV, &full[s], h * HD, g * p.Lk);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SK_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*SkEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+SkEncodeTiledFn sk_encode_fn() {
+  static SkEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<SkEncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D map over a row-major [rows, cols] bf16 activation (row pitch ld elements): box = hd columns x box_rows rows
+int sk_tmap(CUtensorMap* out, const bf16* base, long long ld, long long rows, int cols, int hd, int box_rows) {
+  SkEncodeTiledFn fn = sk_encode_fn();
+  FIBER_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(hd), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, hd == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FIBER_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (attention tile) failed with %d", static_cast<int>(r));
+  return 0;
+}
+
+template <int HD, bool DROPOUT>
+int launch_sk_fwd_t(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = SkFwdCfg<HD>;
+  auto kern = attn_sk_fwd_kernel<HD, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  const int C = p.nH * HD;
+  if (sk_tmap(&tq, p.q, p.ldq, static_cast<long long>(p.G) * p.Lq, C, HD, 128) ||
+      sk_tmap(&tk, p.k, p.ldk, static_cast<long long>(p.G) * p.Lk, C, HD, SK_KEYS) ||
+      sk_tmap(&tv, p.v, p.ldv, static_cast<long long>(p.G) * p.Lk, C, HD, SK_KEYS))
+    return -1;
+  const int ntiles = (p.Lq + 127) / 128;
+  const long long n_items = static_cast<long long>(p.G) * p.nH * ntiles;
+  FIBER_CHECK(n_items < (1ll << 31), "too many attention work items");
+  const int grid = static_cast<int>(n_items < 2ll * num_sms() ? n_items : 2ll * num_sms());
+  kern<<<grid, SK_THREADS, Cfg::SMEM, stream>>>(p, tq, tk, tv, ntiles, static_cast<int>(n_items));
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+static bool sk_aligned16(const void* ptr, long long ld) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0;
+}
+
+// plain mode, at most 64 keys per group, 16-byte addressable rows
+bool attn_sk_supported(const AttnParams& p, int hd) {
+  return p.mode == 0 && (hd == 32 || hd == 64) && p.Lk <= SK_KEYS && sk_aligned16(p.q, p.ldq) && sk_aligned16(p.k, p.ldk) &&
+         sk_aligned16(p.v, p.ldv) && sk_aligned16(p.o, p.ldo);
+}
+
+int launch_attn_sk_fwd(const AttnParams& p, int hd, cudaStream_t stream) {
+  if (hd == 32) return p.drop_p > 0.f ? launch_sk_fwd_t<32, true>(p, stream) : launch_sk_fwd_t<32, false>(p, stream);
+  return p.drop_p > 0.f ? launch_sk_fwd_t<64, true>(p, stream) : launch_sk_fwd_t<64, false>(p, stream);
+}
+
+}  // namespace fiber

@@ -41,6 +41,21 @@ int option_attn_small() {
   }
   return v;
 }
+// "attn_sk": bit 0 routes the forward of plain attention with at most 64 keys per group and at least 96 queries (i2t) to the
+// tcgen05 + TMA kernel of attention_sk.cu, bit 2 also short query sequences (RoBERTa self-attention).  Default 1
+// (validated on B200 in round 2), or FIBER_ATTN_SK.
+static std::atomic<int> g_attn_sk{-1};
+int option_attn_sk() {
+  int v = g_attn_sk.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_ATTN_SK");
+    v = e ? (atoi(e) & 7) : 1;
+    g_attn_sk.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+static std::atomic<int> g_attn_sk_launches{0};
+void count_attn_sk_launch() { g_attn_sk_launches.fetch_add(1, std::memory_order_relaxed); }
 static std::atomic<int> g_winattn_tc_launches{0};  // launches of the tcgen05 generation (tests check the routing)
 void count_winattn_tc_launch() { g_winattn_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 int option_winattn_tc() {
@@ -148,6 +163,10 @@ int fiber_set_option(const char* name, int32_t value) {
     fiber::g_attn_small.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
     return 0;
   }
+  if (name && strcmp(name, "attn_sk") == 0) {
+    fiber::g_attn_sk.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
+    return 0;
+  }
   if (name && strcmp(name, "tq_trace") == 0) {
     fiber::g_tq_trace.store(value > 0 ? 1 : 0, std::memory_order_relaxed);
     return 0;
@@ -159,6 +178,8 @@ int fiber_get_option(const char* name) {
   if (name && strcmp(name, "winattn_tc") == 0) return fiber::option_winattn_tc();
   if (name && strcmp(name, "attn_small") == 0) return fiber::option_attn_small();
   if (name && strcmp(name, "winattn_tc_launches") == 0) return fiber::g_winattn_tc_launches.load();
+  if (name && strcmp(name, "attn_sk") == 0) return fiber::option_attn_sk();
+  if (name && strcmp(name, "attn_sk_launches") == 0) return fiber::g_attn_sk_launches.load();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;
 }

@@ -39,9 +39,12 @@ int64_t fiber_launch_count(void);
  * (head_dim 32, at most 48 keys, more than 48 queries: i2t, swin_transformer.py:226-259) to a 4-warp / three-CTAs-per-SM
  * one, bit 2 the few-query case (head_dim 64, at most 48 queries, more than 48 keys: t2i, roberta.py:441-502) to the
  * 3-warp one; default 7 or FIBER_ATTN_SMALL.
+ * "attn_sk": bit 0 routes the FORWARD of mode-0 attention with at most 64 keys per group and at least 96 queries (i2t) to
+ * the tcgen05 + TMA kernel of csrc/attention_sk.cu, bit 2 also shorter query sequences; default 1 or FIBER_ATTN_SK.
  * "tq_trace" (debug): 1 makes the fourth-generation window backward record an event trace of one CTA (tools/tq_trace.py).
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
- * fiber_get_option returns the value ("winattn_tc_launches", read-only: launches of the tcgen05 generations so far). */
+ * fiber_get_option returns the value ("winattn_tc_launches" / "attn_sk_launches", read-only: launches of the tcgen05
+ * window / small-key kernels so far). */
 int fiber_set_option(const char* name, int32_t value);
 int fiber_get_option(const char* name);
 

@@ -152,6 +152,50 @@ def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked, small):
         lib.set_option("attn_small", -1)
 
 
+# tcgen05 generation of plain attention for at most 64 keys per group (csrc/attention_sk.cu; option "attn_sk": bit 0
+# forward, bit 1 backward).  Cases with more keys must fall through to the mma.sync kernels with the option set.
+SK_CASES = [(3, 12, 64, 40, 40, True), (2, 12, 64, 50, 50, True), (4, 12, 64, 33, 47, True), (256, 12, 64, 40, 40, True),
+            (2, 16, 32, 576, 40, True), (2, 32, 32, 144, 40, True), (3, 16, 32, 100, 48, False), (1, 4, 32, 1296, 50, True),
+            (5, 16, 32, 576, 64, False), (3, 12, 64, 130, 64, True), (2, 12, 64, 40, 576, False), (3, 12, 64, 33, 100, True)]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 5], ids=["mmasync", "sk_long", "sk_all"])
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", SK_CASES)
+def test_plain_attention_tcgen05(cuda_dev, B, nh, hd, Lq, Lk, masked, mode):
+    from fiber_b200 import lib
+    before = lib.get_option("attn_sk_launches")
+    lib.set_option("attn_sk", mode)
+    try:
+        _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked)
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("attn_sk", -1)
+    launched = lib.get_option("attn_sk_launches") - before
+    routed = Lk <= 64 and ((mode & 1 and Lq >= 96) or mode & 4)
+    assert launched == (1 if routed else 0)
+
+
+def test_plain_attention_tcgen05_dropout_matches_mma_sync(cuda_dev):
+    """Probability dropout uses the same counter-based hash in both generations: the tcgen05 forward must reproduce the
+    mma.sync forward's output (same kept set, same scaling) so that either backward can follow."""
+    from fiber_b200 import kernels as K, lib
+    B, nh, hd, Lq, Lk = 3, 12, 64, 130, 50
+    C = nh * hd
+    q = _rand((B * Lq, C), cuda_dev, 11)
+    kv = _rand((B * Lk, 2 * C), cuda_dev, 12)
+    outs = []
+    for mode in (0, 5):
+        lib.set_option("attn_sk", mode)
+        try:
+            outs.append(K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, hd ** -0.5, groups=B, lq=Lq, lk=Lk, drop_p=0.25, seed=99))
+        finally:
+            lib.set_option("attn_sk", -1)
+    (o0, l0), (o1, l1) = outs
+    _close(o1, o0.float(), 2e-2, "o with dropout")
+    torch.testing.assert_close(l1, l0, rtol=1e-3, atol=1e-3)
+    assert (o0.float().abs() > 0).float().mean() > 0.5
+
+
 def _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked):
     from fiber_b200 import kernels as K
     C = nh * hd
