@@ -261,8 +261,15 @@ def _no_dropout(model):
 
 
 def _grad_report(model, sdg, min_params):
-    """l2-rel error of every parameter gradient against the oracle's (sdg: name -> tensor with .grad)."""
+    """l2-rel error of every parameter gradient against the oracle's (sdg: name -> tensor with .grad).
+
+    The scalar gates (alpha_i2t / alpha_t2i) are long dot products with heavy cancellation: a gate whose true gradient
+    happens to be small is noise in ANY bf16 execution (tools/diag_alpha_grads.py: layer-11 alpha_t2i under the ITM loss
+    is -2.6e-4 in fp32, -1.4e-4 for the oracle under bf16 autocast, next to gates of 4e-3 .. 1.5e-2).  Their error is
+    therefore measured against the largest gate gradient, not against each gate's own value."""
     errs, scale = [], max(float(v.grad.norm()) for v in sdg.values() if v.grad is not None)
+    gate_scale = max([float(sdg[n].grad.abs().max()) for n, p in model.named_parameters()
+                      if p.numel() == 1 and n in sdg and sdg[n].grad is not None] + [0.0])
     for n, p in model.named_parameters():
         if n.startswith("rank_output"):
             continue
@@ -274,7 +281,10 @@ def _grad_report(model, sdg, min_params):
         assert torch.isfinite(p.grad).all(), n
         if float(go.norm()) < 1e-6 * scale:
             continue
-        errs.append((_l2rel(p.grad, go), n))
+        if p.numel() == 1 and gate_scale > 0:
+            errs.append((float((p.grad.float() - go.float()).abs().max()) / gate_scale, n))
+        else:
+            errs.append((_l2rel(p.grad, go), n))
     errs.sort()
     assert len(errs) > min_params, len(errs)
     return errs[len(errs) // 2][0], errs[int(len(errs) * 0.9)][0], errs[-1]
@@ -395,7 +405,9 @@ def test_training_step_384_vs_oracle_and_reference_fixture(cuda_dev):
     # ... and the reference's own gradient statistics (fixture): norms of a sample of parameters
     checked = 0
     for n, p in model.named_parameters():
-        if n in gold["grads"] and p.grad is not None and gold["grads"][n][1] > 1e-4:
+        # scalar gates (alpha_i2t / alpha_t2i) are judged in _grad_report on the scale of the largest gate gradient: a
+        # single bf16-noise-sized number has no meaningful relative error of its own
+        if n in gold["grads"] and p.grad is not None and p.numel() > 1 and gold["grads"][n][1] > 1e-4:
             assert abs(float(p.grad.double().norm()) - gold["grads"][n][1]) < 0.1 * gold["grads"][n][1] + 1e-6, n
             checked += 1
     assert checked > 400, checked

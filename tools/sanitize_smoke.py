@@ -36,5 +36,24 @@ K.cast_bf16(torch.randn(1001, device=dev)); K.patch_gather(torch.randn(1, 3, 32,
 ids = torch.randint(3, 50, (2, 10), device=dev); ids[0, 6:] = 1
 wd = torch.randn(50, 64, device=dev); ps = torch.randn(14, 64, device=dev); ty = torch.randn(1, 64, device=dev)
 e = K.embed_gather(ids, wd, ps, ty); K.embed_scatter(ids, e, torch.zeros_like(wd), torch.zeros_like(ps))
+# round 2: single-pass GELU epilogues (two store boxes), aux / residual epilogues with the coalesced loader, small-key
+# tcgen05 attention forward (with and without dropout), fused AdamW
+a2 = torch.randn(256, 128, device=dev).to(bf); w2 = torch.randn(288, 128, device=dev).to(bf)
+aux2 = torch.randn(256, 288, device=dev).to(bf); pre2 = torch.empty(256, 288, device=dev, dtype=bf)
+K.gemm(a2, w2, bias=torch.randn(288, device=dev), act=K.ACT_GELU_CACHE, preact=pre2)
+K.gemm(a2, w2, aux=aux2, act=K.ACT_MUL_AUX)
+K.gemm(a2, w2, bias=torch.randn(288, device=dev), residual=aux2, act=K.ACT_RES_PF, row_scale=torch.ones(2, device=dev), rows_per_scale=128)
+for nhh, hd, lq, lk, dp in ((2, 32, 200, 40, 0.0), (2, 64, 130, 50, 0.2)):
+    Cc = nhh * hd
+    qq = torch.randn(3 * lq, Cc, device=dev).to(bf); kk = torch.randn(3 * lk, 2 * Cc, device=dev).to(bf)
+    mk = torch.zeros(3, lk, device=dev); mk[1, lk - 5:] = -10000.0
+    lib.set_option("attn_sk", 5)
+    K.attn_fwd(qq, kk[:, :Cc], kk[:, Cc:], nhh, hd, hd ** -0.5, groups=3, lq=lq, lk=lk, key_mask=mk, drop_p=dp, seed=5)
+    lib.set_option("attn_sk", -1)
+from fiber_b200.optim import FusedAdamW
+ps = [torch.nn.Parameter(torch.randn(n, device=dev)) for n in (5, 1023, 70000)]
+for p_ in ps:
+    p_.grad = torch.randn_like(p_)
+FusedAdamW(ps, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01).step()
 torch.cuda.synchronize()
 print("sanitize smoke done, launches", lib.launch_count())
