@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
   // fp32 dQ accumulator [nqc*144][HD], only when both the query and the key loop have several chunks
   float* sDQ = reinterpret_cast<float*>(smem + (((sRid + ATT_MAXTOK) - smem + 15) & ~static_cast<ptrdiff_t>(15)));
 
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x;
   const int Lq = p.Lq, Lk = p.Lk;
@@ -413,7 +415,7 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
     if (gy > target) gy = target;
   }
   dim3 grid(p.nH, gy);
-  kern<<<grid, BW_NWARPS * 32, smem, stream>>>(p);
+  FIBER_CUDA(launch_k(kern, grid, dim3(BW_NWARPS * 32), smem, stream, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

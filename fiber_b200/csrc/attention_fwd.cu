@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attn_fwd_kernel(const AttnParams 
   int16_t* sB = reinterpret_cast<int16_t*>(sRow + ATT_MAXTOK);
   uint8_t* sRid = reinterpret_cast<uint8_t*>(sB + ATT_MAXTOK);
 
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * QROWS, h = blockIdx.y, g = blockIdx.z;
   const bool window = p.mode == 1;
@@ -251,7 +253,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.Lq + QROWS - 1) / QROWS, p.nH, p.mode == 1 ? p.G * (p.H / p.ws) * (p.W / p.ws) : p.G);
-  kern<<<grid, NWARPS * 32, smem, stream>>>(p);
+  FIBER_CUDA(launch_k(kern, grid, dim3(NWARPS * 32), smem, stream, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) attn_sk_fwd_kernel(const AttnPa
   const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const float scale2 = p.scale * SK_LOG2E;
 
+  pdl_trigger();
   if (warp == SK_WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) attn_sk_fwd_kernel(const AttnPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // nothing above touched global memory
 
   if (warp < 4) {
     // ================= element-wise warps: thread = query row of the tile =================
@@ -350,7 +352,7 @@ int launch_sk_fwd_t(const AttnParams& p, cudaStream_t stream) {
   const long long n_items = static_cast<long long>(p.G) * p.nH * ntiles;
   FIBER_CHECK(n_items < (1ll << 31), "too many attention work items");
   const int grid = static_cast<int>(n_items < 2ll * num_sms() ? n_items : 2ll * num_sms());
-  kern<<<grid, SK_THREADS, Cfg::SMEM, stream>>>(p, tq, tk, tv, ntiles, static_cast<int>(n_items));
+  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(SK_THREADS), Cfg::SMEM, stream, p, tq, tk, tv, ntiles, static_cast<int>(n_items)));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -68,6 +68,21 @@ int option_winattn_tc() {
   return v;
 }
 
+// "pdl": 1 = every launch carries the programmatic-stream-serialization attribute (common.cuh: launch_k), so a kernel's
+// prologue overlaps the previous kernel's tail; 0 = plain stream order.  Default 0, or FIBER_PDL: measured neutral on the
+// power-capped training step (profiles/r2_pdl_ab.txt: 207.3 / 210.4 ms with, 206.3 / 206.4 ms without), full GPU suite green
+// either way.
+static std::atomic<int> g_pdl{-1};
+int option_pdl() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_PDL");
+    v = e ? (atoi(e) != 0) : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static std::atomic<int> g_tq_trace{0};  // debug: event trace of the fourth-generation window backward (tools/tq_trace.py)
 int option_tq_trace() { return g_tq_trace.load(std::memory_order_relaxed); }
 
@@ -85,6 +100,7 @@ int num_sms() {
 }
 
 int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream);
+int mlm_ce_dispatch(const fiber_ce_args* a, int backward, cudaStream_t stream);
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream);
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream);
 
@@ -167,6 +183,10 @@ int fiber_set_option(const char* name, int32_t value) {
     fiber::g_attn_sk.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
     return 0;
   }
+  if (name && strcmp(name, "pdl") == 0) {
+    fiber::g_pdl.store(value < 0 ? -1 : (value != 0), std::memory_order_relaxed);
+    return 0;
+  }
   if (name && strcmp(name, "tq_trace") == 0) {
     fiber::g_tq_trace.store(value > 0 ? 1 : 0, std::memory_order_relaxed);
     return 0;
@@ -178,6 +198,7 @@ int fiber_get_option(const char* name) {
   if (name && strcmp(name, "winattn_tc") == 0) return fiber::option_winattn_tc();
   if (name && strcmp(name, "attn_small") == 0) return fiber::option_attn_small();
   if (name && strcmp(name, "winattn_tc_launches") == 0) return fiber::g_winattn_tc_launches.load();
+  if (name && strcmp(name, "pdl") == 0) return fiber::option_pdl();
   if (name && strcmp(name, "attn_sk") == 0) return fiber::option_attn_sk();
   if (name && strcmp(name, "attn_sk_launches") == 0) return fiber::g_attn_sk_launches.load();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
@@ -207,6 +228,13 @@ int fiber_init(void) {
 
 int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream) {
   return fiber::gemm_dispatch(args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fiber_mlm_ce_fwd(const fiber_ce_args* args, fiber_stream_t stream) {
+  return fiber::mlm_ce_dispatch(args, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+int fiber_mlm_ce_bwd(const fiber_ce_args* args, fiber_stream_t stream) {
+  return fiber::mlm_ce_dispatch(args, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fiber_attn_fwd(const fiber_attn_args* a, fiber_stream_t stream) {

@@ -38,6 +38,32 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached)
+int option_pdl();  // 1: launch with programmatic stream serialization (FIBER_PDL / fiber_set_option("pdl")); default 0
+
+#ifdef __CUDACC__
+// Every kernel of the library is launched through launch_k.  With the "pdl" option on, the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization: the CTAs of this kernel may become resident while the previous
+// kernel of the stream is still draining, run their prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// shared-memory tables) and then block in pdl_wait() until the previous grid has completed and its writes are visible.
+// Contract for every kernel: pdl_wait() is executed unconditionally by every thread BEFORE the first access to global
+// memory (read or write) and before any early return; pdl_trigger() sits at the top, so the next kernel's CTAs may
+// take the slots this grid frees.  Both instructions are no-ops for a launch without the attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = option_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // device helpers
@@ -49,6 +75,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- programmatic dependent launch (see launch_k) -------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

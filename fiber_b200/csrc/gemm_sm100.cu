@@ -41,6 +41,16 @@ struct GemmParams {
   int out_mode;
   int tma_store;  // epilogue variant: thread=row math -> swizzled smem box -> TMA store (no residual/aux)
   float* colsum;  // MN-major only: colsum[m] += scale * sum_k A[k, m] (extra N=16 MMA against a tile of ones)
+  // Device-side row count (or null): only the first *row_count rows of the activation operand carry work — K-major:
+  // output row tiles past it are skipped; MN-major (wgrad): reduction k-blocks past it are skipped.
+  const int* row_count;
+  // EPI == 2 (fused MLM decoder + cross-entropy, fiber_mlm_ce_fwd / _bwd)
+  const int* ce_labels;  // [M] target column, < 0 = ignored row
+  float* ce_part;        // act 8 out: [tiles_n * 4][ce_mpad] float4 (max2, sum2, best2, argmax bits), log2 domain
+  float* ce_xl;          // act 8 out: [M] logit at the label column (written by the one warp that owns it)
+  const float* ce_lse2;  // act 9 in: [M] log2-domain log-sum-exp
+  const float* ce_g;     // act 9 in: device scalar d(loss) / n_valid
+  int ce_mpad;
 };
 
 constexpr int GEMM_BM = 128;
@@ -55,7 +65,7 @@ constexpr int GEMM_THREADS = 576;  // TMA warp, MMA warp, 16 epilogue warps
 template <int BN, int EPI = 0>
 struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? (EPI == 1 ? 3 : 4) : (EPI == 1 ? 5 : 6);
-  static constexpr int BOXES = EPI == 1 ? 2 : 1;
+  static constexpr int BOXES = EPI == 1 ? 2 : 1;  // EPI == 2 (cross-entropy epilogues) keeps the EPI == 0 budget
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -304,6 +314,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
@@ -335,8 +346,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above touched only shared memory, TMEM and the kernel parameters
 
-  const int total_units = p.tiles_m * p.tiles_n * p.splits;
+  int tiles_m = p.tiles_m, kb_total = p.kb_total;
+  if (p.row_count) {
+    const int cnt = __ldg(p.row_count);
+    if (MN_MAJOR == 0) tiles_m = min(tiles_m, (cnt + GEMM_BM - 1) / GEMM_BM);
+    else               kb_total = min(kb_total, (cnt + GEMM_BK - 1) / GEMM_BK);
+  }
+  const int tiles_mn = tiles_m * p.tiles_n;
+  const int total_units = tiles_mn * p.splits;  // units whose k-range is empty (row_count) are skipped by every role
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -344,12 +363,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int tile = unit % (p.tiles_m * p.tiles_n);
-        const int split = unit / (p.tiles_m * p.tiles_n);
+        const int tile = unit % tiles_mn;
+        const int split = unit / tiles_mn;
         const int m0 = (tile / p.tiles_n) * GEMM_BM;
         const int n0 = (tile % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int kb1 = min(kb0 + p.kb_per_split, kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
@@ -380,10 +399,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const int split = unit / (p.tiles_m * p.tiles_n);
+      const int split = unit / tiles_mn;
       const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-      const bool cs_unit = do_cs && ((unit % (p.tiles_m * p.tiles_n)) % p.tiles_n == 0);  // first n-tile of its row
+      const int kb1 = min(kb0 + p.kb_per_split, kb_total);
+      if (kb0 >= kb1) continue;
+      const bool cs_unit = do_cs && ((unit % tiles_mn) % p.tiles_n == 0);  // first n-tile of its row
       // wait until the epilogue has drained this accumulator
       mbar_wait(&tempty_bar[acc], acc_phase[acc] ^ 1);
       tc_fence_after();
@@ -442,7 +462,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
       };
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int tile = unit % (p.tiles_m * p.tiles_n);
+        const int tile = unit % tiles_mn;
         const int m0 = (tile / p.tiles_n) * GEMM_BM;
         const int n0 = (tile % p.tiles_n) * BN;
         const int ncols = min(BN, p.N - n0);
@@ -552,6 +572,119 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1;
       }
       if (lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
+    } else if constexpr (EPI == 2) {
+      // Fused MLM decoder + cross-entropy (heads.py:40-43 + objectives.py:19-26): the [rows, vocabulary] logits exist
+      // only as TMEM accumulators.  act 8 (forward): every warp folds its 64 columns of the tile into one online
+      // soft-max partial per row — running maximum, sum of exponentials (both in the log2 domain), arg-max — and the
+      // warp that owns a row's label column also writes that logit.  act 9 (backward): the tile is recomputed and
+      // leaves as bf16 d(logits) = (softmax - onehot) * g through the TMA-store box.
+      const int act = p.act;
+      const int swz = (lane >> 1) & 3;
+      const int cnt = p.row_count ? __ldg(p.row_count) : p.M;
+      constexpr float LOG2E = 1.4426950408889634f;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit % tiles_mn;
+        const int m0 = (tile / p.tiles_n) * GEMM_BM;
+        const int tn = tile % p.tiles_n;
+        const int n0 = tn * BN;
+        const int ncols = min(BN, p.N - n0);
+        const long long row = static_cast<long long>(m0) + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const int label = row_ok ? __ldg(p.ce_labels + row) : -1;
+        float lse2 = 0.f, rs = 0.f;
+        if (act == 9 && row_ok) {
+          lse2 = __ldg(p.ce_lse2 + row);
+          rs = (label >= 0 && row < cnt) ? __ldg(p.ce_g) : 0.f;
+        }
+        float m_run = -3.0e38f, s_run = 0.f, best = -3.0e38f;
+        int best_i = 0;
+        mbar_wait(&tfull_bar[acc], (acc_phase >> acc) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < CPW; ++i) {
+          const int c0 = (cgrp * CPW + i) * 32;
+          if (c0 >= ncols) break;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+          uint8_t* box_row = box + lane * 64;
+          if (act == 9) {
+            if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the box
+            __syncwarp();
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[16];
+            tmem_ld16(taddr + hf * 16, r);
+            float4 bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + hf * 16 + j * 4));
+            tmem_ld_wait();
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bv[j].x;
+              x[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bv[j].y;
+              x[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bv[j].z;
+              x[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bv[j].w;
+            }
+            const int col0 = n0 + c0 + hf * 16;
+            const int lc = label - col0;  // in [0, 16) when this half holds the label column
+            if (act == 8) {
+              if (static_cast<unsigned>(lc) < 16u) {
+                float xl = 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) xl = (e == lc) ? x[e] : xl;
+                p.ce_xl[row] = xl;
+              }
+              float cm = -3.0e38f;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                x[e] *= LOG2E;
+                cm = fmaxf(cm, x[e]);
+              }
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (x[e] > best) { best = x[e]; best_i = col0 + e; }  // strict: the first maximum wins, as torch.argmax
+              }
+              const float m_new = fmaxf(m_run, cm);
+              float acc_s = s_run * exp2f(m_run - m_new);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) acc_s += exp2f(x[e] - m_new);
+              s_run = acc_s;
+              m_run = m_new;
+            } else {
+              float d[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float pr = exp2f(fmaf(x[e], LOG2E, -lse2));
+                d[e] = (pr - ((e == lc) ? 1.0f : 0.0f)) * rs;
+              }
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 o;
+                o.x = pack_bf16(d[8 * j + 0], d[8 * j + 1]); o.y = pack_bf16(d[8 * j + 2], d[8 * j + 3]);
+                o.z = pack_bf16(d[8 * j + 4], d[8 * j + 5]); o.w = pack_bf16(d[8 * j + 6], d[8 * j + 7]);
+                *reinterpret_cast<uint4*>(box_row + (((hf * 2 + j) ^ swz) << 4)) = o;
+              }
+            }
+          }
+          if (act == 9) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, box, n0 + c0, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
+        }
+        if (act == 8)
+          reinterpret_cast<float4*>(p.ce_part)[static_cast<long long>(tn * 4 + cgrp) * p.ce_mpad + row] =
+              make_float4(m_run, s_run, best, __int_as_float(best_i));
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc_phase ^= (1u << acc);
+        acc ^= 1;
+      }
+      if (lane == 0) tma_store_wait_read();  // smem must outlive the last bulk store
     } else {
     const float scale = p.scale ? __ldg(p.scale) : 1.0f;
     const float* __restrict__ bias = p.bias;
@@ -561,7 +694,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float* __restrict__ row_scale = p.row_scale;
     const int act = p.act, out_mode = p.out_mode, use_tma = p.tma_store;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const int tile = unit % (p.tiles_m * p.tiles_n);
+      const int tile = unit % tiles_mn;
+      if ((unit / tiles_mn) * p.kb_per_split >= kb_total) continue;  // empty k-range (row_count)
       const int m0 = (tile / p.tiles_n) * GEMM_BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int ncols = min(BN, p.N - n0);
@@ -810,7 +944,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                                     GemmCfg<BN, EPI>::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN, EPI>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, p);
+  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN, EPI>::SMEM_BYTES, stream, ta, tb, tc, tp, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -840,8 +974,9 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   const int mn = a->a_major;
   const int BN = (a->n > 128) ? 256 : 128;
 
-  GemmParams p;
+  GemmParams p{};
   p.M = a->m; p.N = a->n; p.K = a->k;
+  p.row_count = a->row_count;
   p.tiles_m = (a->m + GEMM_BM - 1) / GEMM_BM;
   p.tiles_n = (a->n + BN - 1) / BN;
   p.kb_total = (a->k + GEMM_BK - 1) / GEMM_BK;
@@ -923,6 +1058,102 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
     return mn ? launch_gemm<256, 1>(ta, tb, tc, tp, p, grid, stream) : launch_gemm<256, 0>(ta, tb, tc, tp, p, grid, stream);
   }
   return mn ? launch_gemm<128, 1>(ta, tb, tc, tp, p, grid, stream) : launch_gemm<128, 0>(ta, tb, tc, tp, p, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused MLM decoder + cross-entropy (fiber_mlm_ce_fwd / fiber_mlm_ce_bwd)
+// ------------------------------------------------------------------------------------------
+// One warp per row folds the row's per-warp-per-tile partials of the act-8 epilogue into the log-sum-exp, the arg-max
+// (lowest column on ties) and the row's loss lse - logit[label]; rows that are ignored (label < 0) or not computed
+// (row >= *row_count) get loss 0, prediction 0.
+__global__ void __launch_bounds__(256) ce_combine_kernel(const float4* __restrict__ part, int nparts, int mpad, int M,
+                                                         const int* __restrict__ labels, const int* __restrict__ row_count,
+                                                         const float* __restrict__ xl, float* __restrict__ lse2_out,
+                                                         float* __restrict__ loss_rows, int* __restrict__ pred) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int row = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  if (row >= M) return;
+  const int cnt = row_count ? __ldg(row_count) : M;
+  if (row >= cnt) {
+    if (lane == 0) { lse2_out[row] = 0.f; loss_rows[row] = 0.f; pred[row] = 0; }
+    return;
+  }
+  float m = -3.0e38f, s = 0.f, best = -3.0e38f;
+  int bi = 0x7fffffff;
+  for (int t = lane; t < nparts; t += 32) {
+    const float4 v = part[static_cast<long long>(t) * mpad + row];
+    const float mn = fmaxf(m, v.x);
+    s = s * exp2f(m - mn) + v.y * exp2f(v.x - mn);
+    m = mn;
+    const int vi = __float_as_int(v.w);
+    if (v.y > 0.f && (v.z > best || (v.z == best && vi < bi))) { best = v.z; bi = vi; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    const float mn = fmaxf(m, m2);
+    s = s * exp2f(m - mn) + s2 * exp2f(m2 - mn);
+    m = mn;
+    if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+  }
+  if (lane == 0) {
+    const float lse2 = m + log2f(s);
+    const int label = __ldg(labels + row);
+    lse2_out[row] = lse2;
+    loss_rows[row] = label >= 0 ? (lse2 - __ldg(xl + row) * 1.4426950408889634f) * 0.6931471805599453f : 0.f;
+    pred[row] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+int mlm_ce_dispatch(const fiber_ce_args* a, int backward, cudaStream_t stream) {
+  FIBER_CHECK(a != nullptr, "null args");
+  FIBER_CHECK(a->m > 0 && a->n > 256 && a->k > 0 && a->n % 32 == 0, "mlm_ce: bad shape %d x %d x %d (N %% 32 == 0, N > 256)",
+              a->m, a->n, a->k);
+  FIBER_CHECK(a->x && a->w && a->bias && a->labels && a->lse, "mlm_ce: x, w, bias, labels and lse are required");
+  constexpr int BN = 256;
+  GemmParams p{};
+  p.M = a->m; p.N = a->n; p.K = a->k;
+  p.tiles_m = (a->m + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_n = (a->n + BN - 1) / BN;
+  p.kb_total = (a->k + GEMM_BK - 1) / GEMM_BK;
+  p.splits = 1;
+  p.kb_per_split = p.kb_total;
+  p.bias = a->bias;
+  p.row_count = a->row_count;
+  p.ce_labels = a->labels;
+  p.ce_mpad = p.tiles_m * GEMM_BM;
+  CUtensorMap ta, tb;
+  if (make_tmap_bf16_2d(&ta, a->x, a->k, a->m, a->ldx, GEMM_BK, GEMM_BM)) return -1;
+  if (make_tmap_bf16_2d(&tb, a->w, a->k, a->n, a->ldw, GEMM_BK, BN)) return -1;
+  CUtensorMap tc = ta;
+  const int units = p.tiles_m * p.tiles_n;
+  const int sms = num_sms();
+  const int grid = units < sms ? units : sms;
+  if (!backward) {
+    FIBER_CHECK(a->part && a->label_logit && a->loss_rows && a->pred, "mlm_ce_fwd: part, label_logit, loss_rows, pred required");
+    p.act = 8;
+    p.ce_part = a->part;
+    p.ce_xl = a->label_logit;
+    if (launch_gemm<256, 0, 2>(ta, tb, tc, tc, p, grid, stream)) return -2;
+    const int blocks = (a->m + 7) / 8;  // eight rows (warps) per block
+    FIBER_CUDA(launch_k(ce_combine_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float4*>(a->part),
+                        p.tiles_n * 4, p.ce_mpad, a->m, a->labels, a->row_count, a->label_logit, a->lse, a->loss_rows, a->pred));
+    FIBER_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  FIBER_CHECK(a->dlogits && a->gscale, "mlm_ce_bwd: dlogits and gscale required");
+  FIBER_CHECK((a->lddl * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->dlogits) & 15) == 0,
+              "mlm_ce_bwd: d(logits) rows must be 16-byte aligned");
+  p.act = 9;
+  p.ce_lse2 = a->lse;
+  p.ce_g = a->gscale;
+  if (make_tmap_bf16_2d(&tc, a->dlogits, a->n, a->m, a->lddl, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+  return launch_gemm<256, 0, 2>(ta, tb, tc, tc, p, grid, stream);
 }
 
 }  // namespace fiber

@@ -32,6 +32,8 @@ constexpr int ADAMW_THREADS = 256;
 __global__ void __launch_bounds__(ADAMW_THREADS) adamw_multi_kernel(const AdamWTensor* __restrict__ tensors,
                                                                     const int2* __restrict__ chunks, int chunk_elems,
                                                                     float b1, float b2, float eps, float bias_corr) {
+  pdl_trigger();
+  pdl_wait();
   const int2 ck = chunks[blockIdx.x];  // (tensor index, chunk index inside the tensor)
   const AdamWTensor t = tensors[ck.x];
   const long long lo = static_cast<long long>(ck.y) * chunk_elems;
@@ -85,9 +87,9 @@ int adamw_multi_dispatch(const void* tensors, const void* chunks, int n_chunks, 
   if (n_chunks <= 0) return 0;
   // HF AdamW (correct_bias=True): step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)
   const double bc = sqrt(1.0 - pow(static_cast<double>(b2), step)) / (1.0 - pow(static_cast<double>(b1), step));
-  adamw_multi_kernel<<<n_chunks, ADAMW_THREADS, 0, stream>>>(reinterpret_cast<const AdamWTensor*>(tensors),
+  FIBER_CUDA(launch_k(adamw_multi_kernel, dim3(n_chunks), dim3(ADAMW_THREADS), 0, stream, reinterpret_cast<const AdamWTensor*>(tensors),
                                                              reinterpret_cast<const int2*>(chunks), chunk_elems, b1, b2, eps,
-                                                             static_cast<float>(bc));
+                                                             static_cast<float>(bc)));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

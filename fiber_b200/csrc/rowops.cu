@@ -87,6 +87,8 @@ __device__ __forceinline__ float group_sum(float v) {
 
 template <int VPL, int LPR, int ROWS>
 __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) ln_fwd_kernel(const LnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;  // rows per warp per group
   const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -193,6 +195,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) ln_fwd_kernel(const L
 
 template <int VPL, int LPR, int ROWS>
 __global__ void __launch_bounds__(256, (VPL <= 2) ? 2 : 1) ln_bwd_kernel(const LnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   extern __shared__ float s_acc[];  // [2][C]: dgamma, dbeta block partials
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
@@ -370,6 +374,8 @@ __device__ __forceinline__ long long ln_row_base(const LnParams& p, long long ro
 
 template <int VPL, int LPR, int ROWS, bool MERGE>
 __global__ void __launch_bounds__(256, 3) ln_fwd_fast_kernel(const LnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sl = lane % LPR, sr = lane / LPR;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -446,6 +452,8 @@ __global__ void __launch_bounds__(256, 3) ln_fwd_fast_kernel(const LnParams p) {
 // shared-memory slice instead of registers, which is what lets the packed rows stay register-resident.
 template <int VPL, int LPR, int ROWS, bool MERGE, bool SACC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const LnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   extern __shared__ __align__(16) float s_fast[];  // [2][C] block partials (+ [8 warps][2][C] when SACC)
   float* s_acc = s_fast;
@@ -613,10 +621,10 @@ template <int VPL, int LPR, int ROWS>
 static int ln_launch(const LnParams& p, bool bwd, cudaStream_t stream) {
   const int rpw = ROWS * (32 / LPR);
   if (!bwd) {
-    ln_fwd_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 6), 256, 0, stream>>>(p);
+    FIBER_CUDA(launch_k(ln_fwd_kernel<VPL, LPR, ROWS>, dim3(ln_grid(p.rows, rpw, 6)), dim3(256), 0, stream, p));
   } else {
     // few resident blocks => few global atomics for dgamma/dbeta
-    ln_bwd_kernel<VPL, LPR, ROWS><<<ln_grid(p.rows, rpw, 2), 256, 2 * p.C * sizeof(float), stream>>>(p);
+    FIBER_CUDA(launch_k(ln_bwd_kernel<VPL, LPR, ROWS>, dim3(ln_grid(p.rows, rpw, 2)), dim3(256), 2 * p.C * sizeof(float), stream, p));
   }
   FIBER_CUDA(cudaGetLastError());
   count_launch();
@@ -627,7 +635,7 @@ template <int VPL, int LPR, int ROWS, bool MERGE>
 static int ln_launch_fast(const LnParams& p, bool bwd, cudaStream_t stream) {
   const int rpw = ROWS * (32 / LPR);
   if (!bwd) {
-    ln_fwd_fast_kernel<VPL, LPR, ROWS, MERGE><<<ln_grid(p.rows, rpw, 3), 256, 0, stream>>>(p);
+    FIBER_CUDA(launch_k(ln_fwd_fast_kernel<VPL, LPR, ROWS, MERGE>, dim3(ln_grid(p.rows, rpw, 3)), dim3(256), 0, stream, p));
   } else {
     constexpr bool SACC = VPL >= 3;
     auto kern = ln_bwd_fast_kernel<VPL, LPR, ROWS, MERGE, SACC>;
@@ -639,7 +647,7 @@ static int ln_launch_fast(const LnParams& p, bool bwd, cudaStream_t stream) {
         attr_set = true;
       }
     }
-    kern<<<ln_grid(p.rows, rpw, 2), 256, smem, stream>>>(p);
+    FIBER_CUDA(launch_k(kern, dim3(ln_grid(p.rows, rpw, 2)), dim3(256), smem, stream, p));
   }
   FIBER_CUDA(cudaGetLastError());
   count_launch();
@@ -690,6 +698,8 @@ int ln_dispatch(const LnParams& p, bool bwd, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ld, long long M, int N,
                                                      float* out, const float* scale, const float* row_scale, int rps,
                                                      long long rows_per_block, int cw) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_part[2048];
   const int rpp = 256 / cw;                  // rows per pass
   const int slot = threadIdx.x / cw, lc = threadIdx.x - slot * cw;
@@ -742,6 +752,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // dot(a, b) -> *out += sum a[i]*b[i]   (2-D, row-major with independent leading dimensions)
 __global__ void __launch_bounds__(256) dot_kernel(const bf16* a, long long lda, const bf16* b, long long ldb,
                                                   long long M, int N, float* out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_w[8];
   const int vec_per_row = N / 8;
   const long long total = M * vec_per_row;
@@ -784,6 +796,8 @@ __device__ __forceinline__ bool keep_elem(unsigned long long seed, unsigned long
 __global__ void __launch_bounds__(256) rowwise_scale_kernel(const bf16* x, long long ldx, bf16* y, long long ldy,
                                                             long long M, int N, int mode, float p,
                                                             unsigned long long seed, const float* row_scale, int rps) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = N / 8;
   const long long total = M * vec_per_row;
   const float keep_inv = 1.0f / (1.0f - p);
@@ -809,6 +823,8 @@ __global__ void __launch_bounds__(256) rowwise_scale_kernel(const bf16* x, long 
 // out = add + (*alpha) * x   (gate: a + alpha_t2i * c, roberta.py:483; plain residual add when alpha == null)
 __global__ void __launch_bounds__(256) axpy_kernel(const bf16* x, long long ldx, const bf16* add, long long lda,
                                                    const float* alpha, bf16* out, long long ldo, long long M, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = N / 8;
   const long long total = M * vec_per_row;
   const float al = alpha ? *alpha : 1.0f;
@@ -826,6 +842,8 @@ __global__ void __launch_bounds__(256) axpy_kernel(const bf16* x, long long ldx,
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* x, bf16* y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
     if (i + 3 < n) {
@@ -840,6 +858,8 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* x, bf16
 // w f32 [N, K] (ldw) -> w_out bf16 [N, K] (ld_out) and wt_out bf16 [K, N] (ldt_out), either optional
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* w, long long ldw, int N, int K, bf16* w_out,
                                                              long long ld_out, bf16* wt_out, long long ldt_out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -864,6 +884,8 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* w, lon
 // PatchEmbed gather (timm PatchEmbed conv 4x4/s4 as a GEMM, fiber_module.py:311):
 // img f32 [B,3,R,R] -> patches bf16 [B*(R/4)^2, 64]; column = c*16 + kh*4 + kw, columns 48..63 = 0.
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float* img, bf16* out, int B, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int P = R / 4;
   const long long total = static_cast<long long>(B) * P * P * 16;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -897,6 +919,8 @@ __device__ __forceinline__ int roberta_pos_id(const long long* ids_row, int l, i
 __global__ void __launch_bounds__(256) embed_gather_kernel(const long long* ids, int B, int L, int C, int pad,
                                                            const float* word, const float* pos, const float* type,
                                                            bf16* out, long long ldo) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -919,6 +943,8 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const long long* ids,
 __global__ void __launch_bounds__(256) embed_scatter_kernel(const long long* ids, int B, int L, int C, int pad,
                                                             const bf16* dsum, long long ldd, float* dword,
                                                             float* dpos) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -959,8 +985,8 @@ int colsum_dispatch(const bf16* x, long long ld, long long M, int N, float* out,
   if (gy > (M + min_rows - 1) / min_rows) gy = (M + min_rows - 1) / min_rows;
   if (gy < 1) gy = 1;
   const long long rpb = (M + gy - 1) / gy;
-  colsum_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, stream>>>(x, ld, M, N, out, scale, row_scale,
-                                                                        rps > 0 ? rps : 1, rpb, cw);
+  FIBER_CUDA(launch_k(colsum_kernel, dim3(gx, static_cast<unsigned>(gy)), dim3(256), 0, stream, x, ld, M, N, out, scale, row_scale,
+                                                                        rps > 0 ? rps : 1, rpb, cw));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -971,7 +997,7 @@ int dot_dispatch(const bf16* a, long long lda, const bf16* b, long long ldb, lon
   FIBER_CHECK(N % 8 == 0 && M > 0, "dot: N must be a multiple of 8");
   int grid = ew_grid(M * (N / 8));
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  dot_kernel<<<grid, 256, 0, stream>>>(a, lda, b, ldb, M, N, out);
+  FIBER_CUDA(launch_k(dot_kernel, dim3(grid), dim3(256), 0, stream, a, lda, b, ldb, M, N, out));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -981,8 +1007,8 @@ int rowwise_scale_dispatch(const bf16* x, long long ldx, bf16* y, long long ldy,
                            float p, unsigned long long seed, const float* row_scale, int rps, cudaStream_t stream) {
   FIBER_CHECK(N % 8 == 0 && M > 0, "rowwise op: N must be a multiple of 8");
   FIBER_CHECK(mode == 0 ? (p >= 0.f && p < 1.f) : row_scale != nullptr, "bad rowwise op arguments");
-  rowwise_scale_kernel<<<ew_grid(M * (N / 8)), 256, 0, stream>>>(x, ldx, y, ldy, M, N, mode, p, seed, row_scale,
-                                                                rps > 0 ? rps : 1);
+  FIBER_CUDA(launch_k(rowwise_scale_kernel, dim3(ew_grid(M * (N / 8))), dim3(256), 0, stream, x, ldx, y, ldy, M, N, mode, p, seed, row_scale,
+                                                                rps > 0 ? rps : 1));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -991,7 +1017,7 @@ int rowwise_scale_dispatch(const bf16* x, long long ldx, bf16* y, long long ldy,
 int axpy_dispatch(const bf16* x, long long ldx, const bf16* add, long long lda, const float* alpha, bf16* out,
                   long long ldo, long long M, int N, cudaStream_t stream) {
   FIBER_CHECK(N % 8 == 0 && M > 0, "axpy: N must be a multiple of 8");
-  axpy_kernel<<<ew_grid(M * (N / 8)), 256, 0, stream>>>(x, ldx, add, lda, alpha, out, ldo, M, N);
+  FIBER_CUDA(launch_k(axpy_kernel, dim3(ew_grid(M * (N / 8))), dim3(256), 0, stream, x, ldx, add, lda, alpha, out, ldo, M, N));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -999,7 +1025,7 @@ int axpy_dispatch(const bf16* x, long long ldx, const bf16* add, long long lda, 
 
 int cast_dispatch(const float* x, bf16* y, long long n, cudaStream_t stream) {
   FIBER_CHECK(n > 0, "cast: empty");
-  cast_f32_bf16_kernel<<<ew_grid((n + 3) / 4), 256, 0, stream>>>(x, y, n);
+  FIBER_CUDA(launch_k(cast_f32_bf16_kernel, dim3(ew_grid((n + 3) / 4)), dim3(256), 0, stream, x, y, n));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1008,8 +1034,8 @@ int cast_dispatch(const float* x, bf16* y, long long n, cudaStream_t stream) {
 int cast_transpose_dispatch(const float* w, long long ldw, int N, int K, bf16* w_out, long long ld_out, bf16* wt_out,
                             long long ldt_out, cudaStream_t stream) {
   FIBER_CHECK(N > 0 && K > 0, "cast_transpose: empty");
-  cast_transpose_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), 256, 0, stream>>>(w, ldw, N, K, w_out, ld_out, wt_out,
-                                                                              ldt_out);
+  FIBER_CUDA(launch_k(cast_transpose_kernel, dim3((K + 31) / 32, (N + 31) / 32), dim3(256), 0, stream, w, ldw, N, K, w_out, ld_out, wt_out,
+                                                                              ldt_out));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1017,7 +1043,7 @@ int cast_transpose_dispatch(const float* w, long long ldw, int N, int K, bf16* w
 
 int patch_gather_dispatch(const float* img, bf16* out, int B, int R, cudaStream_t stream) {
   FIBER_CHECK(B > 0 && R % 4 == 0, "patch_gather: image size must be a multiple of 4");
-  patch_gather_kernel<<<ew_grid(static_cast<long long>(B) * (R / 4) * (R / 4) * 16), 256, 0, stream>>>(img, out, B, R);
+  FIBER_CUDA(launch_k(patch_gather_kernel, dim3(ew_grid(static_cast<long long>(B) * (R / 4) * (R / 4) * 16)), dim3(256), 0, stream, img, out, B, R));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1026,8 +1052,8 @@ int patch_gather_dispatch(const float* img, bf16* out, int B, int R, cudaStream_
 int embed_dispatch(const long long* ids, int B, int L, int C, int pad, const float* word, const float* pos,
                    const float* type, bf16* out, long long ldo, cudaStream_t stream) {
   FIBER_CHECK(C % 4 == 0 && B > 0 && L > 0, "embed: width must be a multiple of 4");
-  embed_gather_kernel<<<ew_grid(static_cast<long long>(B) * L * 32), 256, 0, stream>>>(ids, B, L, C, pad, word, pos,
-                                                                                      type, out, ldo);
+  FIBER_CUDA(launch_k(embed_gather_kernel, dim3(ew_grid(static_cast<long long>(B) * L * 32)), dim3(256), 0, stream, ids, B, L, C, pad, word, pos,
+                                                                                      type, out, ldo));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1036,8 +1062,8 @@ int embed_dispatch(const long long* ids, int B, int L, int C, int pad, const flo
 int embed_scatter_dispatch(const long long* ids, int B, int L, int C, int pad, const bf16* dsum, long long ldd,
                            float* dword, float* dpos, cudaStream_t stream) {
   FIBER_CHECK(C % 2 == 0 && B > 0 && L > 0, "embed_scatter: width must be even");
-  embed_scatter_kernel<<<ew_grid(static_cast<long long>(B) * L * 32), 256, 0, stream>>>(ids, B, L, C, pad, dsum, ldd,
-                                                                                       dword, dpos);
+  FIBER_CUDA(launch_k(embed_scatter_kernel, dim3(ew_grid(static_cast<long long>(B) * L * 32)), dim3(256), 0, stream, ids, B, L, C, pad, dsum, ldd,
+                                                                                       dword, dpos));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

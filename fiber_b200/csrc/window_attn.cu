@@ -134,6 +134,8 @@ __device__ __forceinline__ void wf_tile(const bf16* sQ, const bf16* sK, const bf
 }
 
 __global__ void __launch_bounds__(WF_THREADS, 2) win_attn_fwd_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int PITCH = WA_PITCH;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, K, V][144][PITCH]
@@ -379,6 +381,8 @@ __device__ __forceinline__ void w3_job_a(const bf16* sQ, const bf16* sdO, const 
 }
 
 __global__ void __launch_bounds__(W3_THREADS, 1) win_attn_bwd_kernel(const AttnParams p, const float* __restrict__ Dg) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int PITCH = WA_PITCH, SP = WA_SP;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* tiles = reinterpret_cast<bf16*>(smem);  // [2 buffers][Q, dO, K, V][144][PITCH]
@@ -581,6 +585,8 @@ __global__ void __launch_bounds__(W3_THREADS, 1) win_attn_bwd_kernel(const AttnP
 __global__ void __launch_bounds__(256) win_attn_bwd_prep_kernel(const bf16* __restrict__ o, long long ldo,
                                                                 const bf16* __restrict__ d_o, long long lddo,
                                                                 float* __restrict__ D, long long rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = C / 8;
   const long long total = rows * vec_per_row;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -625,7 +631,7 @@ int launch_win_fwd(const AttnParams& p, cudaStream_t stream) {
   int gy = 2 * num_sms() / p.nH;  // two CTAs per SM, single wave, persistent over windows
   if (gy < 1) gy = 1;
   if (gy > n_groups) gy = n_groups;
-  win_attn_fwd_kernel<<<dim3(p.nH, gy), WF_THREADS, smem, stream>>>(p);
+  FIBER_CUDA(launch_k(win_attn_fwd_kernel, dim3(p.nH, gy), dim3(WF_THREADS), smem, stream, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -638,7 +644,7 @@ int launch_win_bwd_prep(const AttnParams& p, float* D, cudaStream_t stream) {
   long long blocks = (rows * (C / 8) + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  win_attn_bwd_prep_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p.o, p.ldo, p.d_o, p.lddo, D, rows, C);
+  FIBER_CUDA(launch_k(win_attn_bwd_prep_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, p.o, p.ldo, p.d_o, p.lddo, D, rows, C));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -657,7 +663,7 @@ int launch_win_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
     FIBER_CUDA(cudaFuncSetAttribute(win_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  win_attn_bwd_kernel<<<dim3(p.nH, gy), W3_THREADS, smem, stream>>>(p, D);
+  FIBER_CUDA(launch_k(win_attn_bwd_kernel, dim3(p.nH, gy), dim3(W3_THREADS), smem, stream, p, D));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

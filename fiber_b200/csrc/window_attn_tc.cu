@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_fwd_kernel(const At
   const int n_my = (n_groups - static_cast<int>(blockIdx.y) + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
   const float scale2 = p.scale * WA_LOG2E;
 
+  pdl_trigger();
+  pdl_wait();
   fill_tables(T, p.bias_table, p.nH, h, TC_WS, p.shift, TC_N, tid, TC_THREADS);
   if (warp == TC_WARP_MMA) {
     if (lane == 0) {
@@ -760,6 +762,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tc_bwd_kernel(const At
   const int n_my = (n_groups - static_cast<int>(blockIdx.y) + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
   const float scale2 = p.scale * WA_LOG2E;
 
+  pdl_trigger();
+  pdl_wait();
   fill_tables(T, p.bias_table, p.nH, h, TC_WS, p.shift, TC_N, tid, TC_THREADS);
   if (warp == TC_WARP_MMA) {
     if (lane == 0) {
@@ -1345,7 +1349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_fwd_kernel(const At
   tq_my_windows(p.G * geo.nW, first, n_my);
   const float scale2 = p.scale * WA_LOG2E;
 
-  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TC_THREADS);
+  pdl_trigger();
   if (warp == TC_WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < TQF_STAGES; ++s) {
@@ -1370,6 +1374,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) win_attn_tq_fwd_kernel(const At
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
+  pdl_wait();  // first global access below (the relative-position table)
+  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TC_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1751,7 +1757,7 @@ __global__ void __launch_bounds__(TQB_THREADS, 1) win_attn_tq_bwd_kernel(const A
   tq_my_windows(p.G * geo.nW, first, n_my);
   const float scale2 = p.scale * WA_LOG2E;
 
-  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TQB_THREADS);
+  pdl_trigger();
   if (warp == TC_WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < TQB_STAGES; ++s) {
@@ -1777,6 +1783,8 @@ __global__ void __launch_bounds__(TQB_THREADS, 1) win_attn_tq_bwd_kernel(const A
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
   }
+  pdl_wait();  // first global access below (the relative-position table)
+  fill_tables_quad(T, p.bias_table, p.nH, h, p.shift, tid, TQB_THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -2085,7 +2093,7 @@ static int launch_win_tq_fwd(const AttnParams& p, cudaStream_t stream) {
   if (win_tmap(&tq, p.q, p.ldq, p.G, p.H, p.W, C) || win_tmap(&tk, p.k, p.ldk, p.G, p.H, p.W, C) ||
       win_tmap(&tv, p.v, p.ldv, p.G, p.H, p.W, C))
     return -1;
-  win_attn_tq_fwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TQF_SMEM, stream>>>(p, tq, tk, tv);
+  FIBER_CUDA(launch_k(win_attn_tq_fwd_kernel, dim3(p.nH, tc_grid_y(p)), dim3(TC_THREADS), TQF_SMEM, stream, p, tq, tk, tv));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   count_winattn_tc_launch();
@@ -2103,7 +2111,7 @@ int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream) {
     FIBER_CUDA(cudaFuncSetAttribute(win_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
     attr_set = true;
   }
-  win_attn_tc_fwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TF_SMEM, stream>>>(p);
+  FIBER_CUDA(launch_k(win_attn_tc_fwd_kernel, dim3(p.nH, tc_grid_y(p)), dim3(TC_THREADS), TF_SMEM, stream, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   count_winattn_tc_launch();
@@ -2136,7 +2144,7 @@ static int launch_win_tq_bwd(const AttnParams& p, cudaStream_t stream) {
       win_tmap(&tk, p.k, p.ldk, p.G, p.H, p.W, C) || win_tmap(&tv, p.v, p.ldv, p.G, p.H, p.W, C) ||
       win_tmap(&to, p.o, p.ldo, p.G, p.H, p.W, C))
     return -1;
-  win_attn_tq_bwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TQB_THREADS, TQB_SMEM, stream>>>(p, tq, tdo, tk, tv, to, trace);
+  FIBER_CUDA(launch_k(win_attn_tq_bwd_kernel, dim3(p.nH, tc_grid_y(p)), dim3(TQB_THREADS), TQB_SMEM, stream, p, tq, tdo, tk, tv, to, trace));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   count_winattn_tc_launch();
@@ -2153,7 +2161,7 @@ int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream) {
     FIBER_CUDA(cudaFuncSetAttribute(win_attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
     attr_set = true;
   }
-  win_attn_tc_bwd_kernel<<<dim3(p.nH, tc_grid_y(p)), TC_THREADS, TB_SMEM, stream>>>(p, D);
+  FIBER_CUDA(launch_k(win_attn_tc_bwd_kernel, dim3(p.nH, tc_grid_y(p)), dim3(TC_THREADS), TB_SMEM, stream, p, D));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   count_winattn_tc_launch();

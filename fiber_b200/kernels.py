@@ -56,12 +56,14 @@ def _rowmajor_2d(t, name):
 
 def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=None, scale=None,
          row_scale=None, rows_per_scale=1, act=ACT_NONE, out=None, out_dtype=BF16,
-         accumulate=False, splits=0, colsum=None):
+         accumulate=False, splits=0, colsum=None, row_count=None):
     """out[M,N] = epilogue(A . B^T).
 
     mn_major=False: a is [M,K], b is [N,K]  (forward / dgrad with a transposed weight copy)
     mn_major=True : a is [K,M], b is [K,N]  (wgrad: a = dY [rows,N_out], b = X [rows,K_in]);
                     colsum (fp32 [M]) additionally accumulates scale * sum_k a[k, :] (the bias gradient)
+    row_count (int32 device scalar): only the first row_count activation rows carry work — output row tiles past it are
+                    not written (mn_major=False), reduction rows past it are not read (mn_major=True)
     """
     _req(a, BF16, "a"); _req(b, BF16, "b")
     lda = _rowmajor_2d(a, "a"); ldb = _rowmajor_2d(b, "b")
@@ -112,6 +114,8 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
         if not mn_major or colsum.numel() != m or not colsum.is_contiguous():
             raise RuntimeError("fiber_b200.gemm: colsum needs mn_major=True and a contiguous fp32 [M] tensor")
         args.colsum = colsum.data_ptr()
+    if row_count is not None:
+        _req(row_count, torch.int32, "row_count"); args.row_count = row_count.data_ptr()
     if GEMM_PROFILE is None:
         _lib.check(_lib.load().fiber_gemm(C.byref(args), _stream()), "gemm")
         return out
@@ -125,6 +129,51 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
                                    ("preact", preact is not None), ("res", residual is not None),
                                    ("wgrad", mn_major)) if on) or "plain"
     GEMM_PROFILE.append(((m, n, k, epi), 2.0 * m * n * k, nbytes, e0, e1))
+    return out
+
+
+def _ce_args(x, w, bias, labels, row_count):
+    _req(x, BF16, "x"); _req(w, BF16, "w"); _req(bias, F32, "bias"); _req(labels, torch.int32, "labels")
+    m, k = x.shape
+    n, k2 = w.shape
+    if k != k2 or bias.numel() != n or labels.numel() != m or n % 32 != 0:
+        raise RuntimeError("fiber_b200.mlm_ce: shapes x %s, w %s, bias %d, labels %d (N %% 32 == 0)"
+                           % (tuple(x.shape), tuple(w.shape), bias.numel(), labels.numel()))
+    args = _lib.CeArgs()
+    args.x, args.w, args.bias, args.labels = x.data_ptr(), w.data_ptr(), bias.data_ptr(), labels.data_ptr()
+    args.m, args.n, args.k = m, n, k
+    args.ldx, args.ldw = _rowmajor_2d(x, "x"), _rowmajor_2d(w, "w")
+    if row_count is not None:
+        _req(row_count, torch.int32, "row_count"); args.row_count = row_count.data_ptr()
+    return args, m, n
+
+
+def mlm_ce_fwd(x, w, bias, labels, row_count=None):
+    """Fused decoder GEMM + cross-entropy forward (include/fiber_b200.h: fiber_mlm_ce_fwd).
+    Returns (lse [M] fp32, log2 domain; loss_rows [M] fp32; pred [M] int32); the logits are never written."""
+    args, m, n = _ce_args(x, w, bias, labels, row_count)
+    mpad = (m + 127) // 128 * 128
+    part = torch.empty((4 * ((n + 255) // 256), mpad, 4), device=x.device, dtype=F32)
+    xl = torch.zeros(m, device=x.device, dtype=F32)
+    lse = torch.empty(m, device=x.device, dtype=F32)
+    loss_rows = torch.empty(m, device=x.device, dtype=F32)
+    pred = torch.empty(m, device=x.device, dtype=torch.int32)
+    args.part, args.label_logit, args.lse = part.data_ptr(), xl.data_ptr(), lse.data_ptr()
+    args.loss_rows, args.pred = loss_rows.data_ptr(), pred.data_ptr()
+    _lib.check(_lib.load().fiber_mlm_ce_fwd(C.byref(args), _stream()), "mlm_ce_fwd")
+    return lse, loss_rows, pred
+
+
+def mlm_ce_bwd(x, w, bias, labels, lse, gscale, row_count=None, out=None):
+    """d(logits) [M, N] bf16 = (softmax - onehot) * gscale of the fused decoder + cross-entropy (fiber_mlm_ce_bwd); row
+    tiles past row_count are left untouched."""
+    args, m, n = _ce_args(x, w, bias, labels, row_count)
+    _req(lse, F32, "lse"); _req(gscale, F32, "gscale")
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=BF16)
+    args.lse, args.gscale = lse.data_ptr(), gscale.data_ptr()
+    args.dlogits, args.lddl = out.data_ptr(), _rowmajor_2d(out, "dlogits")
+    _lib.check(_lib.load().fiber_mlm_ce_bwd(C.byref(args), _stream()), "mlm_ce_bwd")
     return out
 
 

@@ -28,6 +28,18 @@ class GemmArgs(C.Structure):
         ("row_scale", C.c_void_p), ("rows_per_scale", C.c_int32),
         ("act", C.c_int32), ("out_mode", C.c_int32), ("splits", C.c_int32),
         ("colsum", C.c_void_p),
+        ("row_count", C.c_void_p),
+    ]
+
+
+class CeArgs(C.Structure):
+    """Mirror of `fiber_ce_args` (include/fiber_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("labels", C.c_void_p), ("row_count", C.c_void_p),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("ldx", C.c_int64), ("ldw", C.c_int64),
+        ("part", C.c_void_p), ("label_logit", C.c_void_p), ("lse", C.c_void_p), ("loss_rows", C.c_void_p),
+        ("pred", C.c_void_p), ("dlogits", C.c_void_p), ("lddl", C.c_int64), ("gscale", C.c_void_p),
     ]
 
 
@@ -89,6 +101,8 @@ def load():
     lib.fiber_set_option.argtypes = [C.c_char_p, C.c_int32]
     lib.fiber_get_option.argtypes = [C.c_char_p]
     lib.fiber_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.fiber_mlm_ce_fwd.argtypes = [C.POINTER(CeArgs), C.c_void_p]
+    lib.fiber_mlm_ce_bwd.argtypes = [C.POINTER(CeArgs), C.c_void_p]
     lib.fiber_attn_fwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.fiber_attn_bwd.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     V, I64, I32, F = C.c_void_p, C.c_int64, C.c_int32, C.c_float

@@ -55,3 +55,9 @@ class MLMHead(nn.Module):
         if h.is_cuda:  # 768 -> vocab projection (3.1 GFLOP per pair fwd+bwd) on the tcgen05 GEMM
             return ops.VocabDecoderFn.apply(h, self.decoder.weight, self.bias)
         return self.decoder(h) + self.bias
+
+    def loss_and_pred(self, x, labels):
+        """cross_entropy(forward(x), labels, ignore_index=-100) and forward(x).argmax(-1) (0 on ignored rows) without the
+        logits in memory (ops.MlmDecoderCEFn); what objectives.compute_mlm uses on the GPU."""
+        h = self.transform(x)
+        return ops.MlmDecoderCEFn.apply(h, self.decoder.weight, self.bias, labels)

@@ -72,7 +72,9 @@ class Metric(nn.Module):
 class Accuracy(Metric):  # gadgets/my_metrics.py:5-29
     def batch_state(self, logits, target):
         logits, target = logits.detach(), target.detach()
-        preds = logits.argmax(dim=-1)
+        # an integer tensor of the target's shape is taken as the predictions themselves (the fused MLM decoder +
+        # cross-entropy returns the arg-max, not the logits)
+        preds = logits if (not logits.is_floating_point() and logits.shape == target.shape) else logits.argmax(dim=-1)
         keep = target != -100
         # same sums as the reference's boolean-mask indexing, without its two device->host syncs per update
         # (the mask is applied arithmetically; an all-ignored batch adds 0 / 0 exactly like the early return)

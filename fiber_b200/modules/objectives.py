@@ -4,6 +4,8 @@ init_weights :502.  They are callers of infer(); losses are ordinary torch ops o
 infer() returns.  One deliberate change: the 2*B `.item()` host syncs of the
 hard-negative sampling loop (:154-165) are replaced by one batched torch.multinomial per direction
 (same per-row distribution)."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -19,23 +21,44 @@ def init_weights(module):
         module.bias.data.zero_()
 
 
+# On the GPU the MLM loss comes from the fused decoder + cross-entropy (heads.MLMHead.loss_and_pred: the [B L, 50265] fp32
+# logits never reach memory); the returned dict then carries "mlm_pred" (the arg-max the accuracy metric needs) instead
+# of "mlm_logits".  FIBER_MLM_FUSED_CE=0 / set_fused_mlm_ce(False) restore the reference's logits -> F.cross_entropy form.
+FUSED_MLM_CE = os.environ.get("FIBER_MLM_FUSED_CE", "1") != "0"
+
+
+def set_fused_mlm_ce(on):
+    global FUSED_MLM_CE
+    FUSED_MLM_CE = bool(on)
+
+
+def _mlm_tail(pl_module, text_feats, mlm_labels, mlm_ids):
+    """objectives.py:19-41 of the reference on the text features of the masked pairs."""
+    if FUSED_MLM_CE and text_feats.is_cuda and hasattr(pl_module.mlm_score, "loss_and_pred"):
+        mlm_loss, mlm_pred = pl_module.mlm_score.loss_and_pred(text_feats, mlm_labels)
+        ret = {"mlm_loss": mlm_loss, "mlm_pred": mlm_pred, "mlm_labels": mlm_labels, "mlm_ids": mlm_ids}
+        acc_in = mlm_pred
+    else:
+        mlm_logits = pl_module.mlm_score(text_feats)
+        mlm_loss = F.cross_entropy(mlm_logits.view(-1, pl_module.hparams.config["vocab_size"]).float(),
+                                   mlm_labels.view(-1), ignore_index=-100)
+        ret = {"mlm_loss": mlm_loss, "mlm_logits": mlm_logits, "mlm_labels": mlm_labels, "mlm_ids": mlm_ids}
+        acc_in = mlm_logits
+    phase = _phase(pl_module)
+    loss = getattr(pl_module, f"{phase}_mlm_loss")(ret["mlm_loss"])
+    acc = getattr(pl_module, f"{phase}_mlm_accuracy")(acc_in, ret["mlm_labels"])
+    pl_module.log(f"mlm/{phase}/loss", loss)
+    pl_module.log(f"mlm/{phase}/accuracy", acc)
+    return ret
+
+
 def _phase(pl_module):
     return "train" if pl_module.training else "val"
 
 
 def compute_mlm(pl_module, batch):
     infer = pl_module.infer(batch, mask_text=True, mask_image=False)
-    mlm_logits = pl_module.mlm_score(infer["text_feats"])
-    mlm_labels = infer["text_labels"]
-    mlm_loss = F.cross_entropy(mlm_logits.view(-1, pl_module.hparams.config["vocab_size"]).float(),
-                               mlm_labels.view(-1), ignore_index=-100)
-    ret = {"mlm_loss": mlm_loss, "mlm_logits": mlm_logits, "mlm_labels": mlm_labels, "mlm_ids": infer["text_ids"]}
-    phase = _phase(pl_module)
-    loss = getattr(pl_module, f"{phase}_mlm_loss")(ret["mlm_loss"])
-    acc = getattr(pl_module, f"{phase}_mlm_accuracy")(ret["mlm_logits"], ret["mlm_labels"])
-    pl_module.log(f"mlm/{phase}/loss", loss)
-    pl_module.log(f"mlm/{phase}/accuracy", acc)
-    return ret
+    return _mlm_tail(pl_module, infer["text_feats"], infer["text_labels"], infer["text_ids"])
 
 
 def _itm_tail(pl_module, infer, itm_labels):
@@ -93,14 +116,7 @@ def compute_mlm_itm_hardneg_merged(pl_module, batch, image_neg, text_neg, text_m
     merged["text_labels"] = torch.cat([batch["text_labels_mlm"]] + [batch["text_labels"]] * 3, dim=0)
     infer = pl_module.infer(merged, mask_text=False, mask_image=False)
     # ---- MLM on the first B samples (objectives.py:19-41) ----
-    mlm_logits = pl_module.mlm_score(infer["text_feats"][:B])
-    mlm_labels = batch["text_labels_mlm"]
-    mlm_loss = F.cross_entropy(mlm_logits.view(-1, pl_module.hparams.config["vocab_size"]).float(),
-                               mlm_labels.view(-1), ignore_index=-100)
-    ret = {"mlm_loss": mlm_loss, "mlm_logits": mlm_logits, "mlm_labels": mlm_labels, "mlm_ids": batch["text_ids_mlm"]}
-    phase = _phase(pl_module)
-    pl_module.log(f"mlm/{phase}/loss", getattr(pl_module, f"{phase}_mlm_loss")(mlm_loss))
-    pl_module.log(f"mlm/{phase}/accuracy", getattr(pl_module, f"{phase}_mlm_accuracy")(mlm_logits, mlm_labels))
+    ret = _mlm_tail(pl_module, infer["text_feats"][:B], batch["text_labels_mlm"], batch["text_ids_mlm"])
     # ---- ITM on the remaining 3B samples (objectives.py:99-116) ----
     itm_labels = torch.cat([torch.ones(B), torch.zeros(2 * B)]).to(pl_module.device)
     ret.update(_itm_tail(pl_module, {"cls_feats": infer["cls_feats"][B:]}, itm_labels))

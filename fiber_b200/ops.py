@@ -200,10 +200,10 @@ def _fc2_dgrad_gelu(dz, w2_t, buf, cached):
     return K.gemm(dz, w2_t, aux=buf, act=K.ACT_GELU_GRAD)
 
 
-def _wgrad(dy, x, scale=None, out=None, db=None):
+def _wgrad(dy, x, scale=None, out=None, db=None, row_count=None):
     """dW[N,K] = dy[rows,N]^T x[rows,K]  (fp32, split-K atomics on a zeroed buffer); db[N] += colsum(dy)
     comes out of the same kernel (one extra 128x16 MMA per k-step against a tile of ones)."""
-    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale, out=out, colsum=db)
+    return K.gemm(dy, x, mn_major=True, accumulate=True, scale=scale, out=out, colsum=db, row_count=row_count)
 
 
 def _colsum(x, out=None, **kw):
@@ -251,12 +251,13 @@ class LinearFn(torch.autograd.Function):
 class VocabDecoderFn(torch.autograd.Function):
     """MLM decoder (heads.py:40-43): logits = x W^T + b over the 50265-word vocabulary, fp32 out.
     The vocabulary is not a multiple of 8 (TMA rows are 16 bytes), so the cached bf16 weight copy carries
-    zero rows up to the next multiple and the returned logits are the [..., :V] view of the padded buffer."""
+    zero rows up to the next multiple of 32 (the padding MlmDecoderCEFn needs: both share the cached copy) and the
+    returned logits are the [..., :V] view of the padded buffer."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         V = weight.shape[0]
-        Vp = (V + 7) // 8 * 8
+        Vp = (V + 31) // 32 * 32
         x2 = _to_bf16_2d(x)
         w, wt = CACHE.weights((weight,), pad_n=Vp)
         bp = torch.zeros(Vp, device=x2.device, dtype=F32)
@@ -276,6 +277,56 @@ class VocabDecoderFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dyp, wt, out_dtype=F32 if xdtype == F32 else BF16).view(xshape)
         return dx, dw[:V], dbp[:V]
+
+
+class MlmDecoderCEFn(torch.autograd.Function):
+    """MLM decoder + cross-entropy + arg-max in one pass (heads.py:40-43, objectives.py:19-26, my_metrics.py Accuracy):
+    `F.cross_entropy(h W^T + b, labels, ignore_index=-100)` and `(h W^T + b).argmax(-1)` without the [B L, 50265] fp32
+    logits ever reaching HBM.
+
+    Only labelled rows contribute to the loss, its gradient and the accuracy, so the rows are permuted labelled-first (a
+    stable device-side argsort, no host sync) and the kernels take the labelled count as a device scalar: row tiles past
+    it are skipped.  Forward: tcgen05 GEMM whose epilogue reduces each accumulator tile to online-softmax partials +
+    a combine kernel.  Backward: the GEMM is recomputed with an epilogue that emits bf16 d(logits) for the labelled
+    row tiles; dX, dW and db are the usual dgrad / wgrad GEMMs on it.  Returns (loss, predictions [rows], 0 on ignored rows)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, labels):
+        V = weight.shape[0]
+        Vp = (V + 31) // 32 * 32
+        x2 = _to_bf16_2d(h)
+        lab = labels.reshape(-1)
+        valid = lab >= 0
+        order = torch.argsort((~valid).to(torch.uint8), stable=True)  # labelled rows first, original order within
+        n_valid = valid.sum(dtype=torch.int32).reshape(1)
+        xs = x2.index_select(0, order)
+        ls = lab.index_select(0, order).to(torch.int32)
+        w, wt = CACHE.weights((weight,), pad_n=Vp)
+        bp = torch.full((Vp,), -1e30, device=x2.device, dtype=F32)  # pad columns vanish from the soft-max
+        bp[:V] = bias.detach()
+        lse, loss_rows, pred_s = K.mlm_ce_fwd(xs, w, bp, ls, row_count=n_valid)
+        loss = (loss_rows.sum() / n_valid.to(F32)).reshape(())  # 0 / 0 = nan for an all-ignored batch, as F.cross_entropy
+        pred = torch.zeros(x2.shape[0], device=x2.device, dtype=torch.int64)
+        pred.index_copy_(0, order, pred_s.to(torch.int64))
+        ctx.saved = (xs, ls, w, wt, bp, lse, n_valid, order, V, h.shape, h.dtype)
+        ctx.mark_non_differentiable(pred)
+        return loss, pred.view(labels.shape)
+
+    @staticmethod
+    def backward(ctx, dloss, _dpred):
+        xs, ls, w, wt, bp, lse, n_valid, order, V, hshape, hdtype = ctx.saved
+        g = (dloss.to(F32) / n_valid.to(F32)).reshape(1).contiguous()
+        dl = K.mlm_ce_bwd(xs, w, bp, ls, lse, g, row_count=n_valid)
+        dbp = torch.zeros(bp.shape[0], device=xs.device, dtype=F32)
+        dw = _wgrad(dl, xs, db=dbp, row_count=n_valid)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxs = torch.zeros(xs.shape, device=xs.device, dtype=BF16)
+            K.gemm(dl, wt, out=dxs, row_count=n_valid)
+            dx = torch.empty_like(dxs)
+            dx.index_copy_(0, order, dxs)
+            dx = dx.view(hshape).to(hdtype)
+        return dx, dw[:V], dbp[:V], None
 
 
 class LayerNormFn(torch.autograd.Function):

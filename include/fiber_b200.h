@@ -93,9 +93,45 @@ typedef struct fiber_gemm_args {
   /* MN-major (wgrad) only, out_mode 1 / 2: colsum[m] += scale * sum_k A[k, m] — the bias gradient
    * db = dY^T 1 that goes with dW = dY^T X (one extra 128 x 16 MMA per k-step against a tile of ones). */
   float* colsum;
+  /* Device-side row count (int32 scalar in device memory) or NULL.  Only the first *row_count rows of the activation operand
+   * carry work: K-major launches skip the output row tiles past it (those rows of c are NOT written), MN-major (wgrad) launches
+   * skip the reduction k-blocks past it.  Lets a caller that compacted its valid rows to the front (the labelled MLM positions)
+   * launch without reading the count back to the host. */
+  const int32_t* row_count;
 } fiber_gemm_args;
 
 int fiber_gemm(const fiber_gemm_args* args, fiber_stream_t stream);
+
+/* ---- fused MLM decoder + cross-entropy -----------------------------------------------------
+ * Replaces `mlm_logits = decoder(h) + bias` (heads.py:40-43) followed by `F.cross_entropy(mlm_logits.view(-1, V), labels.view(-1),
+ * ignore_index=-100)` (objectives.py:19-26) and the arg-max the accuracy metric takes of the same logits (gadgets/my_metrics.py:
+ * Accuracy.update): the [rows, V] logits live only as TMEM accumulators of the tcgen05 GEMM.
+ *   fiber_mlm_ce_fwd: per row r < *row_count: lse[r] = log2-domain log-sum-exp of x[r] . w^T + bias, loss_rows[r] = natural-log
+ *       lse - logit[r, labels[r]] (0 when labels[r] < 0), pred[r] = arg-max column (first maximum).  Rows >= *row_count get 0.
+ *   fiber_mlm_ce_bwd: dlogits[r, c] = bf16((softmax(logits[r])[c] - (c == labels[r])) * *gscale) for labelled rows, 0 for ignored
+ *       rows; row tiles past *row_count are not written.  dX / dW / dbias then are plain fiber_gemm calls on dlogits
+ *       (with the same row_count).
+ * n % 32 == 0: pad the vocabulary with zero weight rows and a large negative bias (e.g. -1e30) so pad columns vanish. */
+typedef struct fiber_ce_args {
+  const void* x;            /* bf16 [M, K] */
+  const void* w;            /* bf16 [N, K] */
+  const float* bias;        /* [N] */
+  const int32_t* labels;    /* [M], < 0 = ignored row */
+  const int32_t* row_count; /* device scalar or NULL (= all M rows) */
+  int32_t m, n, k;
+  int64_t ldx, ldw;
+  float* part;        /* fwd workspace: 4 * ceil(N / 256) * (ceil(M / 128) * 128) * 4 floats */
+  float* label_logit; /* fwd workspace [M] */
+  float* lse;         /* [M]: fwd out, bwd in (log2 domain) */
+  float* loss_rows;   /* fwd out [M] */
+  int32_t* pred;      /* fwd out [M] */
+  void* dlogits;      /* bwd out bf16 [M, N] */
+  int64_t lddl;
+  const float* gscale; /* bwd in: device scalar */
+} fiber_ce_args;
+
+int fiber_mlm_ce_fwd(const fiber_ce_args* args, fiber_stream_t stream);
+int fiber_mlm_ce_bwd(const fiber_ce_args* args, fiber_stream_t stream);
 
 /* ---- small-sequence attention (flash-style; scores never reach HBM) ------------------------
  * mode 1 (window): Swin W-MSA/SW-MSA core, swin_transformer.py:205-222 with the roll /

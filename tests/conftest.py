@@ -24,3 +24,14 @@ def cuda_dev():
     l = lib.load()
     lib.check(l.fiber_init(), "init")
     return torch.device("cuda:0")
+
+
+@pytest.fixture
+def unfused_mlm_ce():
+    """The reference's logits -> F.cross_entropy form of the MLM loss (tests that compare mlm_logits element-wise); the
+    default on the GPU is the fused decoder + cross-entropy, which never materialises them."""
+    from fiber_b200.modules import objectives as OBJ
+    old = OBJ.FUSED_MLM_CE
+    OBJ.set_fused_mlm_ce(False)
+    yield
+    OBJ.set_fused_mlm_ce(old)

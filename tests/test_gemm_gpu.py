@@ -231,3 +231,30 @@ def test_gemm_residual_prefetch_is_bit_identical(cuda_dev, m, n, k, with_bias, w
     finally:
         K.set_res_prefetch(False)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("count", [0, 1, 100, 128, 300, 1000])
+def test_gemm_device_row_count(cuda_dev, count):
+    """fiber_gemm_args.row_count: a device scalar says how many leading activation rows carry work.  K-major launches leave
+    the output row tiles past it untouched; MN-major (wgrad) launches reduce over the leading rows only (whole 64-row
+    k-blocks: the caller zero-fills up to the block edge, as the fused MLM cross-entropy backward does)."""
+    from fiber_b200 import kernels as K
+    m, n, k = 1000, 384, 256
+    a = _mk((m, k), cuda_dev, 11)
+    b = _mk((n, k), cuda_dev, 12, k ** -0.5)
+    cnt = torch.tensor([count], device=cuda_dev, dtype=torch.int32)
+    out = torch.full((m, n), 7.0, device=cuda_dev, dtype=torch.bfloat16)
+    K.gemm(a, b, out=out, row_count=cnt)
+    edge = min(m, (count + 127) // 128 * 128)
+    ref = a.float() @ b.float().t()
+    torch.testing.assert_close(out[:edge].float(), ref[:edge], rtol=RTOL, atol=ATOL)
+    assert bool((out[edge:] == 7.0).all())
+    # wgrad: dW = dY^T X over the first ceil(count / 64) * 64 rows
+    dy = _mk((m, n), cuda_dev, 13)
+    x = _mk((m, k), cuda_dev, 14)
+    kedge = min(m, (count + 63) // 64 * 64)
+    db = torch.zeros(n, device=cuda_dev)
+    dw = K.gemm(dy, x, mn_major=True, accumulate=True, colsum=db, row_count=cnt)
+    ref_w = dy[:kedge].float().t() @ x[:kedge].float()
+    torch.testing.assert_close(dw, ref_w, rtol=2e-2, atol=2e-2 * max(1.0, kedge ** 0.5))
+    torch.testing.assert_close(db, dy[:kedge].float().sum(0), rtol=2e-2, atol=2e-2 * max(1.0, kedge ** 0.5))

@@ -162,7 +162,7 @@ def test_training_step_with_dropout_runs(cuda_dev, m224):
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
-def test_merged_mlm_itm_pass_equals_separate_passes(cuda_dev):
+def test_merged_mlm_itm_pass_equals_separate_passes(cuda_dev, unfused_mlm_ce):
     """The 4B-sample merged MLM+ITM pass gives the losses of the reference's separate passes."""
     from fiber_b200.modules import fiber_utils
     model, cfg, sd = _build(["itm", "mlm", "itc"], 224, 40, cuda_dev)
@@ -330,7 +330,7 @@ def test_itm_hardneg_vs_oracle_and_reference_fixture(cuda_dev):
     assert median < 3e-2 and p90 < 6e-2 and worst[0] < 0.35, (median, p90, worst)
 
 
-def test_training_step_384_vs_oracle_and_reference_fixture(cuda_dev):
+def test_training_step_384_vs_oracle_and_reference_fixture(cuda_dev, unfused_mlm_ce):
     """The benchmarked objective mix at the benchmarked resolution (BASELINE configs[1]: ITM + ITC + MLM, 384 px,
     40 tokens), B = 2, dropout off, deterministic negatives: the three losses, the ITM and MLM logits ELEMENT-WISE
     and every parameter gradient — against the oracle on this GPU and the unmodified reference's fixture

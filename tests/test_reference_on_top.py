@@ -87,8 +87,17 @@ def test_reference_objectives_run_on_top_of_the_cuda_backbone(cuda_dev):
     batch = to_dev(synth.synth_batch(4, 224, 40, seed=77, false_image=True))
     with torch.no_grad():
         # MLM
+        OBJ.set_fused_mlm_ce(False)
         a, b = ref_obj.compute_mlm(model, dict(batch)), OBJ.compute_mlm(model, dict(batch))
         assert torch.equal(a["mlm_logits"], b["mlm_logits"]) and float(a["mlm_loss"]) == pytest.approx(float(b["mlm_loss"]), rel=1e-6)
+        # ... and the default form of this repo's caller (fused decoder + cross-entropy, no logits): the reference's loss
+        # and the arg-max of the reference's logits at every labelled position
+        OBJ.set_fused_mlm_ce(True)
+        c = OBJ.compute_mlm(model, dict(batch))
+        assert "mlm_logits" not in c
+        assert float(c["mlm_loss"]) == pytest.approx(float(a["mlm_loss"]), rel=2e-5)
+        keep = a["mlm_labels"] != -100
+        assert int(keep.sum()) > 0 and torch.equal(c["mlm_pred"][keep], a["mlm_logits"].argmax(-1)[keep])
         # ITM with false images: same label permutation on both sides through the RNG seed
         torch.manual_seed(3)
         a = ref_obj.compute_itm(model, dict(batch))

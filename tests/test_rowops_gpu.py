@@ -184,3 +184,55 @@ def test_fused_adamw_matches_hf_update(cuda_dev):
     p1 = ps[1].detach().clone()
     opt.step()
     assert torch.equal(ps[0].detach(), before) and torch.equal(ps[1].detach(), p1 * (1 - 0.0 * 0.01))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,V,frac", [(2560, 50265, 0.15), (80, 50265, 0.5), (384, 1000, 1.0), (200, 4096, 0.0),
+                                         (2560, 50265, 1.0)])
+def test_fused_mlm_decoder_cross_entropy(cuda_dev, rows, V, frac):
+    """ops.MlmDecoderCEFn (fiber_mlm_ce_fwd / _bwd: decoder GEMM with cross-entropy epilogues, labelled rows first, device
+    row count) against F.cross_entropy on fp32 logits of the same bf16-rounded operands (heads.py:40-43 +
+    objectives.py:19-26): loss, arg-max at the labelled rows, d(hidden), d(weight), d(bias).  frac = share of labelled rows
+    (0: the all-ignored batch gives nan like F.cross_entropy; 1: no row is skipped)."""
+    from fiber_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(rows * 7 + V)
+    Kd = 768
+    h = (torch.randn(rows, Kd, generator=g) * 1.5).to(cuda_dev).to(torch.bfloat16)
+    w = (torch.randn(V, Kd, generator=g) * 0.05).to(cuda_dev)
+    b = (torch.randn(V, generator=g) * 0.5).to(cuda_dev)
+    labels = torch.randint(0, V, (rows,), generator=g)
+    labels[torch.rand(rows, generator=g) >= frac] = -100
+    if frac > 0 and frac < 1:
+        labels[3] = V - 1  # the last real column (next to the padded ones)
+    labels = labels.to(cuda_dev)
+    hp = h.clone().requires_grad_(True)
+    wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    loss, pred = ops.MlmDecoderCEFn.apply(hp, wp, bp, labels)
+    # fp32 reference on the operands the kernel sees (bf16 hidden rows, bf16 weight copy, fp32 bias)
+    hr = h.float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    logits = hr @ wr.t() + br
+    ref = F.cross_entropy(logits, labels, ignore_index=-100)
+    keep = labels != -100
+    if frac == 0.0:
+        assert torch.isnan(loss) and torch.isnan(ref)
+        return
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref)), (float(loss), float(ref))
+    ref_pred = logits.argmax(-1)
+    agree = (pred[keep] == ref_pred[keep])
+    if not bool(agree.all()):  # a disagreement must be a numerical tie of the two top logits
+        bad = keep.nonzero().flatten()[~agree]
+        top = logits[bad].gather(1, torch.stack([pred[bad], ref_pred[bad]], 1))
+        assert (top[:, 0] - top[:, 1]).abs().max().item() < 1e-4
+    assert int(pred[~keep].abs().sum()) == 0
+    (loss * 3.0).backward()
+    (ref * 3.0).backward()
+
+    def l2rel(a, r):
+        return ((a.float() - r.float()).norm() / r.float().norm().clamp_min(1e-30)).item()
+    # d(logits) leaves the epilogue as bf16 (2^-9 relative per element), accumulated in fp32 by the dgrad / wgrad GEMMs
+    assert l2rel(hp.grad, hr.grad) < 6e-3, l2rel(hp.grad, hr.grad)
+    assert l2rel(wp.grad, wr.grad) < 6e-3, l2rel(wp.grad, wr.grad)
+    assert l2rel(bp.grad, br.grad) < 6e-3, l2rel(bp.grad, br.grad)
+    assert hp.grad[~keep].abs().max().item() == 0.0 if bool((~keep).any()) else True
