@@ -83,6 +83,24 @@ int option_pdl() {
   return v;
 }
 
+// "gemm_cta2": bit 0 runs K-major GEMMs with 256-column tiles and M % 256 == 0 as CTA pairs (2-CTA clusters, tcgen05
+// cta_group::2: 256 x 256 pair tiles, half of the B tile per CTA) for the default epilogues, bit 1 for the two-box epilogues
+// (act 3 .. 7), in both cases only when K >= 1024: measured on B200 (profiles/r2_gemm_cta_pairs.txt) +3 .. +9 % at K >= 1024
+// and -3 .. -20 % at K <= 512, where a tile is four to eight k-blocks and the pair's longer hand-offs (remote arrives,
+// multicast commits) show.  Default 3, or FIBER_GEMM_CTA2; bit 2 lifts the K >= 1024 rule (tests, microbenchmarks).
+static std::atomic<int> g_gemm_cta2{-1};
+static std::atomic<int> g_gemm_cta2_launches{0};
+void count_gemm_cta2_launch() { g_gemm_cta2_launches.fetch_add(1, std::memory_order_relaxed); }
+int option_gemm_cta2() {
+  int v = g_gemm_cta2.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_GEMM_CTA2");
+    v = e ? (atoi(e) & 7) : 3;
+    g_gemm_cta2.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static std::atomic<int> g_tq_trace{0};  // debug: event trace of the fourth-generation window backward (tools/tq_trace.py)
 int option_tq_trace() { return g_tq_trace.load(std::memory_order_relaxed); }
 
@@ -183,6 +201,10 @@ int fiber_set_option(const char* name, int32_t value) {
     fiber::g_attn_sk.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
     return 0;
   }
+  if (name && strcmp(name, "gemm_cta2") == 0) {
+    fiber::g_gemm_cta2.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
+    return 0;
+  }
   if (name && strcmp(name, "pdl") == 0) {
     fiber::g_pdl.store(value < 0 ? -1 : (value != 0), std::memory_order_relaxed);
     return 0;
@@ -199,6 +221,8 @@ int fiber_get_option(const char* name) {
   if (name && strcmp(name, "attn_small") == 0) return fiber::option_attn_small();
   if (name && strcmp(name, "winattn_tc_launches") == 0) return fiber::g_winattn_tc_launches.load();
   if (name && strcmp(name, "pdl") == 0) return fiber::option_pdl();
+  if (name && strcmp(name, "gemm_cta2") == 0) return fiber::option_gemm_cta2();
+  if (name && strcmp(name, "gemm_cta2_launches") == 0) return fiber::g_gemm_cta2_launches.load();
   if (name && strcmp(name, "attn_sk") == 0) return fiber::option_attn_sk();
   if (name && strcmp(name, "attn_sk_launches") == 0) return fiber::g_attn_sk_launches.load();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");

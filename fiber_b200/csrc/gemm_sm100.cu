@@ -21,6 +21,8 @@
 namespace fiber {
 
 void count_launch(int n = 1);
+void count_gemm_cta2_launch();
+int option_gemm_cta2();  // capi.cu: bit 0 = CTA pairs for the default epilogues, bit 1 = for the two-box (EPI = 1) epilogues
 
 struct GemmParams {
   int M, N, K;
@@ -62,12 +64,17 @@ constexpr int GEMM_THREADS = 576;  // TMA warp, MMA warp, 16 epilogue warps
 // before the next result could be staged (6.6 us per tile against 2.3 us of MMAs).  They trade one operand stage for a
 // second box per warp: the two outputs of a chunk (and consecutive chunks) alternate boxes, and a box is rewritten
 // only when the store issued two stores ago has been read (cp.async.bulk.wait_group.read 1).
-template <int BN, int EPI = 0>
+// CTA2 = 1 (K-major, BN = 256): the kernel runs as CTA pairs (2-CTA clusters, tcgen05 cta_group::2).  A pair owns a
+// 256 x 256 output tile: each CTA loads its own 128 rows of A and HALF of the B tile (128 of the 256 weight rows), the
+// leader issues 256 x 256 x 16 MMAs that read both halves, and each CTA drains its own 128 x 256 accumulator.  A stage
+// is 32 KB instead of 48 KB per CTA: a third less L2 -> shared-memory traffic per flop (what bounds the 128 x 256
+// single-CTA tile at ~1.3 PFLOP/s) and two more stages in the same shared memory.
+template <int BN, int EPI = 0, int CTA2 = 0>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? (EPI == 1 ? 3 : 4) : (EPI == 1 ? 5 : 6);
+  static constexpr int STAGES = CTA2 ? (EPI == 1 ? 5 : 6) : (BN == 256) ? (EPI == 1 ? 3 : 4) : (EPI == 1 ? 5 : 6);
   static constexpr int BOXES = EPI == 1 ? 2 : 1;  // EPI == 2 (cross-entropy epilogues) keeps the EPI == 0 budget
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+  static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t STAGING_BYTES = 16 * 2048 * BOXES;  // 16 epilogue warps x BOXES x (32 rows x 64 B) TMA-store box
   static constexpr uint32_t SMEM_BYTES =
@@ -286,12 +293,15 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
 
-template <int BN, int MN_MAJOR, int EPI = 0>
+template <int BN, int MN_MAJOR, int EPI = 0, int CTA2 = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN, EPI>;
+  static_assert(!CTA2 || (MN_MAJOR == 0 && BN == 256), "CTA pairs: K-major operands, 256-column tiles");
+  using Cfg = GemmCfg<BN, EPI, CTA2>;
+  constexpr int NCTA = CTA2 ? 2 : 1;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs, owns the full / tempty barriers)
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem;
@@ -325,13 +335,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 16);
+        mbar_init(&tempty_bar[a], 16 * NCTA);  // pair: the epilogue warps of both CTAs arrive on the leader's barrier
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc2(tmem_ptr, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   // Bias-gradient column sums (wgrad): a tile of bf16 ones in the (otherwise unused) TMA-store staging area is
   // the B operand of one extra 128 x 16 MMA per k-step; its accumulator sits behind the single main accumulator.
@@ -343,7 +358,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   const int nacc = do_cs ? 1 : 2;  // accumulators in flight (the column-sum columns take the second one's place)
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else                __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above touched only shared memory, TMEM and the kernel parameters
@@ -354,18 +370,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (MN_MAJOR == 0) tiles_m = min(tiles_m, (cnt + GEMM_BM - 1) / GEMM_BM);
     else               kb_total = min(kb_total, (cnt + GEMM_BK - 1) / GEMM_BK);
   }
+  if constexpr (CTA2) tiles_m /= 2;  // a pair's unit is a 256-row tile (host: M % 256 == 0, no row_count)
   const int tiles_mn = tiles_m * p.tiles_n;
   const int total_units = tiles_mn * p.splits;  // units whose k-range is empty (row_count) are skipped by every role
+  const int unit0 = static_cast<int>(blockIdx.x) / NCTA, unit_step = static_cast<int>(gridDim.x) / NCTA;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit % tiles_mn;
         const int split = unit / tiles_mn;
-        const int m0 = (tile / p.tiles_n) * GEMM_BM;
+        const int m0 = ((tile / p.tiles_n) * NCTA + static_cast<int>(cta_rank)) * GEMM_BM;
         const int n0 = (tile % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, kb_total);
@@ -373,6 +391,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if constexpr (CTA2) {
+            // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t bar = mapa_cta(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2sm(sa, &tmA, bar, kb * GEMM_BK, m0);
+            tma_load_2d_2sm(sb, &tmB, bar, kb * GEMM_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (MN_MAJOR == 0) {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
@@ -388,17 +415,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (CTA2) {
+        // the leader's multicast commits still arrive on this CTA's empty barriers after its last load was issued:
+        // see every slot released before the CTA may leave the cluster
+        for (int s = 0; s < STAGES; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, MN_MAJOR, MN_MAJOR);
+    // ================= MMA issuer (pair: the leader CTA only) =================
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * NCTA, BN, MN_MAJOR, MN_MAJOR);
     constexpr uint32_t idesc_cs = umma_idesc_bf16(GEMM_BM, 16, MN_MAJOR, MN_MAJOR);
     const uint32_t ones_addr = smem_u32(staging);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < total_units && cta_rank == 0; unit += unit_step) {
       const int split = unit / tiles_mn;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, kb_total);
@@ -424,13 +459,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               adesc = umma_desc_sw128(sa + k * 2048, 8192, 1024);
               bdesc = umma_desc_sw128(sb + k * 2048, 8192, 1024);
             }
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CTA2) umma_f16_ss2(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else                umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (MN_MAJOR == 1 && cs_unit)
               umma_f16_ss(tmem_base + BN, adesc, umma_desc_sw128(ones_addr + k * 2048, 8192, 1024), idesc_cs,
                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+          if constexpr (CTA2) {  // the same barrier offset in both CTAs of the pair
+            umma_commit2_mc(&empty_bar[stage], 3);
+            if (kb == kb1 - 1) umma_commit2_mc(&tfull_bar[acc], 3);
+          } else {
+            umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -461,9 +502,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
       };
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit % tiles_mn;
-        const int m0 = (tile / p.tiles_n) * GEMM_BM;
+        const int m0 = ((tile / p.tiles_n) * NCTA + static_cast<int>(cta_rank)) * GEMM_BM;
         const int n0 = (tile % p.tiles_n) * BN;
         const int ncols = min(BN, p.N - n0);
         const long long row = static_cast<long long>(m0) + q * 32 + lane;
@@ -567,7 +608,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_cluster(mapa_cta(smem_u32(&tempty_bar[acc]), 0));
+          else                mbar_arrive(&tempty_bar[acc]);
+        }
         acc_phase ^= (1u << acc);
         acc ^= 1;
       }
@@ -582,7 +626,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int swz = (lane >> 1) & 3;
       const int cnt = p.row_count ? __ldg(p.row_count) : p.M;
       constexpr float LOG2E = 1.4426950408889634f;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit % tiles_mn;
         const int m0 = (tile / p.tiles_n) * GEMM_BM;
         const int tn = tile % p.tiles_n;
@@ -693,10 +737,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     bf16* __restrict__ preact = p.preact;
     const float* __restrict__ row_scale = p.row_scale;
     const int act = p.act, out_mode = p.out_mode, use_tma = p.tma_store;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int tile = unit % tiles_mn;
       if ((unit / tiles_mn) * p.kb_per_split >= kb_total) continue;  // empty k-range (row_count)
-      const int m0 = (tile / p.tiles_n) * GEMM_BM;
+      const int m0 = ((tile / p.tiles_n) * NCTA + static_cast<int>(cta_rank)) * GEMM_BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int ncols = min(BN, p.N - n0);
       const long long row = static_cast<long long>(m0) + q * 32 + lane;  // this thread's output row
@@ -876,7 +920,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       // every TMEM read of this accumulator by this warp has completed (tmem_ld_wait): hand it back
       tc_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(mapa_cta(smem_u32(&tempty_bar[acc]), 0));
+        else                mbar_arrive(&tempty_bar[acc]);
+      }
       acc_phase ^= (1u << acc);
       acc = nacc == 2 ? acc ^ 1 : 0;
     }
@@ -885,10 +932,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // nothing of the peer (barriers, operand halves) is referenced past this point
+  else                __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else                tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -934,17 +983,18 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
-template <int BN, int MN, int EPI = 0>
+template <int BN, int MN, int EPI = 0, int CTA2 = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
                        const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<BN, MN, EPI>;
+  auto kern = gemm_tcgen05_kernel<BN, MN, EPI, CTA2>;
+  using Cfg = GemmCfg<BN, EPI, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
-    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    GemmCfg<BN, EPI>::SMEM_BYTES));
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN, EPI>::SMEM_BYTES, stream, ta, tb, tc, tp, p));
+  if (CTA2) FIBER_CUDA(launch_k_pair(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tp, p));
+  else      FIBER_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, tc, tp, p));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -1014,11 +1064,15 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->colsum == nullptr || (a->a_major == 1 && a->out_mode != 0 && a->row_scale == nullptr),
               "colsum needs MN-major operands, an fp32 output and no row_scale");
 
+  // CTA pairs (GemmCfg): K-major, 256-column tiles, whole 256-row pair tiles, no split-K / device row count
+  const int cta2_opt = option_gemm_cta2();
+  const bool cta2 = mn == 0 && BN == 256 && a->m % (2 * GEMM_BM) == 0 && a->row_count == nullptr && splits == 1 &&
+                    ((cta2_opt >> (epi1 ? 1 : 0)) & 1) != 0 && a->k >= ((cta2_opt & 4) ? 256 : 1024);
   CUtensorMap ta, tb;
   if (mn == 0) {
     // A[M, K] (lda), B[N, K] (ldb): inner = K
     if (make_tmap_bf16_2d(&ta, a->a, a->k, a->m, a->lda, GEMM_BK, GEMM_BM)) return -1;
-    if (make_tmap_bf16_2d(&tb, a->b, a->k, a->n, a->ldb, GEMM_BK, BN)) return -1;
+    if (make_tmap_bf16_2d(&tb, a->b, a->k, a->n, a->ldb, GEMM_BK, cta2 ? BN / 2 : BN)) return -1;
   } else {
     // A stored [K, M] (lda), B stored [K, N] (ldb): inner = M / N, 64-wide chunks
     if (make_tmap_bf16_2d(&ta, a->a, a->m, a->k, a->lda, 64, GEMM_BK)) return -1;
@@ -1049,6 +1103,15 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   }
   const int units = tiles * p.splits;
   const int grid = units < sms ? units : sms;
+  if (cta2) {
+    count_gemm_cta2_launch();
+    const int pair_grid = units < (sms & ~1) ? units : (sms & ~1);  // units is even (M % 256 == 0): one CTA per 128-row half
+    if (epi1) {
+      FIBER_CHECK(p.tma_store == 1, "act=%d needs the TMA-store epilogue", a->act);
+      return launch_gemm<256, 0, 1, 1>(ta, tb, tc, tp, p, pair_grid, stream);
+    }
+    return launch_gemm<256, 0, 0, 1>(ta, tb, tc, tp, p, pair_grid, stream);
+  }
   if (epi1) {
     FIBER_CHECK(p.tma_store == 1, "act=%d needs the TMA-store epilogue", a->act);
     return BN == 256 ? launch_gemm<256, 0, 1>(ta, tb, tc, tp, p, grid, stream)

@@ -20,13 +20,17 @@ ACT_GELU_ONEPASS = 5  # out GELU(v), preact buffer receives v: the results of AC
 ACT_RES_PF = 6        # act 0 with a residual (+ bias / scale / row_scale) bit for bit, residual rows prefetched
 ACT_GELU_GRAD_PF = 7  # ACT_GELU_GRAD bit for bit, aux rows prefetched into registers one chunk ahead
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
-# Opt-in (FIBER_GEMM_RES_PREFETCH=1 / set_res_prefetch): residual epilogues through ACT_RES_PF
-RES_PREFETCH = __import__("os").environ.get("FIBER_GEMM_RES_PREFETCH", "0") == "1"
+# Residual epilogues through ACT_RES_PF (bit-identical; coalesced residual loads, two store boxes per warp) when the
+# reduction is short (K <= 512: the epilogue-bound proj / fc2 shapes of Swin stages 0-2, 15-30 % faster in
+# gpurun_out/r2m_gemm_shapes_respf.txt; neutral at K = 2048, which keeps the default epilogue and runs as CTA pairs).
+# FIBER_GEMM_RES_PREFETCH=0 / set_res_prefetch(False) turn it off, =2 applies it at every K.
+RES_PREFETCH = int(__import__("os").environ.get("FIBER_GEMM_RES_PREFETCH", "1"))
 
 
 def set_res_prefetch(on):
+    """0 / False: never; 1 / True: K <= 512 (default); 2: every K."""
     global RES_PREFETCH
-    RES_PREFETCH = bool(on)
+    RES_PREFETCH = int(on)
 
 # Optional in-situ profiling (bench.py): when a list is installed here every GEMM launch is bracketed
 # by CUDA events on the launching stream and (class key, flops, algorithmic bytes, start, stop) recorded.
@@ -103,7 +107,7 @@ def gemm(a, b, *, mn_major=False, bias=None, residual=None, aux=None, preact=Non
     if row_scale is not None:
         _req(row_scale, F32, "row_scale"); args.row_scale = row_scale.data_ptr()
     args.rows_per_scale = rows_per_scale
-    if (RES_PREFETCH and act == ACT_NONE and residual is not None and preact is None and aux is None and not mn_major
+    if (RES_PREFETCH and (k <= 512 or RES_PREFETCH == 2) and act == ACT_NONE and residual is not None and preact is None and aux is None and not mn_major
             and out_mode == OUT_BF16 and m % 128 == 0 and n % 32 == 0):
         act = ACT_RES_PF  # opt-in, bit-identical to the default residual epilogue
     args.act = act

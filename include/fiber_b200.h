@@ -41,6 +41,11 @@ int64_t fiber_launch_count(void);
  * 3-warp one; default 7 or FIBER_ATTN_SMALL.
  * "attn_sk": bit 0 routes the FORWARD of mode-0 attention with at most 64 keys per group and at least 96 queries (i2t) to
  * the tcgen05 + TMA kernel of csrc/attention_sk.cu, bit 2 also shorter query sequences; default 1 or FIBER_ATTN_SK.
+ * "gemm_cta2": bit 0 runs K-major fiber_gemm launches with N > 128, M % 256 == 0, K >= 1024 and no row_count as CTA pairs
+ * (2-CTA clusters, tcgen05 cta_group::2, 256 x 256 pair tiles) for the default epilogues, bit 1 for act 3 .. 7, bit 2 lowers
+ * the K threshold to 256; same results bit for bit (same accumulation order); default 3, FIBER_GEMM_CTA2.
+ * "pdl": 1 launches every kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail);
+ * default 0, FIBER_PDL.
  * "tq_trace" (debug): 1 makes the fourth-generation window backward record an event trace of one CTA (tools/tq_trace.py).
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
  * fiber_get_option returns the value ("winattn_tc_launches" / "attn_sk_launches", read-only: launches of the tcgen05

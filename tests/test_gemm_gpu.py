@@ -210,7 +210,7 @@ def test_gemm_gelu_cache_rejects_unsupported(cuda_dev):
 @pytest.mark.parametrize("with_bias,with_scale,with_rows", [(True, False, False), (True, True, True), (False, False, True),
                                                             (False, True, False)])
 def test_gemm_residual_prefetch_is_bit_identical(cuda_dev, m, n, k, with_bias, with_scale, with_rows):
-    """act 6 (ACT_RES_PF, opt-in) == the default residual epilogue, bit for bit."""
+    """act 6 (ACT_RES_PF, the default at K <= 512) == the plain residual epilogue, bit for bit."""
     from fiber_b200 import kernels as K
     a = _mk((m, k), cuda_dev, 21)
     b = _mk((n, k), cuda_dev, 22, k ** -0.5)
@@ -224,12 +224,14 @@ def test_gemm_residual_prefetch_is_bit_identical(cuda_dev, m, n, k, with_bias, w
         rps = 128
         kw["row_scale"] = torch.rand(m // rps, device=cuda_dev) + 0.5
         kw["rows_per_scale"] = rps
-    ref = K.gemm(a, b, **kw)
-    K.set_res_prefetch(True)
+    old = K.RES_PREFETCH
     try:
+        K.set_res_prefetch(0)
+        ref = K.gemm(a, b, **kw)
+        K.set_res_prefetch(2)
         out = K.gemm(a, b, **kw)
     finally:
-        K.set_res_prefetch(False)
+        K.set_res_prefetch(old)
     assert torch.equal(out, ref)
 
 
@@ -258,3 +260,46 @@ def test_gemm_device_row_count(cuda_dev, count):
     ref_w = dy[:kedge].float().t() @ x[:kedge].float()
     torch.testing.assert_close(dw, ref_w, rtol=2e-2, atol=2e-2 * max(1.0, kedge ** 0.5))
     torch.testing.assert_close(db, dy[:kedge].float().sum(0), rtol=2e-2, atol=2e-2 * max(1.0, kedge ** 0.5))
+
+
+PAIR_SHAPES = [(256, 256, 256), (512, 384, 512), (2560, 768, 768), (2560, 3072, 768), (36864, 1536, 512),
+               (36864, 512, 2048), (9216, 4096, 1024), (147456, 512, 512), (768, 264, 320)]
+
+
+@pytest.mark.parametrize("m,n,k", PAIR_SHAPES)
+def test_gemm_cta_pairs(cuda_dev, m, n, k):
+    """fiber_set_option("gemm_cta2", 7): the same GEMMs as CTA pairs (2-CTA clusters, tcgen05.mma.cta_group::2, 256 x 256 pair
+    tiles, half of the B tile per CTA) — plain, bias + residual + scale, and the two-box GELU epilogues — against the
+    single-CTA kernel (bit for bit: same per-element accumulation order) and the fp32 reference."""
+    from fiber_b200 import kernels as K, lib
+    a = _mk((m, k), cuda_dev, 21)
+    b = _mk((n, k), cuda_dev, 22, k ** -0.5)
+    bias = torch.randn(n, device=cuda_dev)
+    res = _mk((m, n), cuda_dev, 23)
+    aux = _mk((m, n), cuda_dev, 24)
+    sc = torch.tensor([0.75], device=cuda_dev)
+
+    def run_all():
+        outs = [K.gemm(a, b), K.gemm(a, b, bias=bias, residual=res, scale=sc)]
+        if n % 32 == 0 and m % 128 == 0:
+            pre = torch.empty((m, n), device=cuda_dev, dtype=torch.bfloat16)
+            outs.append(K.gemm(a, b, bias=bias, preact=pre, act=K.ACT_GELU_CACHE))
+            outs.append(pre)
+            outs.append(K.gemm(a, b, aux=aux, act=K.ACT_MUL_AUX))
+            outs.append(K.gemm(a, b, bias=bias, residual=res, act=K.ACT_RES_PF))
+        return outs
+
+    lib.set_option("gemm_cta2", 0)
+    base = run_all()
+    try:
+        lib.set_option("gemm_cta2", 7)  # bit 2: also below the default K >= 1024 threshold
+        n0 = lib.get_option("gemm_cta2_launches")
+        pair = run_all()
+        torch.cuda.synchronize()
+        assert lib.get_option("gemm_cta2_launches") - n0 == (len(pair) - 1 if len(pair) > 2 else 2)
+    finally:
+        lib.set_option("gemm_cta2", -1)
+    ref = a.float() @ b.float().t()
+    torch.testing.assert_close(pair[0].float(), ref, rtol=RTOL, atol=ATOL)
+    for x, y in zip(base, pair):
+        assert torch.equal(x, y)
