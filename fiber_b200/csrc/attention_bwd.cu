@@ -427,6 +427,10 @@ bool win_attn_tc_supported(const AttnParams& p, int hd, bool bwd);           // 
 int launch_win_tc_bwd(const AttnParams& p, float* D, cudaStream_t stream);   // window_attn_tc.cu
 int option_winattn_tc();                                                     // capi.cu
 int option_attn_small();                                                     // capi.cu
+bool attn_sk_bwd_supported(const AttnParams& p, int hd);                     // attention_sk.cu
+int launch_attn_sk_bwd(const AttnParams& p, int hd, cudaStream_t stream);    // attention_sk.cu
+int option_attn_sk();                                                        // capi.cu
+void count_attn_sk_launch();
 
 int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
@@ -438,6 +442,11 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
       return launch_win_tc_bwd(p, d_scratch, stream);  // opt-in tcgen05 generation
     if (win_attn_supported(p, hd) && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
+  }
+  // tcgen05 + TMA backward for at most 64 keys per group ("attn_sk" bit 1: >= 96 queries (i2t); bit 3: every query count)
+  if (attn_sk_bwd_supported(p, hd) && (((option_attn_sk() & 2) && p.Lq >= 96) || (option_attn_sk() & 8))) {
+    count_attn_sk_launch();
+    return launch_attn_sk_bwd(p, hd, stream);
   }
   // opt-in: at most 48 queries and keys (RoBERTa self-attention at 40 tokens) on 3-warp CTAs, four per SM
   if (hd == 64 && p.Lq <= 48 && p.Lk <= 48 && (option_attn_small() & 1)) return launch_bwd<64, false, 3, 48>(p, stream);

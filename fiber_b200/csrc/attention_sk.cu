@@ -301,6 +301,314 @@ __global__ void __launch_bounds__(SK_THREADS, 2) attn_sk_fwd_kernel(const AttnPa
   }
 }
 
+// =====================================================================================================================
+// Backward.  Work item = (group, head); its query tiles of 128 rows are walked in order by ONE CTA, so dK / dV accumulate
+// in TMEM across the tiles and leave once per item (no atomics).  Per tile: Q, dO, O [128][hd] and K, V [64][hd] arrive as
+// five TMA boxes; S = Q K^T and dP = dO V^T are two tcgen05.mma chains (M = 128, N = 64) into TMEM; thread = query row
+// computes D = rowsum(dO * O) from the staged tiles, P = exp(S * scale + mask - lse) (dropout regenerated from the
+// forward's counter hash), dS = P (dP - D), and writes bf16 P (after dropout) and dS into SWIZZLE_128B chunks; three more
+// chains follow: dV += P^T dO, dK += dS^T Q (M = 128 key rows of which <= 64 are real: accumulator rows are independent,
+// so the operand's upper 64 "keys" simply read whatever follows the chunk in shared memory and their rows are never
+// drained; N = hd, K = 128 queries, MN-major operands straight from the row-major tiles) and dQ = dS K (M = 128, N = hd,
+// K = 64).  Rows of the tile past the group's last query (next group's rows, finite) get P = dS = 0.
+// hd = 32: 96 KB of shared memory and 256 TMEM columns, two CTAs per SM overlap each other's bubbles; hd = 64: one CTA.
+// =====================================================================================================================
+template <int HD>
+struct SkBwdCfg {
+  static constexpr int T_BYTES = 128 * HD * 2, KV_BYTES = SK_KEYS * HD * 2;
+  static constexpr int STAGE_BYTES = 3 * T_BYTES + 2 * KV_BYTES;  // Q, dO, O, K, V
+  static constexpr int STAGES = 2;
+  static constexpr int CHUNK = 128 * 128;                          // [128 query rows][64 keys] bf16, SWIZZLE_128B
+  // dS, P, then the stages: the MN-major P^T / dS^T operands span two chunks (M = 128), the second being the next
+  // 16 KB of shared memory (P for dS, the first stage for P) — finite or not, those accumulator rows are discarded
+  static constexpr int OFF_DS = 0, OFF_P = CHUNK, OFF_STAGES = 2 * CHUNK;
+  static constexpr int OFF_MSK = OFF_STAGES + STAGES * STAGE_BYTES;  // [2][64] fp32 key mask, log2 domain
+  static constexpr int OFF_BARS = OFF_MSK + 2 * SK_KEYS * 4;
+  static constexpr int SMEM = 1024 + OFF_BARS + 16 * 8;
+  static constexpr uint32_t S_COL = 0, DP_COL = 64, DQ_COL = 128, DV_COL = 128 + HD, DK_COL = 128 + 2 * HD;
+  static constexpr uint32_t TMEM_COLS = HD == 32 ? 256 : 512;
+  static constexpr int CTAS_PER_SM = HD == 32 ? 2 : 1;
+};
+static_assert(2 * (SkBwdCfg<32>::SMEM + 1024) <= 227 * 1024, "two hd = 32 CTAs per SM");
+static_assert(SkBwdCfg<64>::SMEM <= 227 * 1024, "backward shared memory");
+
+// D of one tile row from the staged dO / O tiles (HD * 2-byte swizzled rows)
+template <int HD>
+__device__ __forceinline__ float sk_row_dot(const uint8_t* sdO, const uint8_t* sO, int row) {
+  float acc = 0.f;
+#pragma unroll
+  for (int pc = 0; pc < HD / 8; ++pc) {
+    const uint32_t off = HD == 32 ? sw64_off(row, pc) : sw128_off(row, pc);
+    const uint4 a = *reinterpret_cast<const uint4*>(sdO + off);
+    const uint4 b = *reinterpret_cast<const uint4*>(sO + off);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = unpack_bf16(aw[e]), fb = unpack_bf16(bw[e]);
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  return acc;
+}
+
+template <int HD, bool DROPOUT>
+__global__ void __launch_bounds__(SK_THREADS, SkBwdCfg<HD>::CTAS_PER_SM) attn_sk_bwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmdO,
+                                                                   const __grid_constant__ CUtensorMap tmO,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV, int ntiles,
+                                                                   int n_items) {
+  using Cfg = SkBwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem + Cfg::OFF_P;
+  uint8_t* sdS = smem + Cfg::OFF_DS;
+  float* sMsk = reinterpret_cast<float*>(smem + Cfg::OFF_MSK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+  // timeout tags: 401 full, 402 stage_free, 403 s_full, 404 sdp_empty, 405 pds_ready, 406 out_full, 407 acc_empty
+  uint64_t* full = bars;            // [2] TMA boxes of a stage have landed                (expect_tx)
+  uint64_t* stage_free = bars + 2;  // [2] stage may be overwritten                        (tcgen05.commit)
+  uint64_t* s_full = bars + 4;      //     S and dP written                                (tcgen05.commit)
+  uint64_t* sdp_empty = bars + 5;   //     S and dP read                                   (4 element-wise warps)
+  uint64_t* pds_ready = bars + 6;   //     P and dS in smem                                (4 element-wise warps)
+  uint64_t* out_full = bars + 7;    //     dQ (and dV / dK so far) written, P / dS consumed (tcgen05.commit)
+  uint64_t* acc_empty = bars + 8;   //     dQ (and, after an item's last tile, dV / dK) drained (4 element-wise warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n_my = n_my_items * ntiles;  // units = (item, tile), tiles of an item consecutive
+  const float scale2 = p.scale * SK_LOG2E;
+
+  pdl_trigger();
+  if (warp == SK_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&stage_free[s], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(sdp_empty, 4);
+      mbar_init(pds_ready, 4);
+      mbar_init(out_full, 1);
+      mbar_init(acc_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp == SK_WARP_LD && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // nothing above touched global memory
+
+  if (warp < 4) {
+    // ================= element-wise warps: thread = query row of the tile (and key row of the dV / dK drain) =================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint8_t* p_row = sP + row * 128;
+    uint8_t* ds_row = sdS + row * 128;
+    const int xr = row & 7;
+    const float keep_inv = DROPOUT ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+#pragma unroll 1
+    for (int u = 0; u < n_my; ++u) {
+      const int item = blockIdx.x + (u / ntiles) * gridDim.x, t = u % ntiles;
+      const int h = item % p.nH, g = item / p.nH;
+      const int s = u & 1;
+      const int qi = t * 128 + row;
+      const bool valid = qi < p.Lq;
+      const uint8_t* stage = smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES;
+      if (row < SK_KEYS) {
+        float mk = -1e30f;
+        if (row < p.Lk) mk = p.key_mask ? p.key_mask[static_cast<long long>(g) * p.Lk + row] * SK_LOG2E : 0.f;
+        sMsk[s * SK_KEYS + row] = mk;
+      }
+      const float nlse2 = valid ? -p.lse[(static_cast<long long>(g) * p.nH + h) * p.Lq + qi] * SK_LOG2E : 0.f;
+      sk_wait(&full[s], (u >> 1) & 1, 401, u);
+      const float D = sk_row_dot<HD>(stage + Cfg::T_BYTES, stage + 2 * Cfg::T_BYTES, row);
+      sk_bar_sync(1, 128);  // the mask row of this stage is complete
+
+      sk_wait(s_full, u & 1, 403, u);
+      tc_fence_after();
+      const unsigned long long didx0 = DROPOUT ? ((static_cast<unsigned long long>(g) * p.nH + h) * p.Lq + qi) * p.Lk : 0ull;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {  // 32 key columns at a time
+        uint32_t sv[32], dv[32];
+        tmem_ld32(lane_addr + Cfg::S_COL + hf * 32, sv);
+        tmem_ld32(lane_addr + Cfg::DP_COL + hf * 32, dv);
+        tmem_ld_wait();
+        if (hf == 1) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(sdp_empty);  // S / dP may be overwritten by the next tile's MMAs
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float pd[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = hf * 32 + c8 * 8 + e;
+            const float x = fmaf(__uint_as_float(sv[c8 * 8 + e]), scale2, sMsk[s * SK_KEYS + j]) + nlse2;
+            const float pr = valid ? ex2_approx(x) : 0.f;
+            float dpv = __uint_as_float(dv[c8 * 8 + e]);
+            pd[e] = pr;
+            if (DROPOUT) {
+              const bool keep = dropout_keep(p.seed, didx0 + j, p.drop_p);
+              pd[e] = keep ? pr * keep_inv : 0.f;
+              dpv = keep ? dpv * keep_inv : 0.f;
+            }
+            ds[e] = pr * (dpv - D);
+          }
+          uint4 o, d;
+          o.x = pack_bf16(pd[0], pd[1]); o.y = pack_bf16(pd[2], pd[3]);
+          o.z = pack_bf16(pd[4], pd[5]); o.w = pack_bf16(pd[6], pd[7]);
+          d.x = pack_bf16(ds[0], ds[1]); d.y = pack_bf16(ds[2], ds[3]);
+          d.z = pack_bf16(ds[4], ds[5]); d.w = pack_bf16(ds[6], ds[7]);
+          const int piece = hf * 4 + c8;
+          *reinterpret_cast<uint4*>(p_row + ((piece ^ xr) << 4)) = o;
+          *reinterpret_cast<uint4*>(ds_row + ((piece ^ xr) << 4)) = d;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+
+      // drain dQ of this tile (and dV / dK of the item after its last tile)
+      sk_wait(out_full, u & 1, 406, u);
+      tc_fence_after();
+      {
+        uint32_t a[HD];
+        tmem_ld32(lane_addr + Cfg::DQ_COL, reinterpret_cast<uint32_t(&)[32]>(a[0]));
+        if constexpr (HD == 64) tmem_ld32(lane_addr + Cfg::DQ_COL + 32, reinterpret_cast<uint32_t(&)[32]>(a[32]));
+        tmem_ld_wait();
+        if (valid) {
+          bf16* dst = p.dq + (static_cast<long long>(g) * p.Lq + qi) * p.lddq + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD; c += 8) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(a[c]) * p.scale, __uint_as_float(a[c + 1]) * p.scale);
+            v.y = pack_bf16(__uint_as_float(a[c + 2]) * p.scale, __uint_as_float(a[c + 3]) * p.scale);
+            v.z = pack_bf16(__uint_as_float(a[c + 4]) * p.scale, __uint_as_float(a[c + 5]) * p.scale);
+            v.w = pack_bf16(__uint_as_float(a[c + 6]) * p.scale, __uint_as_float(a[c + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dst + c) = v;
+          }
+        }
+      }
+      if (t == ntiles - 1 && warp < 2) {  // accumulator lanes = key rows 0..63
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          uint32_t a[HD];
+          tmem_ld32(lane_addr + (w ? Cfg::DK_COL : Cfg::DV_COL), reinterpret_cast<uint32_t(&)[32]>(a[0]));
+          if constexpr (HD == 64) tmem_ld32(lane_addr + (w ? Cfg::DK_COL : Cfg::DV_COL) + 32, reinterpret_cast<uint32_t(&)[32]>(a[32]));
+          tmem_ld_wait();
+          if (row < p.Lk) {
+            const float sc = w ? p.scale : 1.0f;
+            bf16* dst = (w ? p.dk + (static_cast<long long>(g) * p.Lk + row) * p.lddk
+                           : p.dv + (static_cast<long long>(g) * p.Lk + row) * p.lddv) + h * HD;
+#pragma unroll
+            for (int c = 0; c < HD; c += 8) {
+              uint4 v;
+              v.x = pack_bf16(__uint_as_float(a[c]) * sc, __uint_as_float(a[c + 1]) * sc);
+              v.y = pack_bf16(__uint_as_float(a[c + 2]) * sc, __uint_as_float(a[c + 3]) * sc);
+              v.z = pack_bf16(__uint_as_float(a[c + 4]) * sc, __uint_as_float(a[c + 5]) * sc);
+              v.w = pack_bf16(__uint_as_float(a[c + 6]) * sc, __uint_as_float(a[c + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + c) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  } else if (warp == SK_WARP_MMA) {
+    // ================= tcgen05.mma issuer =================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, SK_KEYS, 0, 0);  // S = Q K^T, dP = dO V^T
+    constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, 1, 1);      // dV = P^T dO, dK = dS^T Q (MN x MN)
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);       // dQ = dS K (K-major x MN-major)
+    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+    auto issue_scores = [&](int u) {
+      const int s = u & 1;
+      sk_wait(&full[s], (u >> 1) & 1, 401, u);
+      sk_wait(sdp_empty, (u & 1) ^ 1, 404, u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES), do_addr = q_addr + Cfg::T_BYTES;
+        const uint32_t k_addr = q_addr + 3 * Cfg::T_BYTES, v_addr = k_addr + Cfg::KV_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(tmem_base + Cfg::S_COL, sk_desc_kmajor<HD>(q_addr, ks), sk_desc_kmajor<HD>(k_addr, ks), idesc_s, ks);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(tmem_base + Cfg::DP_COL, sk_desc_kmajor<HD>(do_addr, ks), sk_desc_kmajor<HD>(v_addr, ks), idesc_s, ks);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) issue_scores(0);
+#pragma unroll 1
+    for (int u = 0; u < n_my; ++u) {
+      const int s = u & 1, t = u % ntiles;
+      sk_wait(pds_ready, u & 1, 405, u);
+      sk_wait(acc_empty, (u & 1) ^ 1, 407, u);  // the previous tile's dQ (and a finished item's dV / dK) are drained
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES), do_addr = q_addr + Cfg::T_BYTES;
+        const uint32_t k_addr = q_addr + 3 * Cfg::T_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 16 query rows per step
+          const uint32_t acc = (t > 0 || kk > 0) ? 1u : 0u;
+          umma_f16_ss(tmem_base + Cfg::DV_COL, umma_desc(p_addr + kk * 2048, Cfg::CHUNK, 1024, LAYOUT_SW128),
+                      sk_desc_mnmajor<HD>(do_addr, kk), idesc_kv, acc);
+          umma_f16_ss(tmem_base + Cfg::DK_COL, umma_desc(ds_addr + kk * 2048, Cfg::CHUNK, 1024, LAYOUT_SW128),
+                      sk_desc_mnmajor<HD>(q_addr, kk), idesc_kv, acc);
+        }
+#pragma unroll
+        for (int kk = 0; kk < SK_KEYS / 16; ++kk)  // 16 keys per step
+          umma_f16_ss(tmem_base + Cfg::DQ_COL, umma_desc_sw128(ds_addr + kk * 32, 16, 1024), sk_desc_mnmajor<HD>(k_addr, kk),
+                      idesc_q, kk);
+        umma_commit(out_full);
+        umma_commit(&stage_free[s]);
+      }
+      __syncwarp();
+      if (u + 1 < n_my) issue_scores(u + 1);
+    }
+  } else {
+    // ================= TMA producer =================
+    if (lane == 0) {
+#pragma unroll 1
+      for (int u = 0; u < n_my; ++u) {
+        const int item = blockIdx.x + (u / ntiles) * gridDim.x, t = u % ntiles;
+        const int h = item % p.nH, g = item / p.nH;
+        const int s = u & 1;
+        if (u >= 2) sk_wait(&stage_free[s], ((u >> 1) - 1) & 1, 402, u);
+        uint8_t* st = smem + Cfg::OFF_STAGES + s * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_2d(st, &tmQ, &full[s], h * HD, g * p.Lq + t * 128);
+        tma_load_2d(st + Cfg::T_BYTES, &tmdO, &full[s], h * HD, g * p.Lq + t * 128);
+        tma_load_2d(st + 2 * Cfg::T_BYTES, &tmO, &full[s], h * HD, g * p.Lq + t * 128);
+        tma_load_2d(st + 3 * Cfg::T_BYTES, &tmK, &full[s], h * HD, g * p.Lk);
+        tma_load_2d(st + 3 * Cfg::T_BYTES + Cfg::KV_BYTES, &tmV, &full[s], h * HD, g * p.Lk);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SK_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*SkEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -358,6 +666,34 @@ int launch_sk_fwd_t(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <int HD, bool DROPOUT>
+int launch_sk_bwd_t(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = SkBwdCfg<HD>;
+  auto kern = attn_sk_bwd_kernel<HD, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tq, tdo, to, tk, tv;
+  const int C = p.nH * HD;
+  const long long qrows = static_cast<long long>(p.G) * p.Lq, krows = static_cast<long long>(p.G) * p.Lk;
+  if (sk_tmap(&tq, p.q, p.ldq, qrows, C, HD, 128) || sk_tmap(&tdo, p.d_o, p.lddo, qrows, C, HD, 128) ||
+      sk_tmap(&to, p.o, p.ldo, qrows, C, HD, 128) || sk_tmap(&tk, p.k, p.ldk, krows, C, HD, SK_KEYS) ||
+      sk_tmap(&tv, p.v, p.ldv, krows, C, HD, SK_KEYS))
+    return -1;
+  const int ntiles = (p.Lq + 127) / 128;
+  const long long n_items = static_cast<long long>(p.G) * p.nH;
+  FIBER_CHECK(n_items * ntiles < (1ll << 31), "too many attention work items");
+  const long long slots = static_cast<long long>(Cfg::CTAS_PER_SM) * num_sms();
+  const int grid = static_cast<int>(n_items < slots ? n_items : slots);
+  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(SK_THREADS), Cfg::SMEM, stream, p, tq, tdo, to, tk, tv, ntiles,
+                      static_cast<int>(n_items)));
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace
 
 static bool sk_aligned16(const void* ptr, long long ld) {
@@ -368,6 +704,17 @@ static bool sk_aligned16(const void* ptr, long long ld) {
 bool attn_sk_supported(const AttnParams& p, int hd) {
   return p.mode == 0 && (hd == 32 || hd == 64) && p.Lk <= SK_KEYS && sk_aligned16(p.q, p.ldq) && sk_aligned16(p.k, p.ldk) &&
          sk_aligned16(p.v, p.ldv) && sk_aligned16(p.o, p.ldo);
+}
+
+// backward: additionally d_o / dq / dk / dv rows 16-byte addressable
+bool attn_sk_bwd_supported(const AttnParams& p, int hd) {
+  return attn_sk_supported(p, hd) && p.d_o && p.dq && p.dk && p.dv && p.lse && sk_aligned16(p.d_o, p.lddo) &&
+         sk_aligned16(p.dq, p.lddq) && sk_aligned16(p.dk, p.lddk) && sk_aligned16(p.dv, p.lddv);
+}
+
+int launch_attn_sk_bwd(const AttnParams& p, int hd, cudaStream_t stream) {
+  if (hd == 32) return p.drop_p > 0.f ? launch_sk_bwd_t<32, true>(p, stream) : launch_sk_bwd_t<32, false>(p, stream);
+  return p.drop_p > 0.f ? launch_sk_bwd_t<64, true>(p, stream) : launch_sk_bwd_t<64, false>(p, stream);
 }
 
 int launch_attn_sk_fwd(const AttnParams& p, int hd, cudaStream_t stream) {

@@ -41,15 +41,16 @@ int option_attn_small() {
   }
   return v;
 }
-// "attn_sk": bit 0 routes the forward of plain attention with at most 64 keys per group and at least 96 queries (i2t) to the
-// tcgen05 + TMA kernel of attention_sk.cu, bit 2 also short query sequences (RoBERTa self-attention).  Default 1
-// (validated on B200 in round 2), or FIBER_ATTN_SK.
+// "attn_sk": bit 0 routes the forward, bit 1 the backward of plain attention with at most 64 keys per group and at least 96
+// queries (i2t) to the tcgen05 + TMA kernels of attention_sk.cu; bits 2 / 3 also route short query sequences (RoBERTa
+// self-attention: 40 of 128 tile rows used, slower than the mma.sync kernels).  Default 3 (validated on B200 in round 2:
+// i2t stage 2 forward 0.255 -> 0.158 ms, backward 0.407 -> 0.317 ms), or FIBER_ATTN_SK.
 static std::atomic<int> g_attn_sk{-1};
 int option_attn_sk() {
   int v = g_attn_sk.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_ATTN_SK");
-    v = e ? (atoi(e) & 7) : 1;
+    v = e ? (atoi(e) & 15) : 3;
     g_attn_sk.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -198,7 +199,7 @@ int fiber_set_option(const char* name, int32_t value) {
     return 0;
   }
   if (name && strcmp(name, "attn_sk") == 0) {
-    fiber::g_attn_sk.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
+    fiber::g_attn_sk.store(value < 0 ? -1 : (value & 15), std::memory_order_relaxed);
     return 0;
   }
   if (name && strcmp(name, "gemm_cta2") == 0) {

@@ -159,7 +159,7 @@ SK_CASES = [(3, 12, 64, 40, 40, True), (2, 12, 64, 50, 50, True), (4, 12, 64, 33
             (5, 16, 32, 576, 64, False), (3, 12, 64, 130, 64, True), (2, 12, 64, 40, 576, False), (3, 12, 64, 33, 100, True)]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 5], ids=["mmasync", "sk_long", "sk_all"])
+@pytest.mark.parametrize("mode", [0, 1, 5, 3, 15, 10], ids=["mmasync", "sk_long", "sk_all", "sk_long_fb", "sk_all_fb", "sk_bwd_only"])
 @pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", SK_CASES)
 def test_plain_attention_tcgen05(cuda_dev, B, nh, hd, Lq, Lk, masked, mode):
     from fiber_b200 import lib
@@ -171,8 +171,38 @@ def test_plain_attention_tcgen05(cuda_dev, B, nh, hd, Lq, Lk, masked, mode):
     finally:
         lib.set_option("attn_sk", -1)
     launched = lib.get_option("attn_sk_launches") - before
-    routed = Lk <= 64 and ((mode & 1 and Lq >= 96) or mode & 4)
-    assert launched == (1 if routed else 0)
+    fwd = Lk <= 64 and ((mode & 1 and Lq >= 96) or mode & 4)
+    bwd = Lk <= 64 and ((mode & 2 and Lq >= 96) or mode & 8)
+    assert launched == int(bool(fwd)) + int(bool(bwd))
+
+
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk", [(3, 12, 64, 40, 40), (2, 12, 64, 130, 50), (2, 16, 32, 300, 40)])
+def test_plain_attention_tcgen05_backward_dropout_matches_mma_sync(cuda_dev, B, nh, hd, Lq, Lk):
+    """The tcgen05 backward regenerates the forward's dropout mask from the same counter hash: with the same forward
+    output it must give the mma.sync backward's gradients (to bf16 rounding of P / dS)."""
+    from fiber_b200 import kernels as K, lib
+    C = nh * hd
+    q = _rand((B * Lq, C), cuda_dev, 21)
+    kv = _rand((B * Lk, 2 * C), cuda_dev, 22)
+    d_o = _rand((B * Lq, C), cuda_dev, 23)
+    mask = torch.zeros(B, Lk, device=cuda_dev)
+    mask[1, Lk - 5:] = -10000.0
+    kw = dict(groups=B, lq=Lq, lk=Lk, key_mask=mask, drop_p=0.2, seed=4242)
+    scale = hd ** -0.5
+    lib.set_option("attn_sk", 0)
+    try:
+        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, scale, **kw)
+        grads = []
+        for mode in (0, 10):
+            lib.set_option("attn_sk", mode)
+            dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+            K.attn_bwd(d_o, q, kv[:, :C], kv[:, C:], o, lse, nh, hd, scale, dq, dkv[:, :C], dkv[:, C:], **kw)
+            grads.append((dq, dkv))
+    finally:
+        lib.set_option("attn_sk", -1)
+    (dq0, dkv0), (dq1, dkv1) = grads
+    _close(dq1, dq0.float(), 2e-2, "dq with dropout")
+    _close(dkv1, dkv0.float(), 2e-2, "dk / dv with dropout")
 
 
 def test_plain_attention_tcgen05_dropout_matches_mma_sync(cuda_dev):
