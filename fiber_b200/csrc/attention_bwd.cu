@@ -429,6 +429,7 @@ int option_winattn_tc();                                                     // 
 int option_attn_small();                                                     // capi.cu
 bool attn_sk_bwd_supported(const AttnParams& p, int hd);                     // attention_sk.cu
 int launch_attn_sk_bwd(const AttnParams& p, int hd, cudaStream_t stream);    // attention_sk.cu
+bool attn_pk_shape(const AttnParams& p);                                     // attention_sk.cu
 int option_attn_sk();                                                        // capi.cu
 void count_attn_sk_launch();
 
@@ -443,8 +444,11 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
     if (win_attn_supported(p, hd) && d_scratch != nullptr) return launch_win_bwd(p, d_scratch, stream);
     return launch_bwd<32, true>(p, stream);
   }
-  // tcgen05 + TMA backward for at most 64 keys per group ("attn_sk" bit 1: >= 96 queries (i2t); bit 3: every query count)
-  if (attn_sk_bwd_supported(p, hd) && (((option_attn_sk() & 2) && p.Lq >= 96) || (option_attn_sk() & 8))) {
+  // tcgen05 + TMA backward for at most 64 keys per group ("attn_sk" bit 1: >= 96 queries (i2t); bit 3: packed
+  // self-attention shapes; bit 4: every other short query sequence, see attn_fwd_dispatch)
+  const int sk_opt = option_attn_sk();
+  if (attn_sk_bwd_supported(p, hd) &&
+      (((sk_opt & 2) && p.Lq >= 96) || ((sk_opt & 8) && p.Lq < 96 && (attn_pk_shape(p) || (sk_opt & 16))))) {
     count_attn_sk_launch();
     return launch_attn_sk_bwd(p, hd, stream);
   }

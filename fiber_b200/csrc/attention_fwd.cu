@@ -282,15 +282,19 @@ int launch_win_tc_fwd(const AttnParams& p, cudaStream_t stream);    // window_at
 int option_winattn_tc();                                            // capi.cu
 bool attn_sk_supported(const AttnParams& p, int hd);                // attention_sk.cu
 int launch_attn_sk_fwd(const AttnParams& p, int hd, cudaStream_t stream);
+bool attn_pk_shape(const AttnParams& p);                            // attention_sk.cu
 int option_attn_sk();                                               // capi.cu
 void count_attn_sk_launch();
 
 int attn_fwd_dispatch(const AttnParams& p, int hd, cudaStream_t stream) {
   if (attn_check(p, hd)) return -1;
   // tcgen05 + TMA forward for at most 64 keys per group.  Bit 0: where a 128-query tile is mostly full (image -> text:
-  // 576 / 144 / 1296 queries per sample; measured 0.255 -> 0.158 ms at stage 2) — the default; bit 2 also routes short
-  // query sequences (RoBERTa self-attention, 40 of 128 tile rows used: 0.041 -> 0.062 ms, slower than mma.sync)
-  if (attn_sk_supported(p, hd) && (((option_attn_sk() & 1) && p.Lq >= 96) || (option_attn_sk() & 4))) {
+  // 576 / 144 / 1296 queries per sample; measured 0.255 -> 0.158 ms at stage 2); bit 2: self-attention shapes that pack
+  // two or three samples into a tile (RoBERTa at 40 / 48 / 64 tokens: as fast as mma.sync forward, 20 % faster backward);
+  // bit 4 (off by default): every other short query sequence, unpacked (40 of 128 tile rows used: slower than mma.sync)
+  const int sk_opt = option_attn_sk();
+  if (attn_sk_supported(p, hd) &&
+      (((sk_opt & 1) && p.Lq >= 96) || ((sk_opt & 4) && p.Lq < 96 && (attn_pk_shape(p) || (sk_opt & 16))))) {
     count_attn_sk_launch();
     return launch_attn_sk_fwd(p, hd, stream);
   }

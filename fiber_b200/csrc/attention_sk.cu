@@ -49,6 +49,13 @@ __device__ __forceinline__ float sk_lg2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 8 columns (the packed kernels read their group's columns from an 8-aligned, not 32-aligned, base)
+__device__ __forceinline__ void sk_tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void sk_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -609,6 +616,541 @@ __global__ void __launch_bounds__(SK_THREADS, SkBwdCfg<HD>::CTAS_PER_SM) attn_sk
   }
 }
 
+// =====================================================================================================================
+// Packed self-attention (RoBERTa self-attention, roberta.py:256-326: Lq = Lk = L, 32 <= L <= 64 tokens, L % 8 == 0).  A 128-row
+// tile holds gpt = 128 / L whole groups (samples): rows [g0 L, g0 L + 128) of the row-major activations are ONE TMA box
+// for Q and one each for K and V, S = Q K^T is a 128 x 128 chain of which row r only reads the L columns of its own
+// group (block diagonal: gi = r / L, columns [gi L, gi L + L)), P is written block-diagonally into two SWIZZLE_128B
+// chunks that were zeroed once (a row always writes the same column range), and O = P V (K = 128 keys) needs no
+// masking: the off-diagonal blocks are zero.  120 of 128 tile rows carry work at L = 40 (40 of 128 unpacked).
+// tcgen05.ld is warp-collective (one column address per warp) and 32 <= L means a warp's 32 rows touch at most two
+// groups: the warp loads the column ranges of both and every thread selects its own.
+// The backward is the same construction on the sk backward: all 128 key rows of dV / dK are real, every tile is its
+// own item.
+// =====================================================================================================================
+template <int HD>
+struct PkCfg {
+  static constexpr int T_BYTES = 128 * HD * 2;
+  static constexpr int CHUNK = 128 * 128;  // [128 rows][64 keys] bf16, SWIZZLE_128B
+  // forward: Q, K, V per stage; backward: Q, dO, O, K, V
+  static constexpr int F_STAGE = 3 * T_BYTES, B_STAGE = 5 * T_BYTES;
+  static constexpr int F_OFF_P = 2 * F_STAGE, F_OFF_MSK = F_OFF_P + 2 * CHUNK, F_OFF_BARS = F_OFF_MSK + 2 * 128 * 4;
+  static constexpr int F_SMEM = 1024 + F_OFF_BARS + 16 * 8;
+  static constexpr int B_OFF_DS = 0, B_OFF_P = 2 * CHUNK, B_OFF_STAGES = 4 * CHUNK;
+  static constexpr int B_OFF_MSK = B_OFF_STAGES + 2 * B_STAGE, B_OFF_BARS = B_OFF_MSK + 2 * 128 * 4;
+  static constexpr int B_SMEM = 1024 + B_OFF_BARS + 16 * 8;
+  static constexpr uint32_t FS_COL0 = 0, FS_COL1 = 128, FO_COL0 = 256, FO_COL1 = 256 + HD;
+  static constexpr uint32_t BS_COL = 0, BDP_COL = 128, BDQ_COL = 256, BDV_COL = 256 + HD, BDK_COL = 256 + 2 * HD;
+};
+static_assert(PkCfg<64>::B_SMEM <= 227 * 1024 && PkCfg<64>::F_SMEM <= 227 * 1024, "packed attention shared memory");
+
+struct PkGeo {
+  int L, gpt, n_tiles;  // tokens per group, groups per 128-row tile, tiles per head
+};
+
+// mask of tile key column c (group g0 + c / L, key c % L) in the log2 domain; columns of no group are switched off
+__device__ __forceinline__ float pk_mask(const AttnParams& p, const PkGeo& geo, int g0, int c) {
+  const int gi = c / geo.L, j = c - gi * geo.L, g = g0 + gi;
+  if (gi >= geo.gpt || g >= p.G) return -1e30f;
+  return p.key_mask ? p.key_mask[static_cast<long long>(g) * geo.L + j] * SK_LOG2E : 0.f;
+}
+
+template <int HD, bool DROPOUT>
+__global__ void __launch_bounds__(SK_THREADS, 1) attn_pk_fwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV, const PkGeo geo,
+                                                                   int n_items) {
+  using Cfg = PkCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem + Cfg::F_OFF_P;
+  float* sMsk = reinterpret_cast<float*>(smem + Cfg::F_OFF_MSK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::F_OFF_BARS);
+  // timeout tags: 501 s_full, 502 o_full, 503 full, 504 s_empty, 505 p_ready, 506 stage_free, 507 o_empty
+  uint64_t* full = bars;
+  uint64_t* stage_free = bars + 2;
+  uint64_t* s_full = bars + 4;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_ready = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint64_t* o_empty = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const float scale2 = p.scale * SK_LOG2E;
+  const int L = geo.L;
+
+  pdl_trigger();
+  if (warp == SK_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&stage_free[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&s_empty[s], 4);
+        mbar_init(&o_full[s], 1);
+        mbar_init(&o_empty[s], 4);
+      }
+      mbar_init(p_ready, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp == SK_WARP_LD && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  for (int i = tid; i < 2 * Cfg::CHUNK / 16; i += SK_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int gi = row / L, qi = row - gi * L;
+    const int kc0 = gi < geo.gpt ? gi * L : 0;  // first key column of this row's group
+    const int gi_lo = (warp * 32) / L;          // first group of this warp's rows (warp-uniform)
+    const int kcw = gi_lo < geo.gpt ? gi_lo * L : 0;
+    const bool two = (warp * 32 + 31) / L != gi_lo;  // the warp's rows span two groups
+    const bool second = gi != gi_lo;
+    uint8_t* p_row = sP + row * 128;
+    const int xr = row & 7;
+    const float keep_inv = DROPOUT ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    float m_prev = 0.f, l_prev = 1.f;
+    long long orow_prev = -1, lse_prev = 0;
+    int h_prev = 0;
+
+    auto epilogue = [&](int itp) {
+      const int bp = itp & 1;
+      sk_wait(&o_full[bp], (itp >> 1) & 1, 502, itp);
+      tc_fence_after();
+      uint32_t o[HD];
+      tmem_ld32(lane_addr + (bp ? Cfg::FO_COL1 : Cfg::FO_COL0), reinterpret_cast<uint32_t(&)[32]>(o[0]));
+      if constexpr (HD == 64) tmem_ld32(lane_addr + (bp ? Cfg::FO_COL1 : Cfg::FO_COL0) + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&o_empty[bp]);
+      if (orow_prev >= 0) {
+        const float inv = 1.0f / l_prev;
+        bf16* dst = p.o + orow_prev * p.ldo + h_prev * HD;
+#pragma unroll
+        for (int c = 0; c < HD; c += 8) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+          v.y = pack_bf16(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+          v.z = pack_bf16(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+          v.w = pack_bf16(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c) = v;
+        }
+        if (p.lse) p.lse[lse_prev] = (m_prev + sk_lg2(l_prev)) * SK_LN2;
+      }
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int tg = item % geo.n_tiles, h = item / geo.n_tiles;
+      const int g0 = tg * geo.gpt, g = g0 + gi;
+      const bool valid = gi < geo.gpt && g < p.G;
+      const int b = it & 1;
+      sMsk[b * 128 + row] = pk_mask(p, geo, g0, row);
+      sk_bar_sync(1, 128);
+
+      sk_wait(&s_full[b], (it >> 1) & 1, 501, it);
+      tc_fence_after();
+      uint32_t v[64];
+      {
+        const uint32_t sbase = lane_addr + (b ? Cfg::FS_COL1 : Cfg::FS_COL0) + kcw;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) sk_tmem_ld8(sbase + c8 * 8, v + c8 * 8);
+        if (two) {
+          uint32_t w[64];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) sk_tmem_ld8(sbase + L + c8 * 8, w + c8 * 8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = second ? w[j] : v[j];
+        }
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+      float mx = -1e30f;
+      const float* mrow = sMsk + b * 128 + kc0;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        float x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          x[e] = (j + e < L) ? fmaf(__uint_as_float(v[j + e]), scale2, mrow[(j + e) & 127]) : -1e30f;
+          v[j + e] = __float_as_uint(x[e]);
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+      }
+      if (it > 0) sk_wait(&o_full[b ^ 1], ((it - 1) >> 1) & 1, 502, it);  // P V of the previous item has consumed P
+      float sum = 0.f;
+      const unsigned long long didx0 = DROPOUT ? ((static_cast<unsigned long long>(g) * p.nH + h) * L + qi) * L : 0ull;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (c8 * 8 < L && gi < geo.gpt) {
+          float pr[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            pr[e] = valid ? ex2_approx(__uint_as_float(v[c8 * 8 + e]) - mx) : 0.f;
+            sum += pr[e];
+            if (DROPOUT) pr[e] = dropout_keep(p.seed, didx0 + c8 * 8 + e, p.drop_p) ? pr[e] * keep_inv : 0.f;
+          }
+          uint4 o;
+          o.x = pack_bf16(pr[0], pr[1]); o.y = pack_bf16(pr[2], pr[3]);
+          o.z = pack_bf16(pr[4], pr[5]); o.w = pack_bf16(pr[6], pr[7]);
+          const int piece = (kc0 >> 3) + c8;
+          *reinterpret_cast<uint4*>(p_row + (piece >> 3) * Cfg::CHUNK + (((piece & 7) ^ xr) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      if (it > 0) epilogue(it - 1);
+      m_prev = mx;
+      l_prev = valid ? sum : 1.f;
+      h_prev = h;
+      orow_prev = valid ? static_cast<long long>(g) * L + qi : -1;
+      lse_prev = (static_cast<long long>(g) * p.nH + h) * L + qi;
+    }
+    if (n_my > 0) epilogue(n_my - 1);
+  } else if (warp == SK_WARP_MMA) {
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+    auto issue_s = [&](int it) {
+      const int s = it & 1;
+      sk_wait(&full[s], (it >> 1) & 1, 503, it);
+      sk_wait(&s_empty[s], ((it >> 1) & 1) ^ 1, 504, it);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + s * Cfg::F_STAGE), k_addr = q_addr + Cfg::T_BYTES;
+        const uint32_t d = tmem_base + (s ? Cfg::FS_COL1 : Cfg::FS_COL0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(d, sk_desc_kmajor<HD>(q_addr, ks), sk_desc_kmajor<HD>(k_addr, ks), idesc_s, ks);
+        umma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) issue_s(0);
+#pragma unroll 1
+    for (int it = 0; it < n_my; ++it) {
+      if (it + 1 < n_my) issue_s(it + 1);
+      const int b = it & 1;
+      sk_wait(p_ready, it & 1, 505, it);
+      sk_wait(&o_empty[b], ((it >> 1) & 1) ^ 1, 507, it);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t v_addr = smem_u32(smem + b * Cfg::F_STAGE + 2 * Cfg::T_BYTES), p_addr = smem_u32(sP);
+        const uint32_t d = tmem_base + (b ? Cfg::FO_COL1 : Cfg::FO_COL0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 16 keys per step, two 64-key chunks
+          umma_f16_ss(d, umma_desc_sw128(p_addr + (kk >> 2) * Cfg::CHUNK + (kk & 3) * 32, 16, 1024), sk_desc_mnmajor<HD>(v_addr, kk),
+                      idesc_o, kk);
+        umma_commit(&o_full[b]);
+        umma_commit(&stage_free[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    if (lane == 0) {
+#pragma unroll 1
+      for (int it = 0; it < n_my; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int tg = item % geo.n_tiles, h = item / geo.n_tiles;
+        const int row0 = tg * geo.gpt * L;
+        const int s = it & 1;
+        if (it >= 2) sk_wait(&stage_free[s], ((it >> 1) - 1) & 1, 506, it);
+        uint8_t* st = smem + s * Cfg::F_STAGE;
+        mbar_arrive_expect_tx(&full[s], Cfg::F_STAGE);
+        tma_load_2d(st, &tmQ, &full[s], h * HD, row0);
+        tma_load_2d(st + Cfg::T_BYTES, &tmK, &full[s], h * HD, row0);
+        tma_load_2d(st + 2 * Cfg::T_BYTES, &tmV, &full[s], h * HD, row0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SK_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD, bool DROPOUT>
+__global__ void __launch_bounds__(SK_THREADS, 1) attn_pk_bwd_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmdO,
+                                                                   const __grid_constant__ CUtensorMap tmO,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV, const PkGeo geo,
+                                                                   int n_items) {
+  using Cfg = PkCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem + Cfg::B_OFF_P;
+  uint8_t* sdS = smem + Cfg::B_OFF_DS;
+  float* sMsk = reinterpret_cast<float*>(smem + Cfg::B_OFF_MSK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::B_OFF_BARS);
+  // timeout tags: 601 full, 602 stage_free, 603 s_full, 604 sdp_empty, 605 pds_ready, 606 out_full, 607 acc_empty
+  uint64_t* full = bars;
+  uint64_t* stage_free = bars + 2;
+  uint64_t* s_full = bars + 4;
+  uint64_t* sdp_empty = bars + 5;
+  uint64_t* pds_ready = bars + 6;
+  uint64_t* out_full = bars + 7;
+  uint64_t* acc_empty = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const float scale2 = p.scale * SK_LOG2E;
+  const int L = geo.L;
+
+  pdl_trigger();
+  if (warp == SK_WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&stage_free[s], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(sdp_empty, 4);
+      mbar_init(pds_ready, 4);
+      mbar_init(out_full, 1);
+      mbar_init(acc_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp == SK_WARP_LD && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  for (int i = tid; i < 4 * Cfg::CHUNK / 16; i += SK_THREADS) reinterpret_cast<uint4*>(sdS)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int gi = row / L, qi = row - gi * L;
+    const int kc0 = gi < geo.gpt ? gi * L : 0;
+    const int gi_lo = (warp * 32) / L;
+    const int kcw = gi_lo < geo.gpt ? gi_lo * L : 0;
+    const bool two = (warp * 32 + 31) / L != gi_lo;
+    const bool second = gi != gi_lo;
+    uint8_t* p_row = sP + row * 128;
+    uint8_t* ds_row = sdS + row * 128;
+    const int xr = row & 7;
+    const float keep_inv = DROPOUT ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+#pragma unroll 1
+    for (int u = 0; u < n_my; ++u) {
+      const int item = blockIdx.x + u * gridDim.x;
+      const int tg = item % geo.n_tiles, h = item / geo.n_tiles;
+      const int g0 = tg * geo.gpt, g = g0 + gi;
+      const bool valid = gi < geo.gpt && g < p.G;
+      const int s = u & 1;
+      const uint8_t* stage = smem + Cfg::B_OFF_STAGES + s * Cfg::B_STAGE;
+      sMsk[s * 128 + row] = pk_mask(p, geo, g0, row);
+      const float nlse2 = valid ? -p.lse[(static_cast<long long>(g) * p.nH + h) * L + qi] * SK_LOG2E : 0.f;
+      sk_wait(&full[s], (u >> 1) & 1, 601, u);
+      const float D = sk_row_dot<HD>(stage + Cfg::T_BYTES, stage + 2 * Cfg::T_BYTES, row);
+      sk_bar_sync(1, 128);
+
+      sk_wait(s_full, u & 1, 603, u);
+      tc_fence_after();
+      const unsigned long long didx0 = DROPOUT ? ((static_cast<unsigned long long>(g) * p.nH + h) * L + qi) * L : 0ull;
+      const float* mrow = sMsk + s * 128 + kc0;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sv[32], dv[32];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          sk_tmem_ld8(lane_addr + Cfg::BS_COL + kcw + hf * 32 + c8 * 8, sv + c8 * 8);
+          sk_tmem_ld8(lane_addr + Cfg::BDP_COL + kcw + hf * 32 + c8 * 8, dv + c8 * 8);
+        }
+        if (two) {
+          uint32_t sw[32], dw[32];
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            sk_tmem_ld8(lane_addr + Cfg::BS_COL + kcw + L + hf * 32 + c8 * 8, sw + c8 * 8);
+            sk_tmem_ld8(lane_addr + Cfg::BDP_COL + kcw + L + hf * 32 + c8 * 8, dw + c8 * 8);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sv[j] = second ? sw[j] : sv[j];
+            dv[j] = second ? dw[j] : dv[j];
+          }
+        }
+        tmem_ld_wait();
+        if (hf == 1) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(sdp_empty);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          if ((hf * 4 + c8) * 8 < L && gi < geo.gpt) {
+            float pd[8], ds[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = hf * 32 + c8 * 8 + e;
+              const float x = fmaf(__uint_as_float(sv[c8 * 8 + e]), scale2, mrow[j]) + nlse2;
+              const float pr = valid ? ex2_approx(x) : 0.f;
+              float dpv = __uint_as_float(dv[c8 * 8 + e]);
+              pd[e] = pr;
+              if (DROPOUT) {
+                const bool keep = dropout_keep(p.seed, didx0 + j, p.drop_p);
+                pd[e] = keep ? pr * keep_inv : 0.f;
+                dpv = keep ? dpv * keep_inv : 0.f;
+              }
+              ds[e] = pr * (dpv - D);
+            }
+            uint4 o, d;
+            o.x = pack_bf16(pd[0], pd[1]); o.y = pack_bf16(pd[2], pd[3]);
+            o.z = pack_bf16(pd[4], pd[5]); o.w = pack_bf16(pd[6], pd[7]);
+            d.x = pack_bf16(ds[0], ds[1]); d.y = pack_bf16(ds[2], ds[3]);
+            d.z = pack_bf16(ds[4], ds[5]); d.w = pack_bf16(ds[6], ds[7]);
+            const int piece = (kc0 >> 3) + hf * 4 + c8;
+            const int off = (piece >> 3) * Cfg::CHUNK + (((piece & 7) ^ xr) << 4);
+            *reinterpret_cast<uint4*>(p_row + off) = o;
+            *reinterpret_cast<uint4*>(ds_row + off) = d;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_ready);
+
+      sk_wait(out_full, u & 1, 606, u);
+      tc_fence_after();
+      // thread = query row for dQ and key row for dV / dK: the same global row g0 L + row of the three outputs
+      const long long grow = static_cast<long long>(g0) * L + row;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        uint32_t a[HD];
+        const uint32_t col = w == 0 ? Cfg::BDQ_COL : (w == 1 ? Cfg::BDV_COL : Cfg::BDK_COL);
+        tmem_ld32(lane_addr + col, reinterpret_cast<uint32_t(&)[32]>(a[0]));
+        if constexpr (HD == 64) tmem_ld32(lane_addr + col + 32, reinterpret_cast<uint32_t(&)[32]>(a[32]));
+        tmem_ld_wait();
+        if (valid) {
+          const float sc = w == 1 ? 1.0f : p.scale;
+          bf16* dst = (w == 0 ? p.dq + grow * p.lddq : (w == 1 ? p.dv + grow * p.lddv : p.dk + grow * p.lddk)) + h * HD;
+#pragma unroll
+          for (int c = 0; c < HD; c += 8) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(a[c]) * sc, __uint_as_float(a[c + 1]) * sc);
+            v.y = pack_bf16(__uint_as_float(a[c + 2]) * sc, __uint_as_float(a[c + 3]) * sc);
+            v.z = pack_bf16(__uint_as_float(a[c + 4]) * sc, __uint_as_float(a[c + 5]) * sc);
+            v.w = pack_bf16(__uint_as_float(a[c + 6]) * sc, __uint_as_float(a[c + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  } else if (warp == SK_WARP_MMA) {
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, 1, 1);
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);
+    const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+    auto issue_scores = [&](int u) {
+      const int s = u & 1;
+      sk_wait(&full[s], (u >> 1) & 1, 601, u);
+      sk_wait(sdp_empty, (u & 1) ^ 1, 604, u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + Cfg::B_OFF_STAGES + s * Cfg::B_STAGE), do_addr = q_addr + Cfg::T_BYTES;
+        const uint32_t k_addr = q_addr + 3 * Cfg::T_BYTES, v_addr = q_addr + 4 * Cfg::T_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(tmem_base + Cfg::BS_COL, sk_desc_kmajor<HD>(q_addr, ks), sk_desc_kmajor<HD>(k_addr, ks), idesc_s, ks);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_f16_ss(tmem_base + Cfg::BDP_COL, sk_desc_kmajor<HD>(do_addr, ks), sk_desc_kmajor<HD>(v_addr, ks), idesc_s, ks);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    if (n_my > 0) issue_scores(0);
+#pragma unroll 1
+    for (int u = 0; u < n_my; ++u) {
+      const int s = u & 1;
+      sk_wait(pds_ready, u & 1, 605, u);
+      sk_wait(acc_empty, (u & 1) ^ 1, 607, u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t q_addr = smem_u32(smem + Cfg::B_OFF_STAGES + s * Cfg::B_STAGE), do_addr = q_addr + Cfg::T_BYTES;
+        const uint32_t k_addr = q_addr + 3 * Cfg::T_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 16 query rows per step; M = the tile's 128 key rows (two chunks)
+          umma_f16_ss(tmem_base + Cfg::BDV_COL, umma_desc(p_addr + kk * 2048, Cfg::CHUNK, 1024, LAYOUT_SW128),
+                      sk_desc_mnmajor<HD>(do_addr, kk), idesc_kv, kk);
+          umma_f16_ss(tmem_base + Cfg::BDK_COL, umma_desc(ds_addr + kk * 2048, Cfg::CHUNK, 1024, LAYOUT_SW128),
+                      sk_desc_mnmajor<HD>(q_addr, kk), idesc_kv, kk);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 16 keys per step
+          umma_f16_ss(tmem_base + Cfg::BDQ_COL, umma_desc_sw128(ds_addr + (kk >> 2) * Cfg::CHUNK + (kk & 3) * 32, 16, 1024),
+                      sk_desc_mnmajor<HD>(k_addr, kk), idesc_q, kk);
+        umma_commit(out_full);
+        umma_commit(&stage_free[s]);
+      }
+      __syncwarp();
+      if (u + 1 < n_my) issue_scores(u + 1);
+    }
+  } else {
+    if (lane == 0) {
+#pragma unroll 1
+      for (int u = 0; u < n_my; ++u) {
+        const int item = blockIdx.x + u * gridDim.x;
+        const int tg = item % geo.n_tiles, h = item / geo.n_tiles;
+        const int row0 = tg * geo.gpt * L;
+        const int s = u & 1;
+        if (u >= 2) sk_wait(&stage_free[s], ((u >> 1) - 1) & 1, 602, u);
+        uint8_t* st = smem + Cfg::B_OFF_STAGES + s * Cfg::B_STAGE;
+        mbar_arrive_expect_tx(&full[s], Cfg::B_STAGE);
+        tma_load_2d(st, &tmQ, &full[s], h * HD, row0);
+        tma_load_2d(st + Cfg::T_BYTES, &tmdO, &full[s], h * HD, row0);
+        tma_load_2d(st + 2 * Cfg::T_BYTES, &tmO, &full[s], h * HD, row0);
+        tma_load_2d(st + 3 * Cfg::T_BYTES, &tmK, &full[s], h * HD, row0);
+        tma_load_2d(st + 4 * Cfg::T_BYTES, &tmV, &full[s], h * HD, row0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SK_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*SkEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -694,6 +1236,66 @@ int launch_sk_bwd_t(const AttnParams& p, cudaStream_t stream) {
   return 0;
 }
 
+static PkGeo pk_geo(const AttnParams& p) {
+  PkGeo geo;
+  geo.L = p.Lq;
+  geo.gpt = 128 / p.Lq;
+  geo.n_tiles = (p.G + geo.gpt - 1) / geo.gpt;
+  return geo;
+}
+
+template <int HD, bool DROPOUT>
+int launch_pk_fwd_t(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = PkCfg<HD>;
+  auto kern = attn_pk_fwd_kernel<HD, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::F_SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tq, tk, tv;
+  const int C = p.nH * HD;
+  const long long rows = static_cast<long long>(p.G) * p.Lq;
+  if (sk_tmap(&tq, p.q, p.ldq, rows, C, HD, 128) || sk_tmap(&tk, p.k, p.ldk, rows, C, HD, 128) ||
+      sk_tmap(&tv, p.v, p.ldv, rows, C, HD, 128))
+    return -1;
+  const PkGeo geo = pk_geo(p);
+  const long long n_items = static_cast<long long>(geo.n_tiles) * p.nH;
+  FIBER_CHECK(n_items < (1ll << 31), "too many attention work items");
+  const int grid = static_cast<int>(n_items < num_sms() ? n_items : num_sms());
+  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(SK_THREADS), Cfg::F_SMEM, stream, p, tq, tk, tv, geo, static_cast<int>(n_items)));
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <int HD, bool DROPOUT>
+int launch_pk_bwd_t(const AttnParams& p, cudaStream_t stream) {
+  using Cfg = PkCfg<HD>;
+  auto kern = attn_pk_bwd_kernel<HD, DROPOUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::B_SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tq, tdo, to, tk, tv;
+  const int C = p.nH * HD;
+  const long long rows = static_cast<long long>(p.G) * p.Lq;
+  if (sk_tmap(&tq, p.q, p.ldq, rows, C, HD, 128) || sk_tmap(&tdo, p.d_o, p.lddo, rows, C, HD, 128) ||
+      sk_tmap(&to, p.o, p.ldo, rows, C, HD, 128) || sk_tmap(&tk, p.k, p.ldk, rows, C, HD, 128) ||
+      sk_tmap(&tv, p.v, p.ldv, rows, C, HD, 128))
+    return -1;
+  const PkGeo geo = pk_geo(p);
+  const long long n_items = static_cast<long long>(geo.n_tiles) * p.nH;
+  FIBER_CHECK(n_items < (1ll << 31), "too many attention work items");
+  const int grid = static_cast<int>(n_items < num_sms() ? n_items : num_sms());
+  FIBER_CUDA(launch_k(kern, dim3(grid), dim3(SK_THREADS), Cfg::B_SMEM, stream, p, tq, tdo, to, tk, tv, geo,
+                      static_cast<int>(n_items)));
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace
 
 static bool sk_aligned16(const void* ptr, long long ld) {
@@ -712,12 +1314,24 @@ bool attn_sk_bwd_supported(const AttnParams& p, int hd) {
          sk_aligned16(p.dq, p.lddq) && sk_aligned16(p.dk, p.lddk) && sk_aligned16(p.dv, p.lddv);
 }
 
+// packed self-attention: Lq == Lk == L, 32 <= L <= 64, L % 8 == 0 (two or three whole groups per 128-row tile)
+// (L >= 32: a warp's rows then touch at most two groups, see the kernels)
+bool attn_pk_shape(const AttnParams& p) { return p.Lq == p.Lk && p.Lq >= 32 && p.Lq <= 64 && p.Lq % 8 == 0; }
+
 int launch_attn_sk_bwd(const AttnParams& p, int hd, cudaStream_t stream) {
+  if (attn_pk_shape(p)) {
+    if (hd == 32) return p.drop_p > 0.f ? launch_pk_bwd_t<32, true>(p, stream) : launch_pk_bwd_t<32, false>(p, stream);
+    return p.drop_p > 0.f ? launch_pk_bwd_t<64, true>(p, stream) : launch_pk_bwd_t<64, false>(p, stream);
+  }
   if (hd == 32) return p.drop_p > 0.f ? launch_sk_bwd_t<32, true>(p, stream) : launch_sk_bwd_t<32, false>(p, stream);
   return p.drop_p > 0.f ? launch_sk_bwd_t<64, true>(p, stream) : launch_sk_bwd_t<64, false>(p, stream);
 }
 
 int launch_attn_sk_fwd(const AttnParams& p, int hd, cudaStream_t stream) {
+  if (attn_pk_shape(p)) {
+    if (hd == 32) return p.drop_p > 0.f ? launch_pk_fwd_t<32, true>(p, stream) : launch_pk_fwd_t<32, false>(p, stream);
+    return p.drop_p > 0.f ? launch_pk_fwd_t<64, true>(p, stream) : launch_pk_fwd_t<64, false>(p, stream);
+  }
   if (hd == 32) return p.drop_p > 0.f ? launch_sk_fwd_t<32, true>(p, stream) : launch_sk_fwd_t<32, false>(p, stream);
   return p.drop_p > 0.f ? launch_sk_fwd_t<64, true>(p, stream) : launch_sk_fwd_t<64, false>(p, stream);
 }

@@ -42,15 +42,17 @@ int option_attn_small() {
   return v;
 }
 // "attn_sk": bit 0 routes the forward, bit 1 the backward of plain attention with at most 64 keys per group and at least 96
-// queries (i2t) to the tcgen05 + TMA kernels of attention_sk.cu; bits 2 / 3 also route short query sequences (RoBERTa
-// self-attention: 40 of 128 tile rows used, slower than the mma.sync kernels).  Default 3 (validated on B200 in round 2:
-// i2t stage 2 forward 0.255 -> 0.158 ms, backward 0.407 -> 0.317 ms), or FIBER_ATTN_SK.
+// queries (i2t) to the tcgen05 + TMA kernels of attention_sk.cu; bits 2 / 3 the forward / backward of self-attention shapes
+// that pack two or three samples into a 128-row tile (RoBERTa, Lq = Lk in {32, 40, 48, 56, 64}); bit 4 every other short
+// query sequence, unpacked (slower than the mma.sync kernels; tests).  Default 15 (validated on B200 in round 2: i2t stage 2
+// forward 0.255 -> 0.158 ms, backward 0.407 -> 0.317 ms; text self-attention forward 0.042 = 0.042 ms, backward
+// 0.089 -> 0.071 ms), or FIBER_ATTN_SK.
 static std::atomic<int> g_attn_sk{-1};
 int option_attn_sk() {
   int v = g_attn_sk.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_ATTN_SK");
-    v = e ? (atoi(e) & 15) : 3;
+    v = e ? (atoi(e) & 31) : 15;
     g_attn_sk.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -199,7 +201,7 @@ int fiber_set_option(const char* name, int32_t value) {
     return 0;
   }
   if (name && strcmp(name, "attn_sk") == 0) {
-    fiber::g_attn_sk.store(value < 0 ? -1 : (value & 15), std::memory_order_relaxed);
+    fiber::g_attn_sk.store(value < 0 ? -1 : (value & 31), std::memory_order_relaxed);
     return 0;
   }
   if (name && strcmp(name, "gemm_cta2") == 0) {

@@ -40,8 +40,9 @@ int64_t fiber_launch_count(void);
  * one, bit 2 the few-query case (head_dim 64, at most 48 queries, more than 48 keys: t2i, roberta.py:441-502) to the
  * 3-warp one; default 7 or FIBER_ATTN_SMALL.
  * "attn_sk": bit 0 routes the forward, bit 1 the backward of mode-0 attention with at most 64 keys per group and at least 96
- * queries (i2t) to the tcgen05 + TMA kernels of csrc/attention_sk.cu, bits 2 / 3 also shorter query sequences; default 3 or
- * FIBER_ATTN_SK.
+ * queries (i2t) to the tcgen05 + TMA kernels of csrc/attention_sk.cu, bits 2 / 3 the forward / backward of self-attention
+ * with Lq = Lk in {32, 40, 48, 56, 64} (RoBERTa, roberta.py:256-326: two or three samples packed into a 128-row tile), bit 4
+ * every other shorter query sequence; default 15 or FIBER_ATTN_SK.
  * "gemm_cta2": bit 0 runs K-major fiber_gemm launches with N > 128, M % 256 == 0, K >= 1024 and no row_count as CTA pairs
  * (2-CTA clusters, tcgen05 cta_group::2, 256 x 256 pair tiles) for the default epilogues, bit 1 for act 3 .. 7, bit 2 lowers
  * the K threshold to 256; same results bit for bit (same accumulation order); default 3, FIBER_GEMM_CTA2.

@@ -156,10 +156,14 @@ def test_plain_attention_small_cfg(cuda_dev, B, nh, hd, Lq, Lk, masked, small):
 # forward, bit 1 backward).  Cases with more keys must fall through to the mma.sync kernels with the option set.
 SK_CASES = [(3, 12, 64, 40, 40, True), (2, 12, 64, 50, 50, True), (4, 12, 64, 33, 47, True), (256, 12, 64, 40, 40, True),
             (2, 16, 32, 576, 40, True), (2, 32, 32, 144, 40, True), (3, 16, 32, 100, 48, False), (1, 4, 32, 1296, 50, True),
-            (5, 16, 32, 576, 64, False), (3, 12, 64, 130, 64, True), (2, 12, 64, 40, 576, False), (3, 12, 64, 33, 100, True)]
+            (5, 16, 32, 576, 64, False), (3, 12, 64, 130, 64, True), (2, 12, 64, 40, 576, False), (3, 12, 64, 33, 100, True),
+            # packed self-attention (Lq == Lk, L % 8 == 0: 128 / L groups per tile), incl. a partial last tile
+            (5, 12, 64, 40, 40, True), (7, 4, 32, 16, 16, True), (3, 12, 64, 64, 64, False), (4, 12, 64, 48, 48, True),
+            (1, 12, 64, 24, 24, True)]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 5, 3, 15, 10], ids=["mmasync", "sk_long", "sk_all", "sk_long_fb", "sk_all_fb", "sk_bwd_only"])
+@pytest.mark.parametrize("mode", [0, 1, 21, 3, 15, 31, 26],
+                         ids=["mmasync", "sk_long", "sk_all", "sk_long_fb", "default", "sk_all_fb", "sk_bwd_only"])
 @pytest.mark.parametrize("B,nh,hd,Lq,Lk,masked", SK_CASES)
 def test_plain_attention_tcgen05(cuda_dev, B, nh, hd, Lq, Lk, masked, mode):
     from fiber_b200 import lib
@@ -171,12 +175,14 @@ def test_plain_attention_tcgen05(cuda_dev, B, nh, hd, Lq, Lk, masked, mode):
     finally:
         lib.set_option("attn_sk", -1)
     launched = lib.get_option("attn_sk_launches") - before
-    fwd = Lk <= 64 and ((mode & 1 and Lq >= 96) or mode & 4)
-    bwd = Lk <= 64 and ((mode & 2 and Lq >= 96) or mode & 8)
+    packed = Lq == Lk and 32 <= Lq <= 64 and Lq % 8 == 0
+    short = Lq < 96 and (packed or mode & 16)
+    fwd = Lk <= 64 and ((mode & 1 and Lq >= 96) or (mode & 4 and short))
+    bwd = Lk <= 64 and ((mode & 2 and Lq >= 96) or (mode & 8 and short))
     assert launched == int(bool(fwd)) + int(bool(bwd))
 
 
-@pytest.mark.parametrize("B,nh,hd,Lq,Lk", [(3, 12, 64, 40, 40), (2, 12, 64, 130, 50), (2, 16, 32, 300, 40)])
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk", [(3, 12, 64, 40, 40), (2, 12, 64, 130, 50), (2, 16, 32, 300, 40), (5, 12, 64, 48, 48)])
 def test_plain_attention_tcgen05_backward_dropout_matches_mma_sync(cuda_dev, B, nh, hd, Lq, Lk):
     """The tcgen05 backward regenerates the forward's dropout mask from the same counter hash: with the same forward
     output it must give the mma.sync backward's gradients (to bf16 rounding of P / dS)."""
@@ -193,7 +199,7 @@ def test_plain_attention_tcgen05_backward_dropout_matches_mma_sync(cuda_dev, B, 
     try:
         o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, scale, **kw)
         grads = []
-        for mode in (0, 10):
+        for mode in (0, 26):
             lib.set_option("attn_sk", mode)
             dq, dkv = torch.empty_like(q), torch.empty_like(kv)
             K.attn_bwd(d_o, q, kv[:, :C], kv[:, C:], o, lse, nh, hd, scale, dq, dkv[:, :C], dkv[:, C:], **kw)
@@ -209,12 +215,17 @@ def test_plain_attention_tcgen05_dropout_matches_mma_sync(cuda_dev):
     """Probability dropout uses the same counter-based hash in both generations: the tcgen05 forward must reproduce the
     mma.sync forward's output (same kept set, same scaling) so that either backward can follow."""
     from fiber_b200 import kernels as K, lib
-    B, nh, hd, Lq, Lk = 3, 12, 64, 130, 50
+    _fwd_dropout_case(cuda_dev, 3, 12, 64, 130, 50)
+    _fwd_dropout_case(cuda_dev, 5, 12, 64, 40, 40)  # packed tiles
+
+
+def _fwd_dropout_case(cuda_dev, B, nh, hd, Lq, Lk):
+    from fiber_b200 import kernels as K, lib
     C = nh * hd
     q = _rand((B * Lq, C), cuda_dev, 11)
     kv = _rand((B * Lk, 2 * C), cuda_dev, 12)
     outs = []
-    for mode in (0, 5):
+    for mode in (0, 21):
         lib.set_option("attn_sk", mode)
         try:
             outs.append(K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, hd ** -0.5, groups=B, lq=Lq, lk=Lk, drop_p=0.25, seed=99))

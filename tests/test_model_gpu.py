@@ -176,9 +176,12 @@ def test_merged_mlm_itm_pass_equals_separate_passes(cuda_dev, unfused_mlm_ce):
         with torch.no_grad():
             outs.append(model(batch))
     a, b = outs
+    # Not bit-identical: the packed self-attention kernels put two or three samples into one 128-row tile, and where a
+    # sample sits in its tile (which depends on the batch it is part of) changes the fp32 summation order of P V; the
+    # difference is fp32 rounding amplified by the bf16 stores of 36 layers.
     for k in ("mlm_loss", "itm_loss", "itc_loss"):
-        assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(1.0, abs(float(b[k]))), k
-    assert torch.equal(a["mlm_logits"], b["mlm_logits"]) and torch.equal(a["itm_logits"], b["itm_logits"])
+        assert abs(float(a[k]) - float(b[k])) <= 2e-4 * max(1.0, abs(float(b[k]))), k
+    assert _l2rel(a["mlm_logits"], b["mlm_logits"]) < 5e-3 and _l2rel(a["itm_logits"], b["itm_logits"]) < 5e-3
 
 
 def test_kernel_generations_agree_384(cuda_dev):
@@ -226,8 +229,14 @@ def test_kernel_generations_agree_384(cuda_dev):
     scale = max(float(v.norm()) for v in g0.values())
     # key biases: softmax is invariant to them, their gradient is exactly 0 in exact arithmetic and pure rounding noise on
     # both sides (the oracle-based tests skip them the same way)
-    errs = sorted((_l2rel(g1[n], g0[n]), n) for n in g0
-                  if float(g0[n].norm()) > 1e-6 * scale and not n.endswith("key.bias"))
+    # scalar gates: judged on the scale of the largest gate gradient (see _grad_report)
+    gate_scale = max([float(v.abs().max()) for v in g0.values() if v.numel() == 1] + [0.0])
+
+    def err(n):
+        if g0[n].numel() == 1 and gate_scale > 0:
+            return float((g1[n].float() - g0[n].float()).abs().max()) / gate_scale
+        return _l2rel(g1[n], g0[n])
+    errs = sorted((err(n), n) for n in g0 if float(g0[n].norm()) > 1e-6 * scale and not n.endswith("key.bias"))
     assert errs[len(errs) // 2][0] < 2e-2, errs[len(errs) // 2]
     assert errs[int(len(errs) * 0.9)][0] < 5e-2, errs[int(len(errs) * 0.9)]
     assert errs[-1][0] < 0.35, errs[-1]

@@ -43,13 +43,27 @@ aux2 = torch.randn(256, 288, device=dev).to(bf); pre2 = torch.empty(256, 288, de
 K.gemm(a2, w2, bias=torch.randn(288, device=dev), act=K.ACT_GELU_CACHE, preact=pre2)
 K.gemm(a2, w2, aux=aux2, act=K.ACT_MUL_AUX)
 K.gemm(a2, w2, bias=torch.randn(288, device=dev), residual=aux2, act=K.ACT_RES_PF, row_scale=torch.ones(2, device=dev), rows_per_scale=128)
-for nhh, hd, lq, lk, dp in ((2, 32, 200, 40, 0.0), (2, 64, 130, 50, 0.2)):
+# tcgen05 plain attention, forward + backward: i2t (many queries), unpacked short, packed self-attention (with dropout)
+for nhh, hd, lq, lk, dp in ((2, 32, 200, 40, 0.0), (2, 64, 130, 50, 0.2), (2, 64, 40, 40, 0.1), (2, 64, 33, 47, 0.0)):
     Cc = nhh * hd
-    qq = torch.randn(3 * lq, Cc, device=dev).to(bf); kk = torch.randn(3 * lk, 2 * Cc, device=dev).to(bf)
-    mk = torch.zeros(3, lk, device=dev); mk[1, lk - 5:] = -10000.0
-    lib.set_option("attn_sk", 5)
-    K.attn_fwd(qq, kk[:, :Cc], kk[:, Cc:], nhh, hd, hd ** -0.5, groups=3, lq=lq, lk=lk, key_mask=mk, drop_p=dp, seed=5)
+    qq = torch.randn(4 * lq, Cc, device=dev).to(bf); kk = torch.randn(4 * lk, 2 * Cc, device=dev).to(bf)
+    dd = torch.randn(4 * lq, Cc, device=dev).to(bf)
+    mk = torch.zeros(4, lk, device=dev); mk[1, lk - 5:] = -10000.0
+    lib.set_option("attn_sk", 31)
+    kw2 = dict(groups=4, lq=lq, lk=lk, key_mask=mk, drop_p=dp, seed=5)
+    oo, ll = K.attn_fwd(qq, kk[:, :Cc], kk[:, Cc:], nhh, hd, hd ** -0.5, **kw2)
+    dq2, dkv2 = torch.empty_like(qq), torch.empty_like(kk)
+    K.attn_bwd(dd, qq, kk[:, :Cc], kk[:, Cc:], oo, ll, nhh, hd, hd ** -0.5, dq2, dkv2[:, :Cc], dkv2[:, Cc:], **kw2)
     lib.set_option("attn_sk", -1)
+# CTA-pair GEMM (2-CTA clusters) and the fused MLM decoder + cross-entropy
+a3 = torch.randn(512, 1024, device=dev).to(bf); w3 = torch.randn(384, 1024, device=dev).to(bf)
+K.gemm(a3, w3, bias=torch.randn(384, device=dev), residual=torch.randn(512, 384, device=dev).to(bf))
+from fiber_b200 import ops
+hh = torch.randn(200, 768, device=dev).to(bf).requires_grad_(True)
+ww = (torch.randn(1000, 768, device=dev) * 0.05).requires_grad_(True); bb = torch.zeros(1000, device=dev, requires_grad=True)
+lab = torch.randint(0, 1000, (200,), device=dev); lab[::3] = -100
+loss_ce, _ = ops.MlmDecoderCEFn.apply(hh, ww, bb, lab)
+loss_ce.backward()
 from fiber_b200.optim import FusedAdamW
 ps = [torch.nn.Parameter(torch.randn(n, device=dev)) for n in (5, 1023, 70000)]
 for p_ in ps:
