@@ -35,6 +35,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._step = 0
+        self._stage = [None, None]  # two pinned staging buffers (+ the event of their last copy), used alternately
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -69,7 +70,22 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step += 1
         t, ch = build_tables(entries)
         raw = torch.from_numpy(np.concatenate([t.view(np.uint8).reshape(-1), ch.view(np.uint8).reshape(-1)]))
-        d = raw.to(dev, non_blocking=False)  # ~50 KB; pageable copy, ordered on the current stream
+        # ~50 KB of tables per step (the scheduler rewrites lr).  A pageable .to(device) makes the host wait for the whole
+        # stream — i.e. for the step's backward — every step, and the next step's first launches then start on an idle GPU
+        # (+14..20 ms per step measured).  Stage through pinned memory instead, two buffers used alternately: a buffer is
+        # rewritten only after the copy issued from it two steps ago has completed.
+        nbytes = raw.numel()
+        slot = self._step & 1
+        stage = self._stage[slot]
+        if stage is None or stage[0].numel() < nbytes:
+            stage = (torch.empty(nbytes, dtype=torch.uint8, pin_memory=True), torch.cuda.Event())
+            self._stage[slot] = stage
+        else:
+            stage[1].synchronize()
+        stage[0][:nbytes].copy_(raw)
+        d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d.copy_(stage[0][:nbytes], non_blocking=True)
+        stage[1].record(torch.cuda.current_stream())
         off = t.nbytes
         _lib.check(_lib.load().fiber_adamw_multi(C.c_void_p(d.data_ptr()), C.c_void_p(d.data_ptr() + off), len(ch), CHUNK,
                                                  float(betas[0]), float(betas[1]), float(eps), self._step,

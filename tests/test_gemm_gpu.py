@@ -303,3 +303,34 @@ def test_gemm_cta_pairs(cuda_dev, m, n, k):
     torch.testing.assert_close(pair[0].float(), ref, rtol=RTOL, atol=ATOL)
     for x, y in zip(base, pair):
         assert torch.equal(x, y)
+
+
+def test_programmatic_dependent_launch_option(cuda_dev):
+    """fiber_set_option("pdl", 1): every launch carries the programmatic-stream-serialization attribute and every kernel
+    waits (griddepcontrol.wait) before its first global access — a chain of dependent launches (GEMM -> LayerNorm ->
+    GEMM with residual -> wgrad) must give the results of plain stream order."""
+    from fiber_b200 import kernels as K, lib
+    a = _mk((1024, 512), cuda_dev, 31)
+    w1 = _mk((512, 512), cuda_dev, 32, 512 ** -0.5)
+    w2 = _mk((384, 512), cuda_dev, 33, 512 ** -0.5)
+    g, b = torch.ones(512, device=cuda_dev), torch.zeros(512, device=cuda_dev)
+
+    def chain():
+        h = K.gemm(a, w1)
+        y = K.layernorm_fwd(h, g, b, 1e-5)[0]
+        o = K.gemm(y, w2, residual=_mk((1024, 384), cuda_dev, 34))
+        dw = K.gemm(o, y, mn_major=True, accumulate=True)
+        return o, dw
+
+    lib.set_option("pdl", 0)
+    ref = chain()
+    try:
+        lib.set_option("pdl", 1)
+        assert lib.get_option("pdl") == 1
+        for _ in range(3):
+            out = chain()
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("pdl", -1)
+    assert torch.equal(out[0], ref[0])
+    torch.testing.assert_close(out[1], ref[1], rtol=1e-4, atol=1e-2)  # split-K atomics: summation order varies
