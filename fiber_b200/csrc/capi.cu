@@ -90,7 +90,9 @@ int option_pdl() {
 // cta_group::2: 256 x 256 pair tiles, half of the B tile per CTA) for the default epilogues, bit 1 for the two-box epilogues
 // (act 3 .. 7), in both cases only when K >= 1024: measured on B200 (profiles/r2_gemm_cta_pairs.txt) +3 .. +9 % at K >= 1024
 // and -3 .. -20 % at K <= 512, where a tile is four to eight k-blocks and the pair's longer hand-offs (remote arrives,
-// multicast commits) show.  Default 3, or FIBER_GEMM_CTA2; bit 2 lifts the K >= 1024 rule (tests, microbenchmarks).
+// multicast commits) show.  Default 3, or FIBER_GEMM_CTA2; bit 2 lifts the K >= 1024 rule (tests, microbenchmarks); bit 3
+// runs wgrad launches (MN-major operands, split-K, fused column sums) as pairs too — correct (test_gemm_cta_pairs_wgrad) but
+// 2 - 4 % slower than single CTAs on every FIBER shape, so off by default.
 static std::atomic<int> g_gemm_cta2{-1};
 static std::atomic<int> g_gemm_cta2_launches{0};
 void count_gemm_cta2_launch() { g_gemm_cta2_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -98,7 +100,7 @@ int option_gemm_cta2() {
   int v = g_gemm_cta2.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_GEMM_CTA2");
-    v = e ? (atoi(e) & 7) : 3;
+    v = e ? (atoi(e) & 15) : 3;
     g_gemm_cta2.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -205,7 +207,7 @@ int fiber_set_option(const char* name, int32_t value) {
     return 0;
   }
   if (name && strcmp(name, "gemm_cta2") == 0) {
-    fiber::g_gemm_cta2.store(value < 0 ? -1 : (value & 7), std::memory_order_relaxed);
+    fiber::g_gemm_cta2.store(value < 0 ? -1 : (value & 15), std::memory_order_relaxed);
     return 0;
   }
   if (name && strcmp(name, "pdl") == 0) {

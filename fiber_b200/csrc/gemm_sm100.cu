@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                     const GemmParams p) {
-  static_assert(!CTA2 || (MN_MAJOR == 0 && BN == 256), "CTA pairs: K-major operands, 256-column tiles");
+  static_assert(!CTA2 || BN == 256, "CTA pairs: 256-column tiles");
   using Cfg = GemmCfg<BN, EPI, CTA2>;
   constexpr int NCTA = CTA2 ? 2 : 1;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs, owns the full / tempty barriers)
@@ -395,8 +395,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the whole pair
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t bar = mapa_cta(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_2sm(sa, &tmA, bar, kb * GEMM_BK, m0);
-            tma_load_2d_2sm(sb, &tmB, bar, kb * GEMM_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            if constexpr (MN_MAJOR == 0) {
+              tma_load_2d_2sm(sa, &tmA, bar, kb * GEMM_BK, m0);
+              tma_load_2d_2sm(sb, &tmB, bar, kb * GEMM_BK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            } else {  // wgrad: this CTA's 128 M columns and its half of the N columns, 64-wide chunks
+#pragma unroll
+              for (int j = 0; j < GEMM_BM / 64; ++j)
+                tma_load_2d_2sm(sa + j * 8192, &tmA, bar, m0 + j * 64, kb * GEMM_BK);
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_2sm(sb + j * 8192, &tmB, bar, n0 + static_cast<int>(cta_rank) * (BN / 2) + j * 64, kb * GEMM_BK);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -427,7 +436,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ================= MMA issuer (pair: the leader CTA only) =================
     constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * NCTA, BN, MN_MAJOR, MN_MAJOR);
-    constexpr uint32_t idesc_cs = umma_idesc_bf16(GEMM_BM, 16, MN_MAJOR, MN_MAJOR);
+    constexpr uint32_t idesc_cs = umma_idesc_bf16(GEMM_BM * NCTA, 16, MN_MAJOR, MN_MAJOR);  // pair: 8 ones-columns per CTA
     const uint32_t ones_addr = smem_u32(staging);
     int stage = 0;
     uint32_t phase = 0;
@@ -461,9 +470,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if constexpr (CTA2) umma_f16_ss2(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else                umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (MN_MAJOR == 1 && cs_unit)
-              umma_f16_ss(tmem_base + BN, adesc, umma_desc_sw128(ones_addr + k * 2048, 8192, 1024), idesc_cs,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+            if (MN_MAJOR == 1 && cs_unit) {
+              if constexpr (CTA2)
+                umma_f16_ss2(tmem_base + BN, adesc, umma_desc_sw128(ones_addr + k * 2048, 8192, 1024), idesc_cs,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
+              else
+                umma_f16_ss(tmem_base + BN, adesc, umma_desc_sw128(ones_addr + k * 2048, 8192, 1024), idesc_cs,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           if constexpr (CTA2) {  // the same barrier offset in both CTAs of the pair
             umma_commit2_mc(&empty_bar[stage], 3);
@@ -1064,10 +1078,12 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
   FIBER_CHECK(a->colsum == nullptr || (a->a_major == 1 && a->out_mode != 0 && a->row_scale == nullptr),
               "colsum needs MN-major operands, an fp32 output and no row_scale");
 
-  // CTA pairs (GemmCfg): K-major, 256-column tiles, whole 256-row pair tiles, no split-K / device row count
+  // CTA pairs (GemmCfg): 256-column tiles, whole 256-row pair tiles, no device row count; K-major launches (bit 0 / bit 1 by
+  // epilogue family) without split-K, wgrad launches (bit 3) with it
   const int cta2_opt = option_gemm_cta2();
-  const bool cta2 = mn == 0 && BN == 256 && a->m % (2 * GEMM_BM) == 0 && a->row_count == nullptr && splits == 1 &&
-                    ((cta2_opt >> (epi1 ? 1 : 0)) & 1) != 0 && a->k >= ((cta2_opt & 4) ? 256 : 1024);
+  const bool cta2 = BN == 256 && a->m % (2 * GEMM_BM) == 0 && a->row_count == nullptr &&
+                    a->k >= ((cta2_opt & 4) ? 256 : 1024) &&
+                    (mn == 0 ? (splits == 1 && ((cta2_opt >> (epi1 ? 1 : 0)) & 1) != 0) : (cta2_opt & 8) != 0);
   CUtensorMap ta, tb;
   if (mn == 0) {
     // A[M, K] (lda), B[N, K] (ldb): inner = K
@@ -1110,7 +1126,8 @@ int gemm_dispatch(const fiber_gemm_args* a, cudaStream_t stream) {
       FIBER_CHECK(p.tma_store == 1, "act=%d needs the TMA-store epilogue", a->act);
       return launch_gemm<256, 0, 1, 1>(ta, tb, tc, tp, p, pair_grid, stream);
     }
-    return launch_gemm<256, 0, 0, 1>(ta, tb, tc, tp, p, pair_grid, stream);
+    return mn ? launch_gemm<256, 1, 0, 1>(ta, tb, tc, tp, p, pair_grid, stream)
+              : launch_gemm<256, 0, 0, 1>(ta, tb, tc, tp, p, pair_grid, stream);
   }
   if (epi1) {
     FIBER_CHECK(p.tma_store == 1, "act=%d needs the TMA-store epilogue", a->act);

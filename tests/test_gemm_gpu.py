@@ -334,3 +334,35 @@ def test_programmatic_dependent_launch_option(cuda_dev):
         lib.set_option("pdl", -1)
     assert torch.equal(out[0], ref[0])
     torch.testing.assert_close(out[1], ref[1], rtol=1e-4, atol=1e-2)  # split-K atomics: summation order varies
+
+
+@pytest.mark.parametrize("rows,m,n", [(4096, 512, 384), (36864, 2048, 512), (9000, 256, 1024), (147456, 512, 2048)])
+def test_gemm_cta_pairs_wgrad(cuda_dev, rows, m, n):
+    """fiber_set_option("gemm_cta2", 8 | 4): wgrad launches (MN-major operands, split-K atomics, fused column sums) as CTA
+    pairs against the single-CTA kernel and the fp32 reference."""
+    from fiber_b200 import kernels as K, lib
+    dy = _mk((rows, m), cuda_dev, 41, 0.5)
+    x = _mk((rows, n), cuda_dev, 42, 0.5)
+
+    def run():
+        db = torch.zeros(m, device=cuda_dev)
+        dw = K.gemm(dy, x, mn_major=True, accumulate=True, colsum=db)
+        return dw, db
+
+    lib.set_option("gemm_cta2", 0)
+    base = run()
+    try:
+        lib.set_option("gemm_cta2", 12)
+        n0 = lib.get_option("gemm_cta2_launches")
+        pair = run()
+        torch.cuda.synchronize()
+        assert lib.get_option("gemm_cta2_launches") - n0 == 1
+    finally:
+        lib.set_option("gemm_cta2", -1)
+    ref_w = dy.float().t() @ x.float()
+    ref_b = dy.float().sum(0)
+    tol = 2e-2 * max(1.0, rows ** 0.5 * 0.25)
+    torch.testing.assert_close(pair[0], ref_w, rtol=2e-2, atol=tol)
+    torch.testing.assert_close(pair[1], ref_b, rtol=2e-2, atol=tol)
+    torch.testing.assert_close(pair[0], base[0], rtol=1e-3, atol=tol * 0.1)  # split-K atomics: order varies
+    torch.testing.assert_close(pair[1], base[1], rtol=1e-3, atol=tol * 0.1)
