@@ -457,3 +457,36 @@ def test_vqa_576_vs_oracle_and_reference_fixture(cuda_dev):
     assert abs(float(ret["vqa_loss"]) - float(ref["vqa_loss"])) < 5e-3 * abs(float(ref["vqa_loss"]))
     median, p90, worst = _grad_report(model, sdg, 500)
     assert median < 3e-2 and p90 < 6e-2 and worst[0] < 0.35, (median, p90, worst)
+
+
+def test_fused_mlm_cross_entropy_equals_logits_form_in_the_model(cuda_dev, m224):
+    """compute_mlm with the fused decoder + cross-entropy (default: no logits in memory, "mlm_pred") against the reference's
+    logits -> F.cross_entropy form on the same model and batch: loss, arg-max at the labelled positions, and the
+    gradients of the MLM head and of the backbone."""
+    from fiber_b200.modules import objectives as OBJ
+    model, cfg, sd = m224
+    batch = _to(synth.synth_batch(4, 224, 40, seed=77), cuda_dev)
+    model.eval()  # no dropout / DropPath: both forms see the same features
+    outs = []
+    old = OBJ.FUSED_MLM_CE
+    try:
+        for fused in (False, True):
+            OBJ.set_fused_mlm_ce(fused)
+            model.zero_grad()
+            r = OBJ.compute_mlm(model, batch)
+            r["mlm_loss"].backward()
+            outs.append((r, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        OBJ.set_fused_mlm_ce(old)
+    (r0, g0), (r1, g1) = outs
+    assert "mlm_logits" in r0 and "mlm_logits" not in r1 and "mlm_pred" in r1
+    assert abs(float(r1["mlm_loss"]) - float(r0["mlm_loss"])) < 2e-5 * abs(float(r0["mlm_loss"]))
+    keep = r0["mlm_labels"] != -100
+    assert int(keep.sum()) > 0 and torch.equal(r1["mlm_pred"][keep], r0["mlm_logits"].argmax(-1)[keep])
+    assert g0.keys() == g1.keys()
+    scale = max(float(v.norm()) for v in g0.values())
+    errs = sorted((_l2rel(g1[n], g0[n]), n) for n in g0
+                  if float(g0[n].norm()) > 1e-6 * scale and not n.endswith("key.bias") and g0[n].numel() > 1)
+    # the fused backward rounds d(logits) to bf16 once (the logits form rounds the fp32 logits' gradient the same way on its
+    # way into the dgrad / wgrad GEMMs), so the two agree to bf16 noise
+    assert errs[len(errs) // 2][0] < 1e-2 and errs[-1][0] < 0.2, (errs[len(errs) // 2], errs[-1])
