@@ -673,11 +673,13 @@ def eager_gpu_baseline(args, dev, host, our_value):
 
 
 def _kernel_options():
-    """Opt-in kernel selections in effect (fiber_set_option / FIBER_* environment); all 0 = the validated defaults."""
+    """Kernel selections in effect (fiber_set_option / FIBER_* environment)."""
     try:
         from fiber_b200 import lib
         from fiber_b200 import ops
-        opts = {k: lib.get_option(k) for k in ("winattn_tc", "attn_small")}
+        opts = {k: lib.get_option(k) for k in ("winattn_tc", "attn_small", "attn_sk", "gemm_cta2", "pdl")}
+        from fiber_b200.modules import objectives
+        opts["mlm_fused_ce"] = int(objectives.FUSED_MLM_CE)
         opts["gelu_cache"] = int(ops.GELU_CACHE)
         opts["gelu_onepass"] = int(ops.GELU_ONEPASS)
         opts["gelu_grad_prefetch"] = int(ops.GELU_GRAD_PREFETCH)

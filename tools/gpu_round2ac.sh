@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2ac_tests.log 2>&1
 tail -n 5 gpurun_out/r2ac_tests.log
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -n 2
-timeout 1500 python bench.py > gpurun_out/r2ac_bench.json 2> gpurun_out/r2ac_bench.err
+timeout 1800 python bench.py > gpurun_out/r2ac_bench.json 2> gpurun_out/r2ac_bench.err
 tail -n 3 gpurun_out/r2ac_bench.err
 python - <<'PY'
 import json
