@@ -161,7 +161,7 @@ int cast_dispatch(const float*, bf16*, long long, cudaStream_t);
 int axpy_dispatch(const bf16*, long long, const bf16*, long long, const float*, bf16*, long long, long long, int,
                   cudaStream_t);
 int cast_transpose_dispatch(const float*, long long, int, int, bf16*, long long, bf16*, long long, cudaStream_t);
-int patch_gather_dispatch(const float*, bf16*, int, int, cudaStream_t);
+int patch_gather_dispatch(const float*, bf16*, int, int, int, cudaStream_t);
 int embed_dispatch(const long long*, int, int, int, int, const float*, const float*, const float*, bf16*, long long,
                    cudaStream_t);
 int embed_scatter_dispatch(const long long*, int, int, int, int, const bf16*, long long, float*, float*, cudaStream_t);
@@ -316,7 +316,10 @@ int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void
   return fiber::cast_transpose_dispatch(w, ldw, n, k, FIBER_BM(w_out), ld_out, FIBER_BM(wt_out), ldt_out, FIBER_S(s));
 }
 int fiber_patch_gather(const float* img, void* out, int32_t batch, int32_t r, fiber_stream_t s) {
-  return fiber::patch_gather_dispatch(img, FIBER_BM(out), batch, r, FIBER_S(s));
+  return fiber::patch_gather_dispatch(img, FIBER_BM(out), batch, r, r, FIBER_S(s));
+}
+int fiber_patch_gather_hw(const float* img, void* out, int32_t batch, int32_t h, int32_t w, fiber_stream_t s) {
+  return fiber::patch_gather_dispatch(img, FIBER_BM(out), batch, h, w, FIBER_S(s));
 }
 int fiber_embed_gather(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const float* word,
                        const float* pos, const float* type, void* out, int64_t ldo, fiber_stream_t s) {

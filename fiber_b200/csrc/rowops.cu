@@ -883,11 +883,11 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* w, lon
 
 // PatchEmbed gather (timm PatchEmbed conv 4x4/s4 as a GEMM, fiber_module.py:311):
 // img f32 [B,3,R,R] -> patches bf16 [B*(R/4)^2, 64]; column = c*16 + kh*4 + kw, columns 48..63 = 0.
-__global__ void __launch_bounds__(256) patch_gather_kernel(const float* img, bf16* out, int B, int R) {
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float* img, bf16* out, int B, int RH, int R) {
   pdl_trigger();
   pdl_wait();
-  const int P = R / 4;
-  const long long total = static_cast<long long>(B) * P * P * 16;
+  const int P = R / 4, PH = RH / 4;  // patches per row / per column (the image is RH x R)
+  const long long total = static_cast<long long>(B) * PH * P * 16;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int j = static_cast<int>(i & 15);
@@ -895,9 +895,9 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* img, bf1
     uint2 o = make_uint2(0u, 0u);
     if (j < 12) {
       const int c = j >> 2, kh = j & 3;
-      const int pw = static_cast<int>(patch % P), ph = static_cast<int>((patch / P) % P);
-      const long long b = patch / (P * P);
-      const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * R + (ph * 4 + kh)) * R + pw * 4);
+      const int pw = static_cast<int>(patch % P), ph = static_cast<int>((patch / P) % PH);
+      const long long b = patch / (static_cast<long long>(P) * PH);
+      const float4 v = *reinterpret_cast<const float4*>(img + ((b * 3 + c) * RH + (ph * 4 + kh)) * R + pw * 4);
       o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     }
     *reinterpret_cast<uint2*>(out + patch * 64 + j * 4) = o;
@@ -1041,9 +1041,9 @@ int cast_transpose_dispatch(const float* w, long long ldw, int N, int K, bf16* w
   return 0;
 }
 
-int patch_gather_dispatch(const float* img, bf16* out, int B, int R, cudaStream_t stream) {
-  FIBER_CHECK(B > 0 && R % 4 == 0, "patch_gather: image size must be a multiple of 4");
-  FIBER_CUDA(launch_k(patch_gather_kernel, dim3(ew_grid(static_cast<long long>(B) * (R / 4) * (R / 4) * 16)), dim3(256), 0, stream, img, out, B, R));
+int patch_gather_dispatch(const float* img, bf16* out, int B, int RH, int R, cudaStream_t stream) {
+  FIBER_CHECK(B > 0 && R > 0 && RH > 0 && R % 4 == 0 && RH % 4 == 0, "patch_gather: image height and width must be multiples of 4");
+  FIBER_CUDA(launch_k(patch_gather_kernel, dim3(ew_grid(static_cast<long long>(B) * (RH / 4) * (R / 4) * 16)), dim3(256), 0, stream, img, out, B, RH, R));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -361,13 +361,14 @@ def cast_transpose(w, w_out=None, wt_out=None):
 
 
 def patch_gather(img):
+    """im2row of the 4x4 / stride-4 patch embedding: fp32 [B,3,H,W] -> bf16 [B*(H/4)*(W/4), 64] (48 values + zero pad)."""
     _req(img, F32, "img")
     img = img.contiguous()
-    b, ch, r, r2 = img.shape
-    if ch != 3 or r != r2:
-        raise RuntimeError("fiber_b200.patch_gather expects [B,3,R,R]")
-    out = torch.empty((b * (r // 4) ** 2, 64), device=img.device, dtype=BF16)
-    _lib.check(_lib.load().fiber_patch_gather(img.data_ptr(), out.data_ptr(), b, r, _stream()), "patch_gather")
+    b, ch, h, w = img.shape
+    if ch != 3 or h % 4 or w % 4:
+        raise RuntimeError("fiber_b200.patch_gather expects [B,3,H,W] with H and W multiples of 4")
+    out = torch.empty((b * (h // 4) * (w // 4), 64), device=img.device, dtype=BF16)
+    _lib.check(_lib.load().fiber_patch_gather_hw(img.data_ptr(), out.data_ptr(), b, h, w, _stream()), "patch_gather")
     return out
 
 

@@ -352,13 +352,13 @@ class LayerNormFn(torch.autograd.Function):
 class PatchEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, proj_w, proj_b, norm_w, norm_b):
-        B, _, R, _ = img.shape
+        B, _, RH, RW = img.shape
         patches = K.patch_gather(img.float())
         w, _ = CACHE.weights((proj_w,), need_t=False, pad_k=64)
         e = K.gemm(patches, w, bias=proj_b.detach())
         x, mean, rstd, _ = K.layernorm_fwd(e, norm_w.detach(), norm_b.detach(), LN_EPS)
         ctx.saved = (patches, e, mean, rstd, norm_w.detach(), proj_w.shape)
-        return x.view(B, (R // 4) ** 2, proj_w.shape[0])
+        return x.view(B, (RH // 4) * (RW // 4), proj_w.shape[0])
 
     @staticmethod
     def backward(ctx, dx):
@@ -521,6 +521,89 @@ class SwinBlockFn(torch.autograd.Function):
                              dgamma=g["norm1.weight"], dbeta=g["norm1.bias"])
         ctx.sv = None
         return (dx.view(B, T, C), dtext, None, None, None, None) + tuple(g[n] for n in names)
+
+
+# ---------------------------------------------------------------------------------------------
+# Composable pieces (fine-grained fused backbone, modules/fusion_swin_fg.py): the same kernels as SwinBlockFn behind
+# one autograd Function each, so that padding / cropping of ragged window grids can sit between them as torch ops
+# ---------------------------------------------------------------------------------------------
+class WindowAttnFn(torch.autograd.Function):
+    """W-MSA / SW-MSA on image-ordered tokens: qkv [B*H*W, 3C] bf16 -> [B*H*W, C]; H and W multiples of the window
+    (fusion_swin_transformer_v2.py:148-186 with the roll / partition / reverse of :316-338 as index math)."""
+
+    @staticmethod
+    def forward(ctx, qkv, table, geom, nh):
+        B, H, W, ws, shift = geom
+        C = qkv.shape[1] // 3
+        hd = C // nh
+        scale = hd ** -0.5
+        tab = table.detach()
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+        o, lse = K.attn_fwd(q, k, v, nh, hd, scale, window=(B, H, W, ws, shift), bias_table=tab)
+        ctx.saved = (qkv, o, lse, tab, geom, nh)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse, tab, geom, nh = ctx.saved
+        C = qkv.shape[1] // 3
+        hd = C // nh
+        dqkv = torch.empty_like(qkv)
+        dtab = torch.zeros_like(tab)
+        K.attn_bwd(_to_bf16_2d(do), qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, nh, hd, hd ** -0.5,
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dbias_table=dtab, window=geom, bias_table=tab)
+        return dqkv, dtab, None, None
+
+
+class CrossAttnFn(torch.autograd.Function):
+    """Plain attention of q [G*Lq, C] against packed kv [G*Lk, 2C] with an additive key mask [G, Lk] (image -> text,
+    fusion_swin_transformer_v2.py:188-222)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, key_mask, G, Lq, Lk, nh):
+        C = q.shape[1]
+        hd = C // nh
+        km = None if key_mask is None else key_mask.contiguous()
+        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], nh, hd, hd ** -0.5, groups=G, lq=Lq, lk=Lk, key_mask=km)
+        ctx.saved = (q, kv, o, lse, km, G, Lq, Lk, nh)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse, km, G, Lq, Lk, nh = ctx.saved
+        C = q.shape[1]
+        hd = C // nh
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        K.attn_bwd(_to_bf16_2d(do), q, kv[:, :C], kv[:, C:], o, lse, nh, hd, hd ** -0.5, dq, dkv[:, :C], dkv[:, C:],
+                   groups=G, lq=Lq, lk=Lk, key_mask=km)
+        return dq, dkv, None, None, None, None, None
+
+
+class MlpFn(torch.autograd.Function):
+    """fc2(GELU(fc1(x))) with the GELU (and the GELU' cache) in the fc1 epilogue and GELU' in the fc2-dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = _to_bf16_2d(x)
+        w1b, w1t = CACHE.weights((w1,))
+        h = torch.empty((x2.shape[0], w1.shape[0]), device=x2.device, dtype=BF16)
+        a, cached = _fc1_gelu(x2, w1b, b1.detach(), h)
+        w2b, w2t = CACHE.weights((w2,))
+        out = K.gemm(a, w2b, bias=b2.detach())
+        ctx.saved = (x2, h, a, cached, w1t, w2t, x.shape)
+        return out.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, h, a, cached, w1t, w2t, xshape = ctx.saved
+        dz = _to_bf16_2d(dout)
+        db2 = torch.zeros(dz.shape[1], device=dz.device, dtype=F32)
+        dw2 = _wgrad(dz, a, db=db2)
+        dh = _fc2_dgrad_gelu(dz, w2t, h, cached)
+        db1 = torch.zeros(dh.shape[1], device=dz.device, dtype=F32)
+        dw1 = _wgrad(dh, x2, db=db1)
+        dx = K.gemm(dh, w1t).view(xshape)
+        return dx, dw1, db1, dw2, db2
 
 
 # ---------------------------------------------------------------------------------------------

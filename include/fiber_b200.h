@@ -244,6 +244,9 @@ int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void
                          int64_t ldt_out, fiber_stream_t stream);
 /* timm PatchEmbed im2row: img fp32 [B,3,R,R] -> bf16 [B*(R/4)^2, 64], col = c*16+kh*4+kw, cols 48..63 zero */
 int fiber_patch_gather(const float* img, void* out, int32_t batch, int32_t r, fiber_stream_t stream);
+/* the same for rectangular images [B,3,H,W], H % 4 == 0 and W % 4 == 0 (fine-grained model: PatchEmbed of
+ * fine_grained/maskrcnn_benchmark/modeling/backbone/fusion_swin_transformer_v2.py:548-566 after its padding) */
+int fiber_patch_gather_hw(const float* img, void* out, int32_t batch, int32_t h, int32_t w, fiber_stream_t stream);
 /* RobertaEmbeddings sum (roberta.py:169-196): out[t] = word[ids[t]] + pos[pos_id(t)] + type[0] */
 int fiber_embed_gather(const int64_t* ids, int32_t batch, int32_t len, int32_t c, int32_t pad_id, const float* word,
                        const float* pos, const float* type, void* out, int64_t ldo, fiber_stream_t stream);
