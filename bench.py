@@ -165,6 +165,87 @@ def measure_extra_config(name, dev, steps=3, warmup=3):
             "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
 
 
+def measure_fg_backbone(dev, B=8, Hi=800, Wi=1344, L=256, steps=3, warmup=2):
+    """BASELINE configs[4] (fine-grained grounding, 800 px short side, 8 images / GPU), the part of it that is this repo's
+    path: forward + backward of the FUSED BACKBONE (fiber_b200.modules.fusion_swin_fg — Swin-B over
+    800 x 1344 images with padded 12 x 12 windows, roberta-base over 256 query tokens, 6 fused pairs) under a probe loss on
+    its outputs; FPN / DyHead / detection losses are not part of it.  Next to it: the UNMODIFIED reference modules
+    (baseline/ref_fg.py) in PyTorch eager under bf16 autocast on the same GPU, same inputs and loss."""
+    import gc
+    import types
+    from fiber_b200.modules import fusion_swin_fg as M
+    g = torch.Generator(device="cpu").manual_seed(77)
+    img = torch.randn(B, 3, Hi, Wi, generator=g).to(dev)
+    ids = torch.randint(3, 50265, (B, L), generator=g)
+    ids[:, 0] = 0
+    mask = torch.ones(B, L, dtype=torch.long)
+    for b in range(B):  # grounding captions are short: 20 .. 60 real tokens of the 256-token query
+        n = int(torch.randint(20, 60, (1,), generator=g))
+        ids[b, n - 1] = 2
+        ids[b, n:] = 1
+        mask[b, n:] = 0
+    tok = {"input_ids": ids.to(dev), "attention_mask": mask.to(dev)}
+
+    def timed(model, autocast):
+        def step():
+            for p in model.parameters():
+                p.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                outs, lang, _ = model(tok, types.SimpleNamespace(tensors=img))
+            loss = sum(o.float().mean() for o in outs) + lang["hidden"].float().mean()
+            loss.backward()
+            return loss
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, float(loss.detach())
+
+    torch.manual_seed(1234)
+    torch.cuda.reset_peak_memory_stats()
+    model = M.FusionSwinTransformer(M.SwinTransformer(drop_path_rate=0.2)).to(dev).train()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith(("alpha_i2t", "alpha_t2i")):
+                p.fill_(0.5)
+    ms, loss = timed(model, False)
+    out = {"value": B / ms * 1e3, "unit": "images/s", "ms_per_step": ms, "per_gpu_batch": B, "image": [Hi, Wi], "text_len": L,
+           "what": "fused backbone fwd+bwd (Swin-B + roberta-base, 6 fused pairs), probe loss; FPN / DyHead not included",
+           "steps": steps, "warmup": warmup, "last_loss": loss,
+           "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    try:
+        from baseline import ref_fg
+        if not ref_fg.available():
+            raise RuntimeError("baseline/_ref/fine_grained not installed")
+        torch.manual_seed(1234)
+        torch.cuda.reset_peak_memory_stats()
+        ref, _swin, _rob = ref_fg.build(drop_path_rate=0.2)
+        ref = ref.to(dev).train()
+        with torch.no_grad():
+            for n, p in ref.named_parameters():
+                if n.endswith(("alpha_i2t", "alpha_t2i")):
+                    p.fill_(0.5)
+        rms, rloss = timed(ref, True)
+        out["eager_reference"] = {"value": B / rms * 1e3, "unit": "images/s", "ms_per_step": rms, "dtype": "bf16 autocast",
+                                  "impl": "unmodified reference modules (baseline/_ref/fine_grained), PyTorch eager",
+                                  "last_loss": rloss, "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                                  "ours_over_eager": rms / ms}
+        del ref
+    except Exception as e:  # noqa: BLE001
+        out["eager_reference"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def to_device(batch, dev, non_blocking=True):
     out = {}
     for k, v in batch.items():
@@ -612,6 +693,10 @@ def run_ours(args):
             import gc
             gc.collect()
             torch.cuda.empty_cache()
+        try:  # configs[4]: the fused backbone of the fine-grained model
+            line["extra_configs"]["fg800_backbone"] = measure_fg_backbone(dev)
+        except Exception as e:  # noqa: BLE001
+            line["extra_configs"]["fg800_backbone"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if world == 1 and args.eager_baseline:
         # the north-star's denominator: the reference PyTorch-eager GPU path, timed in this process after our arm
         line["eager_gpu_baseline"] = eager_gpu_baseline(args, dev, host, value)

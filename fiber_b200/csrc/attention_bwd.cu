@@ -389,6 +389,16 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
 }
 
 
+// shared memory the backward needs for (Lq, Lk) in a given configuration (same formula as launch_bwd)
+template <int HD, int NW, int SK>
+static size_t bwd_smem_bytes(const AttnParams& p) {
+  constexpr int QROWS = 16 * NW, SP = SK + 8, PITCH = HD + 8;
+  const int nqc = (p.Lq + QROWS - 1) / QROWS, nkc = (p.Lk + SK - 1) / SK;
+  const size_t base = (2 * QROWS + 2 * SK) * PITCH * 2 + 2 * QROWS * SP * 2 + (2 * QROWS + SK) * 4 + 2 * ATT_MAXTBL * 4 +
+                      ATT_MAXTOK * 4 + 3 * ATT_MAXTOK + 32;
+  return base + ((nqc > 1 && nkc > 1) ? static_cast<size_t>(nqc) * QROWS * HD * 4 : 0);
+}
+
 template <int HD, bool WINDOW, int NW = 9, int SK = ATT_SKEYS>
 static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   constexpr int BW_NWARPS = NW;
@@ -459,6 +469,13 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
   if (hd == 64 && p.Lq <= 48 && p.Lk > 48 && (option_attn_small() & 4)) return launch_bwd<64, false, 3, 48>(p, stream);
   // opt-in (bit 1): few keys, many queries (i2t: 576 / 144 queries x 40 text tokens) on 4-warp CTAs, three per SM
   if (hd == 32 && p.Lk <= 48 && p.Lq > 48 && (option_attn_small() & 2)) return launch_bwd<32, false, 4, 48>(p, stream);
+  // many queries AND many keys (fine-grained t2i: 256 query tokens x 4200 / 1050 image keys): the fp32 dQ accumulator of
+  // all query chunks lives in shared memory next to the tiles; where the 9-warp / 144-key tiles leave no room for it, the
+  // small-tile configurations do
+  if (hd == 64 && bwd_smem_bytes<64, 9, ATT_SKEYS>(p) > 227 * 1024 && bwd_smem_bytes<64, 3, 48>(p) <= 227 * 1024)
+    return launch_bwd<64, false, 3, 48>(p, stream);
+  if (hd == 32 && bwd_smem_bytes<32, 9, ATT_SKEYS>(p) > 227 * 1024 && bwd_smem_bytes<32, 4, 48>(p) <= 227 * 1024)
+    return launch_bwd<32, false, 4, 48>(p, stream);
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);
 }
 

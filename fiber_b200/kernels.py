@@ -220,8 +220,36 @@ def attn_fwd(q, k, v, heads, head_dim, scale, **kw):
     return o, lse
 
 
+def _attn_bwd_key_chunks(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, kw):
+    """Plain attention backward with MANY queries and MANY keys per group (fine-grained i2t: 5040 / 1728 image queries x a
+    256-token text query): the kernels keep the fp32 dQ accumulator of every query chunk in shared memory while they walk
+    the key chunks, which does not fit there.  The softmax statistics (lse) are global, so the backward is exact per key
+    chunk: run it once per chunk of <= 144 keys (contiguous copies of the few key / value rows), add the dQ parts, scatter
+    the dK / dV parts.  No dropout (the keep-mask hash indexes keys by the full row length)."""
+    G, Lq, Lk = kw["groups"], kw["lq"], kw["lk"]
+    if kw.get("drop_p", 0.0):
+        raise RuntimeError("fiber_b200.attn_bwd: dropout with > 144 queries and > 144 keys per group is not supported")
+    Ck = k.shape[1]
+    k3, v3 = k.reshape(G, Lk, Ck), v.reshape(G, Lk, Ck)
+    km = kw.get("key_mask")
+    acc = None
+    for c0 in range(0, Lk, 144):
+        c1 = min(Lk, c0 + 144)
+        kc, vc = k3[:, c0:c1].reshape(G * (c1 - c0), Ck).contiguous(), v3[:, c0:c1].reshape(G * (c1 - c0), Ck).contiguous()
+        dkc, dvc, dqc = torch.empty_like(kc), torch.empty_like(vc), torch.empty_like(dq, memory_format=torch.contiguous_format)
+        kw_c = dict(kw, lk=c1 - c0, key_mask=None if km is None else km[:, c0:c1].contiguous())
+        attn_bwd(d_o, q, kc, vc, o, lse, heads, head_dim, scale, dqc, dkc, dvc, **kw_c)
+        acc = dqc.float() if acc is None else acc.add_(dqc)
+        for dst, part in ((dk, dkc), (dv, dvc)):  # dk / dv may be column slices of a packed [G Lk, 2C] buffer
+            dst.unflatten(0, (G, Lk))[:, c0:c1] = part.view(G, c1 - c0, Ck)
+    dq.copy_(acc)
+
+
 def attn_bwd(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, dbias_table=None, **kw):
     """Writes dq/dk/dv (bf16 views with the layout of q/k/v); accumulates into dbias_table."""
+    if (kw.get("window") is None and kw.get("lq", 0) > 144 and kw.get("lk", 0) > 144
+            and kw["lq"] * head_dim * 4 > (96 << 10)):
+        return _attn_bwd_key_chunks(d_o, q, k, v, o, lse, heads, head_dim, scale, dq, dk, dv, kw)
     a = _attn_args(q, k, v, o, lse, heads, head_dim, scale, **kw)
     for name, t in (("d_o", d_o), ("dq", dq), ("dk", dk), ("dv", dv)):
         _req(t, BF16, name)

@@ -552,6 +552,8 @@ class WindowAttnFn(torch.autograd.Function):
         dtab = torch.zeros_like(tab)
         K.attn_bwd(_to_bf16_2d(do), qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, nh, hd, hd ** -0.5,
                    dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], dbias_table=dtab, window=geom, bias_table=tab)
+        ctx.saved = None  # `o` is this node's own output: drop the reference cycle node -> ctx -> o -> node now, not at the
+        # next cyclic GC (the step's activations would otherwise stay allocated and every step would cudaMalloc anew)
         return dqkv, dtab, None, None
 
 
@@ -576,6 +578,7 @@ class CrossAttnFn(torch.autograd.Function):
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         K.attn_bwd(_to_bf16_2d(do), q, kv[:, :C], kv[:, C:], o, lse, nh, hd, hd ** -0.5, dq, dkv[:, :C], dkv[:, C:],
                    groups=G, lq=Lq, lk=Lk, key_mask=km)
+        ctx.saved = None  # see WindowAttnFn
         return dq, dkv, None, None, None, None, None
 
 

@@ -268,6 +268,16 @@ def _plain_case(cuda_dev, B, nh, hd, Lq, Lk, masked):
     _close(dkv[:, C:].reshape(B, Lk, nh, hd).transpose(1, 2), vf.grad, 3e-2, "dv")
 
 
+@pytest.mark.parametrize("B,nh,hd,Lq,Lk", [(2, 12, 64, 256, 1050), (1, 12, 64, 256, 4200), (2, 16, 32, 300, 500),
+                                           (2, 32, 32, 1728, 256), (1, 16, 32, 5040, 200)])
+def test_plain_attention_many_queries_and_keys(cuda_dev, B, nh, hd, Lq, Lk):
+    """Fine-grained t2i shapes (256 query tokens x 4200 / 1050 image keys): several query chunks AND several key chunks —
+    the backward falls to the small-tile configuration that leaves room for the shared-memory dQ accumulator — and
+    fine-grained i2t shapes (5040 / 1728 image queries x a 256-token text query), where the wrapper runs the backward per
+    chunk of 144 keys."""
+    _plain_case(cuda_dev, B, nh, hd, Lq, Lk, False)
+
+
 def test_attention_dropout_statistics(cuda_dev):
     """Probability dropout: E[o] is unchanged, the mask is identical in forward and backward."""
     from fiber_b200 import kernels as K

@@ -5,7 +5,6 @@ baseline/ref_shims.py (+ two HF 4.6 -> 5.x aliases).  Weights / inputs are oracl
 so the oracle and the CUDA path rebuild the same tensors.  Writes tests/golden/fg_fused_backbone.pt.
     python tools/make_golden_fg.py
 """
-import importlib.util
 import os
 import sys
 import types
@@ -17,69 +16,12 @@ sys.path.insert(0, ROOT)
 from baseline import ref_shims  # noqa: E402
 from oracle import synth  # noqa: E402
 
-FG = "/root/reference/fine_grained/maskrcnn_benchmark/modeling/"
 NS = types.SimpleNamespace
 
 
-def load_reference():
-    ref_shims.install()
-    import transformers.modeling_utils as mu
-    import transformers.pytorch_utils as pu
-    if not hasattr(mu, "apply_chunking_to_forward"):
-        mu.apply_chunking_to_forward = pu.apply_chunking_to_forward
-
-    def load(name, path):
-        spec = importlib.util.spec_from_file_location(name, path)
-        m = importlib.util.module_from_spec(spec)
-        sys.modules[name] = m
-        spec.loader.exec_module(m)
-        return m
-    V = load("fg_swin_v2", FG + "backbone/fusion_swin_transformer_v2.py")
-    Lm = load("fg_roberta_v2", FG + "language_backbone/roberta_fused_model_v2.py")
-
-    def init_weights(self):
-        self.apply(self._init_weights)
-
-    def get_extended_attention_mask(self, attention_mask, input_shape=None, device=None):  # HF 4.6 semantics
-        return (1.0 - attention_mask[:, None, None, :].to(dtype=torch.float32)) * -10000.0
-    Lm.RobertaModel.init_weights = init_weights
-    Lm.RobertaModel.get_extended_attention_mask = get_extended_attention_mask
-    return V, Lm
-
-
-def build(V, Lm):
-    from transformers.models.roberta.configuration_roberta import RobertaConfig
-    cfg = RobertaConfig(vocab_size=50265, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
-                        hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
-                        max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1, bos_token_id=0,
-                        eos_token_id=2)
-    cfg.position_embedding_type = "absolute"
-    cfg.chunk_size_feed_forward = 0
-    cfg.is_decoder = False
-    cfg.add_cross_attention = False
-    rob = Lm.RobertaModel(cfg, add_pooling_layer=False)
-    swin = V.SwinTransformer(patch_size=4, in_chans=3, embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32],
-                             window_size=12, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
-                             drop_path_rate=0.0, norm_layer=torch.nn.LayerNorm, ape=False, patch_norm=True, frozen_stages=-1,
-                             backbone_arch="SWINT-FPN-RETINANET", use_checkpoint=False,
-                             out_features=["stage2", "stage3", "stage4", "stage5"], max_query_len=256, lang_dim=768)
-
-    class LangBody(torch.nn.Module):
-        def __init__(self, model):
-            super().__init__()
-            self.model = model
-            self.cfg = NS(MODEL=NS(DYHEAD=NS(FUSE_CONFIG=NS(USE_DOT_PRODUCT_TOKEN_LOSS=True)),
-                                   LANGUAGE_BACKBONE=NS(LANG_DIM=768)))
-        get_aggregated_output = Lm.RobertaFusedEncoder.get_aggregated_output
-
-    class Wrap(torch.nn.Module):
-        def __init__(self, body):
-            super().__init__()
-            self.body = body
-
-        def fpn(self, outs):  # the FPN is out of scope: the fixture holds its inputs
-            return outs
-    fusion = V.FusionSwinTransformer(Wrap(swin), Wrap(LangBody(rob)))
+def build():
+    from baseline import ref_fg
+    fusion, swin, rob = ref_fg.build(drop_path_rate=0.0)
     # synthetic weights by (coarse-oracle style) name
     shapes = {}
     for k, v in swin.state_dict().items():
@@ -108,8 +50,7 @@ def inputs(B, Hi, Wi, L, seed=4242):
 
 
 def main():
-    V, Lm = load_reference()
-    fusion, sd, shapes = build(V, Lm)
+    fusion, sd, shapes = build()
     gold = {"cases": {}}
     for name, (B, Hi, Wi, L) in {"pad_224x320": (2, 224, 320, 20), "nopad_384x384": (1, 384, 384, 12)}.items():
         img, ids, mask = inputs(B, Hi, Wi, L)
