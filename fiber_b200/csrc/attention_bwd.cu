@@ -472,8 +472,11 @@ int attn_bwd_dispatch(const AttnParams& p, int hd, float* d_scratch, cudaStream_
   // many queries AND many keys (fine-grained t2i: 256 query tokens x 4200 / 1050 image keys): the fp32 dQ accumulator of
   // all query chunks lives in shared memory next to the tiles; where the 9-warp / 144-key tiles leave no room for it, the
   // small-tile configurations do
-  if (hd == 64 && bwd_smem_bytes<64, 9, ATT_SKEYS>(p) > 227 * 1024 && bwd_smem_bytes<64, 3, 48>(p) <= 227 * 1024)
-    return launch_bwd<64, false, 3, 48>(p, stream);
+  if (hd == 64 && bwd_smem_bytes<64, 9, ATT_SKEYS>(p) > 227 * 1024) {
+    // 144 query rows per chunk with 48-key staging first (a third of the chunk iterations of the 48 x 48 form)
+    if (bwd_smem_bytes<64, 9, 48>(p) <= 227 * 1024) return launch_bwd<64, false, 9, 48>(p, stream);
+    if (bwd_smem_bytes<64, 3, 48>(p) <= 227 * 1024) return launch_bwd<64, false, 3, 48>(p, stream);
+  }
   if (hd == 32 && bwd_smem_bytes<32, 9, ATT_SKEYS>(p) > 227 * 1024 && bwd_smem_bytes<32, 4, 48>(p) <= 227 * 1024)
     return launch_bwd<32, false, 4, 48>(p, stream);
   return hd == 32 ? launch_bwd<32, false>(p, stream) : launch_bwd<64, false>(p, stream);
