@@ -1,0 +1,121 @@
+// fiber_b200 — image side of the input pipeline on the GPU (include/fiber_b200.h: fiber_image_transform).
+//
+// A batch of decoded, ragged RGB byte images -> the normalised float32 NCHW batch FIBERTransformerSS.infer consumes
+// (coarse_grained/fiber/modules/fiber_module.py:237-241), with the arithmetic of the reference's per-image CPU
+// transform (transforms/transform.py:10-17: PIL bicubic Resize, ToTensor, Normalize) reproduced bit for bit.
+// HBM-bound byte work: per image the source box is read once (3 box_w box_h bytes), the horizontally resampled byte
+// planes (3 box_h out_w bytes, L2-resident for a batch) written and read once, and 12 out_h out_w bytes written.
+// Three launches per batch, grids sized by the largest image of the batch; per-element bodies live in
+// image_resample.cuh so that the CPU test-suite can replay them.
+#include "common.cuh"
+#include "image_resample.cuh"
+
+namespace fiber {
+void count_launch(int n);
+
+namespace img {
+
+struct Norm {
+  float mean[3], stdv[3];
+};
+
+__global__ void __launch_bounds__(128) image_coeffs_kernel(const fiber_image_desc* descs, void* ws, int out_h, int out_w) {
+  pdl_trigger();
+  pdl_wait();
+  coeffs_body(descs, ws, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256) image_hpass_kernel(const fiber_image_desc* descs, void* ws, int out_h, int out_w) {
+  pdl_trigger();
+  pdl_wait();
+  hpass_body(descs, ws, out_h, out_w, blockIdx.y, static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256) image_vpass_kernel(const fiber_image_desc* descs, const void* ws, Norm norm, float* out,
+                                                          int out_h, int out_w) {
+  __shared__ float lut[3 * 256];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = normalize_one(i & 255, norm.mean[i >> 8], norm.stdv[i >> 8]);
+  __syncthreads();
+  pdl_wait();
+  vpass_body(descs, ws, lut, out, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace img
+}  // namespace fiber
+
+extern "C" {
+
+size_t fiber_image_transform_plan(fiber_image_desc* d, int32_t n, int32_t out_h, int32_t out_w) {
+  using namespace fiber::img;
+  if (!d || n <= 0 || out_h <= 0 || out_w <= 0 || (out_w & 3)) {
+    fiber::set_last_error("image_transform_plan: need n > 0, out_h > 0, out_w > 0 and out_w %% 4 == 0");
+    return 0;
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    fiber_image_desc& e = d[i];
+    if (!e.src || e.h <= 0 || e.w <= 0 || e.stride < 3LL * e.w || e.box_w <= 0 || e.box_h <= 0 || e.box_x < 0 || e.box_y < 0 ||
+        e.box_x + e.box_w > e.w || e.box_y + e.box_h > e.h) {
+      fiber::set_last_error("image_transform_plan: image %d: bad size, stride or crop box", i);
+      return 0;
+    }
+    if (e.box_h > 100LL * e.box_w && out_h < e.box_h) {
+      fiber::set_last_error("image_transform_plan: image %d: box taller than 100x its width (Pillow resamples rows first there)", i);
+      return 0;
+    }
+    e.ksize_x = ksize_for(e.box_w, out_w);
+    e.ksize_y = ksize_for(e.box_h, out_h);
+    e.reserved = 0;
+    e.coef_off = static_cast<int64_t>(off);
+    off = align_up(off + static_cast<size_t>(table_ints(e, out_h, out_w)) * sizeof(int32_t), 16);
+  }
+  for (int i = 0; i < n; ++i) {
+    d[i].tmp_off = static_cast<int64_t>(off);
+    off = align_up(off + 3ull * d[i].box_h * tmp_pitch(out_w), 16);
+  }
+  return off;
+}
+
+int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd, int32_t n, int32_t out_h, int32_t out_w,
+                          const float* mean, const float* stdv, void* ws, size_t ws_bytes, float* out, fiber_stream_t s) {
+  using namespace fiber::img;
+  cudaStream_t stream = static_cast<cudaStream_t>(s);
+  FIBER_CHECK(dh && dd && n > 0 && out_h > 0 && out_w > 0 && (out_w & 3) == 0 && mean && stdv && ws && out,
+              "image_transform: null argument, n <= 0 or out_w %% 4 != 0");
+  FIBER_CHECK((reinterpret_cast<uintptr_t>(ws) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "image_transform: workspace and out must be 16-byte aligned");
+  FIBER_CHECK(n <= 65535, "image_transform: at most 65535 images per call");
+  int max_box_h = 0;
+  size_t need = 0;
+  for (int i = 0; i < n; ++i) {
+    const fiber_image_desc& e = dh[i];
+    FIBER_CHECK(e.ksize_x == ksize_for(e.box_w, out_w) && e.ksize_y == ksize_for(e.box_h, out_h) && e.coef_off >= 0 &&
+                    e.tmp_off >= 0,
+                "image_transform: descriptor %d was not planned for this output size (fiber_image_transform_plan)", i);
+    max_box_h = e.box_h > max_box_h ? e.box_h : max_box_h;
+    const size_t end = static_cast<size_t>(e.tmp_off) + 3ull * e.box_h * tmp_pitch(out_w);
+    need = end > need ? end : need;
+  }
+  FIBER_CHECK(ws_bytes >= need, "image_transform: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  Norm norm;
+  for (int c = 0; c < 3; ++c) {
+    norm.mean[c] = mean[c];
+    norm.stdv[c] = stdv[c];
+  }
+  const dim3 g1((out_w + out_h + 127) / 128, n);
+  FIBER_CUDA(fiber::launch_k(image_coeffs_kernel, g1, dim3(128), 0, stream, dd, ws, out_h, out_w));
+  const long long hwork = static_cast<long long>((max_box_h + kRowsPerThread - 1) / kRowsPerThread) * out_w;
+  const dim3 g2(static_cast<unsigned>((hwork + 255) / 256), n);
+  FIBER_CUDA(fiber::launch_k(image_hpass_kernel, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
+  const long long vwork = 3LL * out_h * (out_w / 4);
+  const dim3 g3(static_cast<unsigned>((vwork + 255) / 256), n);
+  FIBER_CUDA(fiber::launch_k(image_vpass_kernel, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), norm, out, out_h,
+                             out_w));
+  fiber::count_launch(3);
+  return 0;
+}
+
+}  // extern "C"

@@ -77,6 +77,16 @@ class LnArgs(C.Structure):
     ]
 
 
+class ImageDesc(C.Structure):
+    """Mirror of `fiber_image_desc` (include/fiber_b200.h)."""
+    _fields_ = [
+        ("src", C.c_void_p), ("stride", C.c_int64), ("h", C.c_int32), ("w", C.c_int32),
+        ("box_x", C.c_int32), ("box_y", C.c_int32), ("box_w", C.c_int32), ("box_h", C.c_int32),
+        ("flip", C.c_int32), ("ksize_x", C.c_int32), ("ksize_y", C.c_int32), ("reserved", C.c_int32),
+        ("coef_off", C.c_int64), ("tmp_off", C.c_int64),
+    ]
+
+
 def declared_symbols():
     """Every `fiber_*` function declared in include/fiber_b200.h (parsed from the header)."""
     import re
@@ -120,6 +130,10 @@ def load():
     lib.fiber_embed_gather.argtypes = [V, I32, I32, I32, I32, V, V, V, V, I64, V]
     lib.fiber_embed_scatter.argtypes = [V, I32, I32, I32, I32, V, I64, V, V, V]
     lib.fiber_adamw_multi.argtypes = [V, V, I32, I32, F, F, F, I32, V]
+    lib.fiber_image_transform_plan.restype = C.c_size_t
+    lib.fiber_image_transform_plan.argtypes = [C.POINTER(ImageDesc), I32, I32, I32]
+    lib.fiber_image_transform.argtypes = [C.POINTER(ImageDesc), V, I32, I32, I32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                          V, C.c_size_t, V, V]
     _lib = lib
     return lib
 

@@ -273,6 +273,38 @@ typedef struct fiber_adamw_tensor {
 int fiber_adamw_multi(const void* tensors, const void* chunks, int32_t n_chunks, int32_t chunk_elems, float beta1, float beta2,
                       float eps, int32_t step, fiber_stream_t stream);
 
+/* ---- image side of the input pipeline --------------------------------------
+ * Replaces, per batch instead of per image in DataLoader workers, what the reference's `albef` transform and the
+ * geometric part of `albef_randaug` do to a decoded RGB image (coarse_grained/fiber/transforms/transform.py:10-17 and
+ * :20-24,42-44; called from datasets/base_dataset.py:93-110 get_raw_image / get_image / get_false_image):
+ *   [crop box -> ] PIL Image.resize((out_w, out_h), BICUBIC) [-> horizontal flip] -> ToTensor -> Normalize(mean, std)
+ * with the libraries' own arithmetic, bit for bit: Pillow's 8-bit two-pass resampling (horizontal pass first, 22-bit
+ * fixed-point coefficients evaluated in double precision, each pass rounded and clamped to a byte) and torchvision's
+ * float32 (v / 255 - mean) / std.  JPEG decoding and RandomAugment's photometric / affine operations stay with the caller.
+ *
+ * One fiber_image_desc per image.  The caller fills src .. flip; fiber_image_transform_plan (host only, no CUDA call)
+ * fills the rest and returns the workspace size in bytes (0 on error).  Images are ragged: every descriptor has its own
+ * size, row stride and crop box.  Pillow >= 11 resamples the vertical axis first when h > 100 w; such boxes are rejected. */
+typedef struct fiber_image_desc {
+  const uint8_t* src;                  /* DEVICE pointer: row 0, column 0 of the decoded image, RGB interleaved */
+  int64_t stride;                      /* bytes between source rows (>= 3 w) */
+  int32_t h, w;                        /* decoded size */
+  int32_t box_x, box_y, box_w, box_h;  /* crop (torchvision resized_crop: left, top, width, height); whole image = 0,0,w,h */
+  int32_t flip;                        /* 1: RandomHorizontalFlip applied after the resize */
+  int32_t ksize_x, ksize_y;            /* plan: taps per output sample, horizontal / vertical */
+  int32_t reserved;
+  int64_t coef_off;                    /* plan: byte offset of this image's coefficient tables in the workspace */
+  int64_t tmp_off;                     /* plan: byte offset of its horizontally resampled byte planes [3][box_h][pitch] */
+} fiber_image_desc;
+size_t fiber_image_transform_plan(fiber_image_desc* descs_host, int32_t n, int32_t out_h, int32_t out_w);
+/* descs_host: the planned descriptors (read on the host for grid sizes); descs_dev: a DEVICE copy of the same array;
+ * mean / std: HOST float[3]; out: DEVICE float32 [n, 3, out_h, out_w] (16-byte aligned, out_w % 4 == 0);
+ * workspace: DEVICE, at least the planned size, 16-byte aligned.  Three launches: coefficient tables, horizontal pass
+ * (bytes -> byte planes), vertical pass + normalisation. */
+int fiber_image_transform(const fiber_image_desc* descs_host, const fiber_image_desc* descs_dev, int32_t n, int32_t out_h,
+                          int32_t out_w, const float* mean, const float* std, void* workspace, size_t workspace_bytes,
+                          float* out, fiber_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

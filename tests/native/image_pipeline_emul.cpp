@@ -1,0 +1,34 @@
+// CPU replay of the image-transform kernels (fiber_b200/csrc/image_pipeline.cu) — TEST INFRASTRUCTURE, built with g++
+// and driven by tests/test_image_pipeline_cpu.py.  Includes the kernels' own per-element bodies
+// (fiber_b200/csrc/image_resample.cuh) and calls them for every (block, thread) index of the three launches, with the
+// launcher's grid arithmetic, on host memory.  Descriptors come planned from the real library
+// (fiber_image_transform_plan is host-only), so offsets and tap counts are the product's.
+#include <cstdint>
+#include <vector>
+
+#include "../../fiber_b200/csrc/image_resample.cuh"
+
+using namespace fiber::img;
+
+extern "C" int emul_image_transform(const fiber_image_desc* d, int n, int out_h, int out_w, const float* mean,
+                                    const float* stdv, void* ws, float* out) {
+  int max_box_h = 0;
+  for (int i = 0; i < n; ++i) max_box_h = d[i].box_h > max_box_h ? d[i].box_h : max_box_h;
+  std::vector<float> lut(3 * 256);
+  for (int i = 0; i < 3 * 256; ++i) lut[i] = normalize_one(i & 255, mean[i >> 8], stdv[i >> 8]);
+  const int g1 = (out_w + out_h + 127) / 128;
+  const long long hwork = static_cast<long long>((max_box_h + kRowsPerThread - 1) / kRowsPerThread) * out_w;
+  const long long g2 = (hwork + 255) / 256;
+  const long long vwork = 3LL * out_h * (out_w / 4);
+  const long long g3 = (vwork + 255) / 256;
+  for (int img = 0; img < n; ++img)
+    for (int b = 0; b < g1; ++b)
+      for (int t = 0; t < 128; ++t) coeffs_body(d, ws, out_h, out_w, img, b * 128 + t);
+  for (int img = 0; img < n; ++img)
+    for (long long b = 0; b < g2; ++b)
+      for (int t = 0; t < 256; ++t) hpass_body(d, ws, out_h, out_w, img, b * 256 + t);
+  for (int img = 0; img < n; ++img)
+    for (long long b = 0; b < g3; ++b)
+      for (int t = 0; t < 256; ++t) vpass_body(d, ws, lut.data(), out, out_h, out_w, img, static_cast<int>(b * 256 + t));
+  return 0;
+}

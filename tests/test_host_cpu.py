@@ -36,7 +36,7 @@ def test_ctypes_structs_match_header_field_order():
     from fiber_b200 import lib
     text = open(os.path.join(ROOT, "include", "fiber_b200.h")).read()
     for cname, cls in (("fiber_gemm_args", lib.GemmArgs), ("fiber_attn_args", lib.AttnArgs), ("fiber_ln_args", lib.LnArgs),
-               ("fiber_ce_args", lib.CeArgs)):
+               ("fiber_ce_args", lib.CeArgs), ("fiber_image_desc", lib.ImageDesc)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -58,7 +58,7 @@ def test_ctypes_struct_layout_matches_the_c_compiler(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
     structs = (("fiber_gemm_args", lib.GemmArgs), ("fiber_attn_args", lib.AttnArgs), ("fiber_ln_args", lib.LnArgs),
-               ("fiber_ce_args", lib.CeArgs))
+               ("fiber_ce_args", lib.CeArgs), ("fiber_image_desc", lib.ImageDesc))
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fiber_b200.h"', 'int main(void) {']
     for cname, cls in structs:
         lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

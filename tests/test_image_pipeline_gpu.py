@@ -1,0 +1,107 @@
+"""Image side of the input pipeline on the GPU, through fiber_b200.transforms -> the C-ABI
+(fiber_image_transform): bit-exact against the oracle and against the golden outputs of Pillow / torchvision."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import image_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "image_pipeline.npz"))
+CASES = [tuple(int(v) for v in c) for c in GOLD["cases"]]
+
+
+def _launches():
+    from fiber_b200 import lib
+    return lib.launch_count()
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_golden_cases(on_device):
+    from fiber_b200.transforms import BatchImageTransform
+    for s in sorted({c[2] for c in CASES}):
+        idx = [i for i, c in enumerate(CASES) if c[2] == s]
+        srcs = [GOLD["src_%d" % i] for i in idx]
+        boxes = [tuple(int(v) for v in GOLD["box_%d" % i][:4]) for i in idx]
+        flips = [int(GOLD["box_%d" % i][4]) for i in idx]
+        imgs = [torch.from_numpy(a).cuda() for a in srcs] if on_device else srcs
+        tr = BatchImageTransform(s)
+        before = _launches()
+        full = tr(imgs).cpu().numpy()
+        assert _launches() - before == 3
+        crop = tr(imgs, boxes=boxes, flips=flips).cpu().numpy()
+        for j, i in enumerate(idx):
+            assert np.array_equal(full[j], GOLD["albef_%d" % i]), ("albef", CASES[i])
+            assert np.array_equal(crop[j], GOLD["crop_%d" % i]), ("crop", CASES[i])
+
+
+def test_ragged_batch_vs_oracle_rectangular_output_and_strides():
+    from fiber_b200.transforms import BatchImageTransform
+    rng = np.random.default_rng(3)
+    sizes = [(97, 131), (48, 64), (64, 64), (7, 5), (211, 89), (30, 300), (64, 65), (1, 1), (130, 64), (500, 375)]
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    # device images as views into wider buffers: row stride > 3 w
+    wide = [torch.from_numpy(np.pad(a, ((0, 0), (0, 3 + i), (0, 0)))).cuda()[:, :a.shape[1]] for i, a in enumerate(images)]
+    for out_hw in [(64, 64), (96, 32), (40, 72)]:
+        tr = BatchImageTransform(out_hw)
+        for batch in (images, wide):
+            got = tr(batch).cpu().numpy()
+            for i, img in enumerate(images):
+                assert np.array_equal(got[i], O.albef_transform_hw(img, *out_hw)), (sizes[i], out_hw)
+
+
+def test_random_crop_same_seed_as_torchvision():
+    T = pytest.importorskip("torchvision.transforms")
+    Image = pytest.importorskip("PIL.Image")
+    from fiber_b200.transforms import albef_transform_randaug
+    rng = np.random.default_rng(8)
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(120, 160), (90, 60), (300, 200), (64, 64)]]
+    torch.manual_seed(21)
+    got = albef_transform_randaug(96)(images).cpu().numpy()
+    torch.manual_seed(21)
+    ref_tr = T.Compose([T.RandomResizedCrop(96, scale=(0.5, 1.0), interpolation=T.InterpolationMode.BICUBIC),
+                        T.RandomHorizontalFlip(), T.ToTensor(), T.Normalize(O.MEAN, O.STD)])   # transform.py:20-44 minus RandomAugment
+    for i, img in enumerate(images):
+        assert np.array_equal(got[i], ref_tr(Image.fromarray(img)).numpy()), i
+
+
+def test_full_size_batch_properties_and_buffer_reuse():
+    """BASELINE configs[1] input shape: 64 images -> 384 x 384.  Spot-checks against the oracle plus size-independent
+    properties: an image already at the output size passes through the look-up table untouched, a constant image stays
+    constant, and a second call that reuses the staging buffers gives the same bytes."""
+    from fiber_b200.transforms import albef_transform
+    rng = np.random.default_rng(1)
+    B, S = 64, 384
+    sizes = [(480, 640), (640, 480), (384, 384), (333, 500), (512, 512), (768, 1024), (240, 320), (427, 640)]
+    images = []
+    for i in range(B):
+        h, w = sizes[i % len(sizes)]
+        images.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if i != 5 else np.full((h, w, 3), (17, 130, 255), np.uint8))
+    tr = albef_transform(S)
+    out = torch.empty(B, 3, S, S, device="cuda")
+    got = tr(images, out=out)
+    assert got.data_ptr() == out.data_ptr()
+    got = got.cpu().numpy()
+    lut = O.normalize_lut()
+    for i in (0, 1, 3, 7, 63):
+        assert np.array_equal(got[i], O.albef_transform(images[i], S)), i
+    for i in range(2, B, len(sizes)):                      # 384 x 384 sources: identity resampling
+        want = np.stack([lut[c][images[i][:, :, c]] for c in range(3)], 0)
+        assert np.array_equal(got[i], want), i
+    for c, v in enumerate((17, 130, 255)):
+        assert np.all(got[5][c] == lut[c][v])
+    again = tr(list(reversed(images))).cpu().numpy()
+    assert np.array_equal(again[::-1], got)
+
+
+def test_errors_are_loud():
+    from fiber_b200.transforms import BatchImageTransform
+    with pytest.raises(RuntimeError, match="uint8"):
+        BatchImageTransform(32)([np.zeros((8, 8, 3), np.float32)])
+    with pytest.raises(RuntimeError, match="image_transform_plan"):
+        BatchImageTransform(32)([np.zeros((8, 8, 3), np.uint8)], boxes=[(4, 4, 8, 8)], flips=[0])
+    with pytest.raises(RuntimeError, match="image_transform_plan"):
+        BatchImageTransform((32, 30))([np.zeros((8, 8, 3), np.uint8)])
