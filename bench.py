@@ -697,6 +697,12 @@ def run_ours(args):
             line["extra_configs"]["fg800_backbone"] = measure_fg_backbone(dev)
         except Exception as e:  # noqa: BLE001
             line["extra_configs"]["fg800_backbone"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    if world == 1 and args.extra_configs:
+        try:  # the image side of the input pipeline (ragged uint8 images -> batch["image"][0])
+            from tools.bench_image import measure_image_pipeline
+            line["extra_configs"]["input_pipeline_albef384"] = measure_image_pipeline(dev, steps=10, warmup=3)
+        except Exception as e:  # noqa: BLE001
+            line["extra_configs"]["input_pipeline_albef384"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if world == 1 and args.eager_baseline:
         # the north-star's denominator: the reference PyTorch-eager GPU path, timed in this process after our arm
         line["eager_gpu_baseline"] = eager_gpu_baseline(args, dev, host, value)

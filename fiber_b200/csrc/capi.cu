@@ -9,6 +9,8 @@
 #include <cstring>
 
 namespace fiber {
+void set_image_variant(int v);  // image_pipeline.cu
+int get_image_variant();
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -218,6 +220,10 @@ int fiber_set_option(const char* name, int32_t value) {
     fiber::g_tq_trace.store(value > 0 ? 1 : 0, std::memory_order_relaxed);
     return 0;
   }
+  if (name && strcmp(name, "image_variant") == 0) {
+    fiber::set_image_variant(value);
+    return 0;
+  }
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;
 }
@@ -230,6 +236,7 @@ int fiber_get_option(const char* name) {
   if (name && strcmp(name, "gemm_cta2_launches") == 0) return fiber::g_gemm_cta2_launches.load();
   if (name && strcmp(name, "attn_sk") == 0) return fiber::option_attn_sk();
   if (name && strcmp(name, "attn_sk_launches") == 0) return fiber::g_attn_sk_launches.load();
+  if (name && strcmp(name, "image_variant") == 0) return fiber::get_image_variant();
   fiber::set_last_error("unknown option '%s'", name ? name : "(null)");
   return -1;
 }

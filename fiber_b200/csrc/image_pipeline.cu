@@ -10,8 +10,13 @@
 #include "common.cuh"
 #include "image_resample.cuh"
 
+#include <atomic>
+#include <cstdlib>
+
 namespace fiber {
 void count_launch(int n);
+void set_image_variant(int v);
+int get_image_variant();
 
 namespace img {
 
@@ -19,31 +24,57 @@ struct Norm {
   float mean[3], stdv[3];
 };
 
-__global__ void __launch_bounds__(128) image_coeffs_kernel(const fiber_image_desc* descs, void* ws, int out_h, int out_w) {
+__global__ void __launch_bounds__(128) image_coeffs_kernel(const fiber_image_desc* descs, void* ws, Norm norm, int out_h,
+                                                           int out_w) {
   pdl_trigger();
   pdl_wait();
-  coeffs_body(descs, ws, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+  coeffs_body(descs, ws, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, norm.mean, norm.stdv);
 }
 
+template <int R>
 __global__ void __launch_bounds__(256) image_hpass_kernel(const fiber_image_desc* descs, void* ws, int out_h, int out_w) {
   pdl_trigger();
   pdl_wait();
-  hpass_body(descs, ws, out_h, out_w, blockIdx.y, static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x);
+  hpass_body<R>(descs, ws, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void __launch_bounds__(256) image_vpass_kernel(const fiber_image_desc* descs, const void* ws, Norm norm, float* out,
-                                                          int out_h, int out_w) {
+template <int R>
+__global__ void __launch_bounds__(256) image_hpass_words_kernel(const fiber_image_desc* descs, void* ws, int out_h, int out_w) {
+  pdl_trigger();
+  pdl_wait();
+  hpass_words_body<R>(descs, ws, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) image_vpass_kernel(const fiber_image_desc* descs, const void* ws, float* out, int out_h,
+                                                          int out_w) {
   __shared__ float lut[3 * 256];
   pdl_trigger();
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = normalize_one(i & 255, norm.mean[i >> 8], norm.stdv[i >> 8]);
-  __syncthreads();
   pdl_wait();
-  vpass_body(descs, ws, lut, out, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = static_cast<const float*>(ws)[i];
+  __syncthreads();
+  vpass_body<W>(descs, ws, lut, out, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// "image_variant": bit 0 = the horizontal pass reads the source as aligned words (hpass_words_body) instead of bytes,
+// bit 1 = eight output columns per thread in the vertical pass instead of four.  Same bytes out either way.
+// FIBER_IMAGE_VARIANT.
+static std::atomic<int> g_variant{-1};
+static int option_variant() {
+  int v = g_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("FIBER_IMAGE_VARIANT");
+    v = e ? (atoi(e) & 3) : kDefaultVariant;
+    g_variant.store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace img
+void set_image_variant(int v) { img::g_variant.store(v < 0 ? -1 : (v & 3), std::memory_order_relaxed); }
+int get_image_variant() { return img::option_variant(); }
 }  // namespace fiber
 
 extern "C" {
@@ -54,7 +85,7 @@ size_t fiber_image_transform_plan(fiber_image_desc* d, int32_t n, int32_t out_h,
     fiber::set_last_error("image_transform_plan: need n > 0, out_h > 0, out_w > 0 and out_w %% 4 == 0");
     return 0;
   }
-  size_t off = 0;
+  size_t off = kLutBytes;
   for (int i = 0; i < n; ++i) {
     fiber_image_desc& e = d[i];
     if (!e.src || e.h <= 0 || e.w <= 0 || e.stride < 3LL * e.w || e.box_w <= 0 || e.box_h <= 0 || e.box_x < 0 || e.box_y < 0 ||
@@ -92,7 +123,7 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
   size_t need = 0;
   for (int i = 0; i < n; ++i) {
     const fiber_image_desc& e = dh[i];
-    FIBER_CHECK(e.ksize_x == ksize_for(e.box_w, out_w) && e.ksize_y == ksize_for(e.box_h, out_h) && e.coef_off >= 0 &&
+    FIBER_CHECK(e.ksize_x == ksize_for(e.box_w, out_w) && e.ksize_y == ksize_for(e.box_h, out_h) && e.coef_off >= kLutBytes &&
                     e.tmp_off >= 0,
                 "image_transform: descriptor %d was not planned for this output size (fiber_image_transform_plan)", i);
     max_box_h = e.box_h > max_box_h ? e.box_h : max_box_h;
@@ -105,15 +136,25 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
     norm.mean[c] = mean[c];
     norm.stdv[c] = stdv[c];
   }
-  const dim3 g1((out_w + out_h + 127) / 128, n);
-  FIBER_CUDA(fiber::launch_k(image_coeffs_kernel, g1, dim3(128), 0, stream, dd, ws, out_h, out_w));
-  const long long hwork = static_cast<long long>((max_box_h + kRowsPerThread - 1) / kRowsPerThread) * out_w;
+  const dim3 g1(((out_w + out_h > 768 ? out_w + out_h : 768) + 127) / 128, n);
+  FIBER_CUDA(fiber::launch_k(image_coeffs_kernel, g1, dim3(128), 0, stream, dd, ws, norm, out_h, out_w));
+  const int variant = option_variant();
+  const int R = 4, W = (variant & 2) ? 2 : 1;
+  const long long hwork = static_cast<long long>((max_box_h + R - 1) / R) * out_w;
+  const long long vwork = static_cast<long long>(out_h) * ((out_w / 4 + W - 1) / W);
+  FIBER_CHECK(hwork < (1LL << 31) && vwork < (1LL << 31), "image_transform: image too large for 32-bit indexing");
   const dim3 g2(static_cast<unsigned>((hwork + 255) / 256), n);
-  FIBER_CUDA(fiber::launch_k(image_hpass_kernel, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
-  const long long vwork = 3LL * out_h * (out_w / 4);
+  if (variant & 1)
+    FIBER_CUDA(fiber::launch_k(image_hpass_words_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
+  else
+    FIBER_CUDA(fiber::launch_k(image_hpass_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
   const dim3 g3(static_cast<unsigned>((vwork + 255) / 256), n);
-  FIBER_CUDA(fiber::launch_k(image_vpass_kernel, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), norm, out, out_h,
-                             out_w));
+  if (W == 2)
+    FIBER_CUDA(fiber::launch_k(image_vpass_kernel<2>, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), out, out_h,
+                               out_w));
+  else
+    FIBER_CUDA(fiber::launch_k(image_vpass_kernel<1>, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), out, out_h,
+                               out_w));
   fiber::count_launch(3);
   return 0;
 }

@@ -24,7 +24,6 @@ namespace fiber {
 namespace img {
 
 constexpr int kPrecisionBits = 32 - 8 - 2;  // Resample.c: PRECISION_BITS
-constexpr int kRowsPerThread = 4;            // horizontal pass: source rows per thread (same coefficients)
 
 FIBER_HD double dmul(double a, double b) {
 #ifdef __CUDA_ARCH__
@@ -66,7 +65,8 @@ FIBER_HD int ksize_for(int in_size, int out_size) {
 }
 
 // Fixed-point coefficients of output sample xx (full-image box: in0 = 0, in1 = in_size), written tap-major:
-// k[t * out_size] for t in [0, ksize); bounds[0] = first source sample, bounds[1] = tap count.
+// k[t * out_size] for t in [0, ksize) (zero past the tap count; ksize may be the padded table height);
+// bounds[0] = first source sample, bounds[1] = tap count.
 FIBER_HD void coeffs_one(int in_size, int out_size, int xx, int ksize, int32_t* k, int32_t* bounds) {
   const double scale = ddiv(static_cast<double>(in_size), static_cast<double>(out_size));
   const double fs = scale < 1.0 ? 1.0 : scale;
@@ -95,6 +95,16 @@ FIBER_HD void coeffs_one(int in_size, int out_size, int xx, int ksize, int32_t* 
   bounds[1] = n;
 }
 
+// Read-only global loads (ld.global.nc): source pixels, byte planes and tables are never written by the reading kernel.
+template <typename T>
+FIBER_HD T ldg(const T* p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 FIBER_HD uint8_t clip8(int32_t acc) {
   int32_t v = acc >> kPrecisionBits;  // arithmetic shift, as the library's lookup index
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
@@ -113,19 +123,20 @@ FIBER_HD float normalize_one(int v, float mean, float stdv) {
 
 // Per-image slices of the workspace (offsets filled by fiber_image_transform_plan).
 struct Tables {
-  const int32_t* kx;  // [ksize_x][out_w]
+  const int32_t* kx;  // [ksize_x rounded up to a multiple of 4][out_w], zero beyond a sample's tap count
   const int32_t* bx;  // [out_w][2]
   const int32_t* ky;  // [ksize_y][out_h]
   const int32_t* by;  // [out_h][2]
 };
+FIBER_HD int kpad_x(const fiber_image_desc& d) { return (d.ksize_x + 3) & ~3; }  // horizontal taps, zero-padded to fours
 FIBER_HD int64_t table_ints(const fiber_image_desc& d, int out_h, int out_w) {
-  return static_cast<int64_t>(d.ksize_x + 2) * out_w + static_cast<int64_t>(d.ksize_y + 2) * out_h;
+  return static_cast<int64_t>(kpad_x(d) + 2) * out_w + static_cast<int64_t>(d.ksize_y + 2) * out_h;
 }
 FIBER_HD Tables tables_of(const fiber_image_desc& d, const void* ws, int out_h, int out_w) {
   const int32_t* base = reinterpret_cast<const int32_t*>(static_cast<const uint8_t*>(ws) + d.coef_off);
   Tables t;
   t.kx = base;
-  t.bx = t.kx + static_cast<int64_t>(d.ksize_x) * out_w;
+  t.bx = t.kx + static_cast<int64_t>(kpad_x(d)) * out_w;
   t.ky = t.bx + 2 * out_w;
   t.by = t.ky + static_cast<int64_t>(d.ksize_y) * out_h;
   return t;
@@ -135,96 +146,207 @@ struct alignas(16) Float4 {
   float a, b, c, d;
 };
 
-// ---- kernel 1: coefficient tables.  idx in [0, out_w + out_h) per image. ------------------------------------------
-FIBER_HD void coeffs_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int idx) {
+constexpr int kDefaultVariant = 3;            // "image_variant" when neither the option nor the environment sets it
+constexpr int kLutBytes = 3 * 256 * 4;        // the workspace starts with the [3][256] float32 normalisation table
+
+// ---- kernel 1: coefficient tables.  idx in [0, max(out_w + out_h, 768)) per image; image 0 also fills the table of
+// normalised values (ToTensor + Normalize of every byte value, per channel) at the head of the workspace. -------------
+FIBER_HD void coeffs_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int idx,
+                          const float* mean, const float* stdv) {
+  if (image == 0 && idx < 3 * 256)
+    static_cast<float*>(ws)[idx] = normalize_one(idx & 255, mean[idx >> 8], stdv[idx >> 8]);
   if (idx >= out_w + out_h) return;
   const fiber_image_desc d = descs[image];
   Tables t = tables_of(d, ws, out_h, out_w);
   if (idx < out_w)
-    coeffs_one(d.box_w, out_w, idx, d.ksize_x, const_cast<int32_t*>(t.kx) + idx, const_cast<int32_t*>(t.bx) + 2 * idx);
+    coeffs_one(d.box_w, out_w, idx, kpad_x(d), const_cast<int32_t*>(t.kx) + idx, const_cast<int32_t*>(t.bx) + 2 * idx);
   else
     coeffs_one(d.box_h, out_h, idx - out_w, d.ksize_y, const_cast<int32_t*>(t.ky) + (idx - out_w),
                const_cast<int32_t*>(t.by) + 2 * (idx - out_w));
 }
 
-// ---- kernel 2: horizontal pass.  idx in [0, ceil(box_h / kRowsPerThread) * out_w) per image: one output column of
-// kRowsPerThread consecutive source rows; interleaved RGB bytes in, three byte planes [3][box_h][pitch] out. ----------
-FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int64_t idx) {
+// ---- kernel 2: horizontal pass.  idx in [0, ceil(box_h / R) * out_w) per image: one output column of R consecutive
+// source rows, all three channels (3 R accumulators per coefficient load); interleaved RGB bytes in, three byte planes
+// [3][box_h][pitch] out.  Rows past the box are computed on a duplicate of the last row and not stored, so the tap
+// loop carries no predicates. ----------------------------------------------------
+template <int R>
+FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int idx) {
   const fiber_image_desc d = descs[image];
-  const int groups = (d.box_h + kRowsPerThread - 1) / kRowsPerThread;
-  if (idx >= static_cast<int64_t>(groups) * out_w) return;
-  const int x = static_cast<int>(idx % out_w);
-  const int y0 = static_cast<int>(idx / out_w) * kRowsPerThread;
+  const int groups = (d.box_h + R - 1) / R;
+  if (idx >= groups * out_w) return;
+  const int g = idx / out_w;
+  const int x = idx - g * out_w;
+  const int y0 = g * R;
   const Tables t = tables_of(d, ws, out_h, out_w);
-  const int xmin = t.bx[2 * x], n = t.bx[2 * x + 1];
-  const int pitch = tmp_pitch(out_w);
-  uint8_t* tmp = static_cast<uint8_t*>(ws) + d.tmp_off;
-  const uint8_t* src = d.src + static_cast<int64_t>(d.box_y + y0) * d.stride + static_cast<int64_t>(d.box_x + xmin) * 3;
-  int32_t acc[kRowsPerThread][3];
+  const int xmin = ldg(t.bx + 2 * x), n = ldg(t.bx + 2 * x + 1);
+  const int rows = d.box_h - y0 < R ? d.box_h - y0 : R;
+  const uint8_t* p[R];
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
-  const int rows = d.box_h - y0 < kRowsPerThread ? d.box_h - y0 : kRowsPerThread;
-  for (int tp = 0; tp < n; ++tp) {
-    const int32_t k = t.kx[static_cast<int64_t>(tp) * out_w + x];
+  for (int r = 0; r < R; ++r)
+    p[r] = d.src + static_cast<int64_t>(d.box_y + y0 + (r < rows ? r : rows - 1)) * d.stride +
+           static_cast<int64_t>(d.box_x + xmin) * 3;
+  int32_t acc[R][3];
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
-      if (r < rows) {
-        const uint8_t* p = src + r * d.stride + tp * 3;
-        acc[r][0] += static_cast<int32_t>(p[0]) * k;
-        acc[r][1] += static_cast<int32_t>(p[1]) * k;
-        acc[r][2] += static_cast<int32_t>(p[2]) * k;
-      }
+  for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
+  const int32_t* kp = t.kx + x;
+  for (int tp = 0; tp < n; ++tp, kp += out_w) {
+    const int32_t k = ldg(kp);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r][0] += static_cast<int32_t>(ldg(p[r])) * k;
+      acc[r][1] += static_cast<int32_t>(ldg(p[r] + 1)) * k;
+      acc[r][2] += static_cast<int32_t>(ldg(p[r] + 2)) * k;
+      p[r] += 3;
     }
   }
+  const int pitch = tmp_pitch(out_w);
   const int64_t plane = static_cast<int64_t>(d.box_h) * pitch;
+  uint8_t* o = static_cast<uint8_t*>(ws) + d.tmp_off + static_cast<int64_t>(y0) * pitch + x;
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; ++r) {
+  for (int r = 0; r < R; ++r) {
     if (r < rows) {
-      uint8_t* o = tmp + static_cast<int64_t>(y0 + r) * pitch + x;
       o[0] = clip8(acc[r][0]);
       o[plane] = clip8(acc[r][1]);
       o[2 * plane] = clip8(acc[r][2]);
     }
+    o += pitch;
   }
 }
 
-// ---- kernel 3: vertical pass + ToTensor + Normalize (+ horizontal flip).  idx in [0, 3 * out_h * out_w / 4) per
-// image: four consecutive output columns of one (channel, row); float32 NCHW out.  lut = [3][256] normalised values. ----
+FIBER_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bytes of the pair (lo, hi) starting sh / 8 bytes in
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// ---- kernel 2, word form ("image_variant" bit 0): the same sums, with the source row read as aligned 32-bit words
+// instead of single bytes — a byte load of a warp touches the same two 128-byte lines as a word load, so the pass
+// was bound by L1 wavefronts (three per pixel and tap), not by instruction issue.  Four taps = twelve bytes = three
+// words per step and row; the row's byte stream starts `off` bytes into its first word, a funnel shift re-aligns it.
+// Only words that hold at least one byte of the sample's taps are loaded (such a word lies in the same page as a valid
+// byte even when it straddles the image's first or last byte); the coefficient rows are zero-padded to fours, so
+// whatever shares a word with the last tap is multiplied by zero. ------------------------------------------------------
+template <int R>
+FIBER_HD void hpass_words_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int idx) {
+  const fiber_image_desc d = descs[image];
+  const int groups = (d.box_h + R - 1) / R;
+  if (idx >= groups * out_w) return;
+  const int g = idx / out_w;
+  const int x = idx - g * out_w;
+  const int y0 = g * R;
+  const Tables t = tables_of(d, ws, out_h, out_w);
+  const int xmin = ldg(t.bx + 2 * x), n = ldg(t.bx + 2 * x + 1);
+  const int rows = d.box_h - y0 < R ? d.box_h - y0 : R;
+  const uint32_t* wp[R];
+  uint32_t sh[R], carry[R];
+  int nw[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint8_t* p = d.src + static_cast<int64_t>(d.box_y + y0 + (r < rows ? r : rows - 1)) * d.stride +
+                       static_cast<int64_t>(d.box_x + xmin) * 3;
+    const uint32_t off = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 3);
+    wp[r] = reinterpret_cast<const uint32_t*>(p - off);
+    sh[r] = off * 8;
+    nw[r] = static_cast<int>(off + 3 * n + 3) >> 2;   // words holding the sample's 3 n bytes
+    carry[r] = n > 0 ? ldg(wp[r]) : 0u;
+  }
+  int32_t acc[R][3];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
+  const int32_t* kp = t.kx + x;
+  for (int tp = 0, j = 1; tp < n; tp += 4, j += 3, kp += 4 * out_w) {
+    const int32_t k0 = ldg(kp), k1 = ldg(kp + out_w), k2 = ldg(kp + 2 * out_w), k3 = ldg(kp + 3 * out_w);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t w1 = j < nw[r] ? ldg(wp[r] + j) : 0u;
+      const uint32_t w2 = j + 1 < nw[r] ? ldg(wp[r] + j + 1) : 0u;
+      const uint32_t w3 = j + 2 < nw[r] ? ldg(wp[r] + j + 2) : 0u;
+      const uint32_t a0 = funnel_r(carry[r], w1, sh[r]);   // R0 G0 B0 R1
+      const uint32_t a1 = funnel_r(w1, w2, sh[r]);         // G1 B1 R2 G2
+      const uint32_t a2 = funnel_r(w2, w3, sh[r]);         // B2 R3 G3 B3
+      carry[r] = w3;
+      acc[r][0] += static_cast<int32_t>(a0 & 0xff) * k0 + static_cast<int32_t>(a0 >> 24) * k1 +
+                   static_cast<int32_t>((a1 >> 16) & 0xff) * k2 + static_cast<int32_t>((a2 >> 8) & 0xff) * k3;
+      acc[r][1] += static_cast<int32_t>((a0 >> 8) & 0xff) * k0 + static_cast<int32_t>(a1 & 0xff) * k1 +
+                   static_cast<int32_t>(a1 >> 24) * k2 + static_cast<int32_t>((a2 >> 16) & 0xff) * k3;
+      acc[r][2] += static_cast<int32_t>((a0 >> 16) & 0xff) * k0 + static_cast<int32_t>((a1 >> 8) & 0xff) * k1 +
+                   static_cast<int32_t>(a2 & 0xff) * k2 + static_cast<int32_t>(a2 >> 24) * k3;
+    }
+  }
+  const int pitch = tmp_pitch(out_w);
+  const int64_t plane = static_cast<int64_t>(d.box_h) * pitch;
+  uint8_t* o = static_cast<uint8_t*>(ws) + d.tmp_off + static_cast<int64_t>(y0) * pitch + x;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (r < rows) {
+      o[0] = clip8(acc[r][0]);
+      o[plane] = clip8(acc[r][1]);
+      o[2 * plane] = clip8(acc[r][2]);
+    }
+    o += pitch;
+  }
+}
+
+// ---- kernel 3: vertical pass + ToTensor + Normalize (+ horizontal flip).  idx in [0, out_h * ceil(out_w / (4 W)))
+// per image: 4 W consecutive output columns of one row, all three channels (12 W accumulators per coefficient load);
+// float32 NCHW out.  lut = the [3][256] table of normalised values (shared memory on the device).  W = 1 or 2
+// ("image_variant" bit 1). -------------------------------------------------------------------------------------------
+template <int W>
 FIBER_HD void vpass_body(const fiber_image_desc* descs, const void* ws, const float* lut, float* out, int out_h, int out_w,
                          int image, int idx) {
   const int w4 = out_w >> 2;
-  if (idx >= 3 * out_h * w4) return;
+  const int per_row = (w4 + W - 1) / W;
+  if (idx >= out_h * per_row) return;
   const fiber_image_desc d = descs[image];
-  const int x = (idx % w4) * 4;
-  const int yy = (idx / w4) % out_h;
-  const int c = idx / (w4 * out_h);
+  const int yy = idx / per_row;
+  const int x = (idx - yy * per_row) * (4 * W);
   const Tables t = tables_of(d, ws, out_h, out_w);
-  const int ymin = t.by[2 * yy], n = t.by[2 * yy + 1];
+  const int ymin = ldg(t.by + 2 * yy), n = ldg(t.by + 2 * yy + 1);
   const int pitch = tmp_pitch(out_w);
-  const uint8_t* col = static_cast<const uint8_t*>(ws) + d.tmp_off +
-                       (static_cast<int64_t>(c) * d.box_h + ymin) * pitch + x;
-  int32_t a0, a1, a2, a3;
-  a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
-  for (int tp = 0; tp < n; ++tp) {
-    const int32_t k = t.ky[static_cast<int64_t>(tp) * out_h + yy];
-    const uint32_t p = *reinterpret_cast<const uint32_t*>(col + static_cast<int64_t>(tp) * pitch);  // x % 4 == 0, pitch % 16 == 0
-    a0 += static_cast<int32_t>(p & 0xff) * k;
-    a1 += static_cast<int32_t>((p >> 8) & 0xff) * k;
-    a2 += static_cast<int32_t>((p >> 16) & 0xff) * k;
-    a3 += static_cast<int32_t>(p >> 24) * k;
+  const int64_t plane = static_cast<int64_t>(d.box_h) * pitch;
+  const uint8_t* col = static_cast<const uint8_t*>(ws) + d.tmp_off + static_cast<int64_t>(ymin) * pitch + x;
+  int32_t a[3][W][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int w = 0; w < W; ++w) a[c][w][0] = a[c][w][1] = a[c][w][2] = a[c][w][3] = 1 << (kPrecisionBits - 1);
+  const int32_t* kp = t.ky + yy;
+  for (int tp = 0; tp < n; ++tp, kp += out_h, col += pitch) {
+    const int32_t k = ldg(kp);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        // x % 4 == 0 and pitch % 16 == 0: aligned; the pitch padding keeps a partial last group inside the plane row
+        const uint32_t p = ldg(reinterpret_cast<const uint32_t*>(col + c * plane) + w);
+        a[c][w][0] += static_cast<int32_t>(p & 0xff) * k;
+        a[c][w][1] += static_cast<int32_t>((p >> 8) & 0xff) * k;
+        a[c][w][2] += static_cast<int32_t>((p >> 16) & 0xff) * k;
+        a[c][w][3] += static_cast<int32_t>(p >> 24) * k;
+      }
+    }
   }
-  const float* l = lut + c * 256;
-  const float v0 = l[clip8(a0)], v1 = l[clip8(a1)], v2 = l[clip8(a2)], v3 = l[clip8(a3)];
-  float* o = out + ((static_cast<int64_t>(image) * 3 + c) * out_h + yy) * out_w;   // out 16-byte aligned, out_w % 4 == 0
-  Float4 v;
-  if (d.flip) {
-    o += out_w - 4 - x;
-    v.a = v3; v.b = v2; v.c = v1; v.d = v0;
-  } else {
-    o += x;
-    v.a = v0; v.b = v1; v.c = v2; v.d = v3;
+  float* row = out + (static_cast<int64_t>(image) * 3 * out_h + yy) * out_w;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {   // out 16-byte aligned, out_w % 4 == 0: one 128-bit store per channel and group
+    const float* l = lut + c * 256;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int xw = x + 4 * w;
+      if (xw < out_w) {
+        const float v0 = l[clip8(a[c][w][0])], v1 = l[clip8(a[c][w][1])], v2 = l[clip8(a[c][w][2])], v3 = l[clip8(a[c][w][3])];
+        Float4 v;
+        if (d.flip) {
+          v.a = v3; v.b = v2; v.c = v1; v.d = v0;
+        } else {
+          v.a = v0; v.b = v1; v.c = v2; v.d = v3;
+        }
+        *reinterpret_cast<Float4*>(row + static_cast<int64_t>(c) * out_h * out_w + (d.flip ? out_w - 4 - xw : xw)) = v;
+      }
+    }
   }
-  *reinterpret_cast<Float4*>(o) = v;   // one 128-bit store
 }
 
 }  // namespace img

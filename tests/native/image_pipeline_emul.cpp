@@ -10,25 +10,39 @@
 
 using namespace fiber::img;
 
-extern "C" int emul_image_transform(const fiber_image_desc* d, int n, int out_h, int out_w, const float* mean,
-                                    const float* stdv, void* ws, float* out) {
+template <int R, int W, bool WORDS>
+static int run(const fiber_image_desc* d, int n, int out_h, int out_w, const float* mean, const float* stdv, void* ws,
+               float* out) {
   int max_box_h = 0;
   for (int i = 0; i < n; ++i) max_box_h = d[i].box_h > max_box_h ? d[i].box_h : max_box_h;
-  std::vector<float> lut(3 * 256);
-  for (int i = 0; i < 3 * 256; ++i) lut[i] = normalize_one(i & 255, mean[i >> 8], stdv[i >> 8]);
-  const int g1 = (out_w + out_h + 127) / 128;
-  const long long hwork = static_cast<long long>((max_box_h + kRowsPerThread - 1) / kRowsPerThread) * out_w;
+  const float* lut = static_cast<const float*>(ws);   // written by coeffs_body (the device copies it to shared memory)
+  const int g1 = ((out_w + out_h > 768 ? out_w + out_h : 768) + 127) / 128;
+  const long long hwork = static_cast<long long>((max_box_h + R - 1) / R) * out_w;
   const long long g2 = (hwork + 255) / 256;
-  const long long vwork = 3LL * out_h * (out_w / 4);
+  const long long vwork = static_cast<long long>(out_h) * ((out_w / 4 + W - 1) / W);
   const long long g3 = (vwork + 255) / 256;
   for (int img = 0; img < n; ++img)
     for (int b = 0; b < g1; ++b)
-      for (int t = 0; t < 128; ++t) coeffs_body(d, ws, out_h, out_w, img, b * 128 + t);
+      for (int t = 0; t < 128; ++t) coeffs_body(d, ws, out_h, out_w, img, b * 128 + t, mean, stdv);
   for (int img = 0; img < n; ++img)
     for (long long b = 0; b < g2; ++b)
-      for (int t = 0; t < 256; ++t) hpass_body(d, ws, out_h, out_w, img, b * 256 + t);
+      for (int t = 0; t < 256; ++t) {
+        if (WORDS) hpass_words_body<R>(d, ws, out_h, out_w, img, static_cast<int>(b * 256 + t));
+        else hpass_body<R>(d, ws, out_h, out_w, img, static_cast<int>(b * 256 + t));
+      }
   for (int img = 0; img < n; ++img)
     for (long long b = 0; b < g3; ++b)
-      for (int t = 0; t < 256; ++t) vpass_body(d, ws, lut.data(), out, out_h, out_w, img, static_cast<int>(b * 256 + t));
+      for (int t = 0; t < 256; ++t) vpass_body<W>(d, ws, lut, out, out_h, out_w, img, static_cast<int>(b * 256 + t));
   return 0;
+}
+
+// variant: the library's "image_variant" option (bit 0: word-form horizontal pass, bit 1: eight columns per thread)
+extern "C" int emul_image_transform(const fiber_image_desc* d, int n, int out_h, int out_w, const float* mean,
+                                    const float* stdv, void* ws, float* out, int variant) {
+  switch (variant & 3) {
+    case 0: return run<4, 1, false>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 1: return run<4, 1, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 2: return run<4, 2, false>(d, n, out_h, out_w, mean, stdv, ws, out);
+    default: return run<4, 2, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+  }
 }

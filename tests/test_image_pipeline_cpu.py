@@ -60,7 +60,7 @@ def emul(tmp_path_factory):
     return C.CDLL(str(so))
 
 
-def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None):
+def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, variant=0):
     from fiber_b200 import lib as L
     lib = L.load()
     n = len(images)
@@ -69,9 +69,11 @@ def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None):
     for i, img in enumerate(images):
         h, w = img.shape[:2]
         stride = strides[i] if strides else 3 * w
-        buf = np.full((h, stride), 0xAB, np.uint8)
+        lead = 16 + i % 4       # every byte alignment of the first pixel; padding for the word-form pass's aligned words
+        raw = np.full(lead + h * stride + 16, 0xAB, np.uint8)
+        buf = raw[lead:lead + h * stride].reshape(h, stride)
         buf[:, :3 * w] = img.reshape(h, 3 * w)
-        keep.append(buf)
+        keep.append(raw)
         d = descs[i]
         d.src, d.stride, d.h, d.w = buf.ctypes.data, stride, h, w
         d.box_x, d.box_y, d.box_w, d.box_h = boxes[i] if boxes else (0, 0, w, h)
@@ -82,16 +84,18 @@ def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None):
     base = (ws.ctypes.data + 15) // 16 * 16
     out = np.full((n, 3, out_h, out_w), np.nan, np.float32)
     mean, std = (C.c_float * 3)(*O.MEAN), (C.c_float * 3)(*O.STD)
-    emul.emul_image_transform(descs, n, out_h, out_w, mean, std, C.c_void_p(base), C.c_void_p(out.ctypes.data))
+    emul.emul_image_transform(descs, n, out_h, out_w, mean, std, C.c_void_p(base), C.c_void_p(out.ctypes.data), variant)
     return out
 
 
-def test_kernel_bodies_match_oracle_ragged_batch(emul):
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_kernel_bodies_match_oracle_ragged_batch(emul, variant):
     rng = np.random.default_rng(11)
     sizes = [(97, 131), (48, 64), (64, 64), (7, 5), (211, 89), (30, 300), (64, 65), (1, 1), (130, 64)]
     images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
-    for out_h, out_w in [(64, 64), (96, 32), (40, 72)]:
-        got = _run_emul(emul, images, out_h, out_w, strides=[3 * w + (5 * i) % 7 for i, (h, w) in enumerate(sizes)])
+    for out_h, out_w in [(64, 64), (96, 32), (40, 72), (24, 12)]:
+        got = _run_emul(emul, images, out_h, out_w, strides=[3 * w + (5 * i) % 7 for i, (h, w) in enumerate(sizes)],
+                        variant=variant)
         for i, img in enumerate(images):
             r = O.resize_bicubic_u8(img, out_h, out_w)
             lut = O.normalize_lut()
@@ -99,11 +103,13 @@ def test_kernel_bodies_match_oracle_ragged_batch(emul):
             assert np.array_equal(got[i], want), (sizes[i], out_h, out_w)
 
 
-def test_kernel_bodies_match_library_golden_with_crop_and_flip(emul):
+@pytest.mark.parametrize("variant", [0, 3])
+def test_kernel_bodies_match_library_golden_with_crop_and_flip(emul, variant):
     for i, (h, w, s) in enumerate(CASES):
         src = GOLD["src_%d" % i]
         left, top, bw, bh, flip = (int(v) for v in GOLD["box_%d" % i])
-        got = _run_emul(emul, [src, src], s, s, boxes=[(0, 0, w, h), (left, top, bw, bh)], flips=[0, flip])
+        got = _run_emul(emul, [src, src], s, s, boxes=[(0, 0, w, h), (left, top, bw, bh)], flips=[0, flip],
+                        variant=variant)
         assert np.array_equal(got[0], GOLD["albef_%d" % i])
         assert np.array_equal(got[1], GOLD["crop_%d" % i])
 

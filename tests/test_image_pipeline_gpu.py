@@ -38,14 +38,23 @@ def test_golden_cases(on_device):
             assert np.array_equal(crop[j], GOLD["crop_%d" % i]), ("crop", CASES[i])
 
 
-def test_ragged_batch_vs_oracle_rectangular_output_and_strides():
+@pytest.fixture
+def variant(request):
+    from fiber_b200 import lib
+    lib.set_option("image_variant", request.param)
+    yield request.param
+    lib.set_option("image_variant", -1)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], indirect=True)
+def test_ragged_batch_vs_oracle_rectangular_output_and_strides(variant):
     from fiber_b200.transforms import BatchImageTransform
     rng = np.random.default_rng(3)
     sizes = [(97, 131), (48, 64), (64, 64), (7, 5), (211, 89), (30, 300), (64, 65), (1, 1), (130, 64), (500, 375)]
     images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
     # device images as views into wider buffers: row stride > 3 w
     wide = [torch.from_numpy(np.pad(a, ((0, 0), (0, 3 + i), (0, 0)))).cuda()[:, :a.shape[1]] for i, a in enumerate(images)]
-    for out_hw in [(64, 64), (96, 32), (40, 72)]:
+    for out_hw in [(64, 64), (96, 32), (40, 72), (24, 12)]:
         tr = BatchImageTransform(out_hw)
         for batch in (images, wide):
             got = tr(batch).cpu().numpy()

@@ -36,7 +36,7 @@ def _peak_gbs():
     return 6551.0, "SURVEY.md §9 (measured copy bandwidth)"
 
 
-def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, warmup=5, cpu_sample=16):
+def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, warmup=5, cpu_sample=16, sweep=False):
     from fiber_b200 import lib
     from fiber_b200.transforms import albef_transform
     h, w = src
@@ -65,6 +65,13 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
         torch.cuda.synchronize()
         return t_host / n if with_host else float(np.median([a.elapsed_time(b) for a, b in ev])) * 1e-3
 
+    variants = {}
+    if sweep:   # every "image_variant" (rows / columns per thread), same bytes out
+        for v in range(4):
+            lib.set_option("image_variant", v)
+            run(resident, warmup, False)
+            variants[str(v)] = run(resident, steps, False) * 1e3
+        lib.set_option("image_variant", -1)
     run(resident, warmup, False)
     l0 = lib.launch_count()
     t_dev = run(resident, steps, False)
@@ -80,6 +87,7 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
                    "l2": "256 MB flush write between iterations"},
         "dtype": "u8 -> int32 fixed point -> f32",
         "gpu_launches_per_batch": int(launches),
+        "image_variant": lib.get_option("image_variant"),
         "e2e": {"value": batch / t_e2e, "unit": "images/s", "h2d_bytes_per_step": batch * 3 * h * w,
                 "d2h_bytes_per_step": 0, "note": "host wall clock around the call + synchronize: staging memcpy into pinned "
                                                  "memory, one H2D copy, three kernels"},
@@ -88,6 +96,8 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
                      "algorithmic_bytes_per_image": 3 * h * w + 12 * size * size,
                      "note": "all three launches of a batch timed together (coefficients, horizontal, vertical pass)"},
     }
+    if variants:
+        rec["variant_ms_per_batch"] = variants
     try:  # the reference's own per-image path on the host: PIL resize + torchvision ToTensor / Normalize
         from PIL import Image
         from torchvision import transforms as T
@@ -117,11 +127,12 @@ def main():
     ap.add_argument("--size", type=int, default=384)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--sweep", action="store_true", help="also time every image_variant")
     a = ap.parse_args()
     h, w = (int(v) for v in a.src.split("x"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup)))
+    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup, sweep=a.sweep)))
 
 
 if __name__ == "__main__":
