@@ -213,6 +213,13 @@ FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int
   }
 }
 
+FIBER_HD uint32_t byte_at(uint32_t w, int i) {  // byte i of w, zero-extended: one PRMT on the device
+#ifdef __CUDA_ARCH__
+  return __byte_perm(w, 0u, 0x4440u + static_cast<uint32_t>(i));
+#else
+  return (w >> (8 * i)) & 0xffu;
+#endif
+}
 FIBER_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bytes of the pair (lo, hi) starting sh / 8 bytes in
 #ifdef __CUDA_ARCH__
   return __funnelshift_r(lo, hi, sh);
@@ -239,9 +246,9 @@ FIBER_HD void hpass_words_body(const fiber_image_desc* descs, void* ws, int out_
   const Tables t = tables_of(d, ws, out_h, out_w);
   const int xmin = ldg(t.bx + 2 * x), n = ldg(t.bx + 2 * x + 1);
   const int rows = d.box_h - y0 < R ? d.box_h - y0 : R;
-  const uint32_t* wp[R];
+  const uint32_t* wp[R];   // the next word to load of each row (advances three words per step)
   uint32_t sh[R], carry[R];
-  int nw[R];
+  int rem[R];              // words of the row's taps not loaded yet
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const uint8_t* p = d.src + static_cast<int64_t>(d.box_y + y0 + (r < rows ? r : rows - 1)) * d.stride +
@@ -249,30 +256,33 @@ FIBER_HD void hpass_words_body(const fiber_image_desc* descs, void* ws, int out_
     const uint32_t off = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 3);
     wp[r] = reinterpret_cast<const uint32_t*>(p - off);
     sh[r] = off * 8;
-    nw[r] = static_cast<int>(off + 3 * n + 3) >> 2;   // words holding the sample's 3 n bytes
+    rem[r] = (static_cast<int>(off + 3 * n + 3) >> 2) - 1;   // words holding the sample's 3 n bytes, minus the first
     carry[r] = n > 0 ? ldg(wp[r]) : 0u;
+    ++wp[r];
   }
   int32_t acc[R][3];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
   const int32_t* kp = t.kx + x;
-  for (int tp = 0, j = 1; tp < n; tp += 4, j += 3, kp += 4 * out_w) {
+  for (int tp = 0; tp < n; tp += 4, kp += 4 * out_w) {
     const int32_t k0 = ldg(kp), k1 = ldg(kp + out_w), k2 = ldg(kp + 2 * out_w), k3 = ldg(kp + 3 * out_w);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const uint32_t w1 = j < nw[r] ? ldg(wp[r] + j) : 0u;
-      const uint32_t w2 = j + 1 < nw[r] ? ldg(wp[r] + j + 1) : 0u;
-      const uint32_t w3 = j + 2 < nw[r] ? ldg(wp[r] + j + 2) : 0u;
+      const uint32_t w1 = rem[r] > 0 ? ldg(wp[r]) : 0u;
+      const uint32_t w2 = rem[r] > 1 ? ldg(wp[r] + 1) : 0u;
+      const uint32_t w3 = rem[r] > 2 ? ldg(wp[r] + 2) : 0u;
+      wp[r] += 3;
+      rem[r] -= 3;
       const uint32_t a0 = funnel_r(carry[r], w1, sh[r]);   // R0 G0 B0 R1
       const uint32_t a1 = funnel_r(w1, w2, sh[r]);         // G1 B1 R2 G2
       const uint32_t a2 = funnel_r(w2, w3, sh[r]);         // B2 R3 G3 B3
       carry[r] = w3;
-      acc[r][0] += static_cast<int32_t>(a0 & 0xff) * k0 + static_cast<int32_t>(a0 >> 24) * k1 +
-                   static_cast<int32_t>((a1 >> 16) & 0xff) * k2 + static_cast<int32_t>((a2 >> 8) & 0xff) * k3;
-      acc[r][1] += static_cast<int32_t>((a0 >> 8) & 0xff) * k0 + static_cast<int32_t>(a1 & 0xff) * k1 +
-                   static_cast<int32_t>(a1 >> 24) * k2 + static_cast<int32_t>((a2 >> 16) & 0xff) * k3;
-      acc[r][2] += static_cast<int32_t>((a0 >> 16) & 0xff) * k0 + static_cast<int32_t>((a1 >> 8) & 0xff) * k1 +
-                   static_cast<int32_t>(a2 & 0xff) * k2 + static_cast<int32_t>(a2 >> 24) * k3;
+      acc[r][0] += static_cast<int32_t>(byte_at(a0, 0)) * k0 + static_cast<int32_t>(byte_at(a0, 3)) * k1 +
+                   static_cast<int32_t>(byte_at(a1, 2)) * k2 + static_cast<int32_t>(byte_at(a2, 1)) * k3;
+      acc[r][1] += static_cast<int32_t>(byte_at(a0, 1)) * k0 + static_cast<int32_t>(byte_at(a1, 0)) * k1 +
+                   static_cast<int32_t>(byte_at(a1, 3)) * k2 + static_cast<int32_t>(byte_at(a2, 2)) * k3;
+      acc[r][2] += static_cast<int32_t>(byte_at(a0, 2)) * k0 + static_cast<int32_t>(byte_at(a1, 1)) * k1 +
+                   static_cast<int32_t>(byte_at(a2, 0)) * k2 + static_cast<int32_t>(byte_at(a2, 3)) * k3;
     }
   }
   const int pitch = tmp_pitch(out_w);

@@ -104,7 +104,7 @@ class BatchImageTransform:
         stage_dev = self._grow("_stage_dev", total, device=dev)
         stage_np = stage.numpy()
         descs = (_lib.ImageDesc * n).from_buffer(stage_np)   # descriptors live at the head of the staging buffer
-        keep = []
+        keep, direct = [], []
         for i, t in enumerate(imgs):
             h, w = int(t.shape[0]), int(t.shape[1])
             d = descs[i]
@@ -113,6 +113,9 @@ class BatchImageTransform:
                     t = t.to(dev)
                 keep.append(t)
                 d.src, d.stride = t.data_ptr(), t.stride(0)
+            elif t.is_pinned():   # already page-locked (DataLoader pin_memory): straight to the device, no host memcpy
+                direct.append((offs[i], t))
+                d.src, d.stride = stage_dev.data_ptr() + offs[i], 3 * w
             else:
                 stage[offs[i]:offs[i] + t.numel()].view(h, w, 3).copy_(t)
                 d.src, d.stride = stage_dev.data_ptr() + offs[i], 3 * w
@@ -122,7 +125,13 @@ class BatchImageTransform:
         need = lib.fiber_image_transform_plan(descs, n, oh, ow)
         if need == 0:
             raise RuntimeError("fiber_b200.image_transform_plan failed: %s" % lib.fiber_last_error().decode())
-        stage_dev[:total].copy_(stage[:total], non_blocking=True)
+        if direct:   # descriptors + the pageable images' staging area in one copy, pinned images one copy each
+            head = max([n * dsz] + [o + imgs[i].numel() for i, o in enumerate(offs) if o is not None and not imgs[i].is_pinned()])
+            stage_dev[:head].copy_(stage[:head], non_blocking=True)
+            for o, t in direct:
+                stage_dev[o:o + t.numel()].view(t.shape).copy_(t, non_blocking=True)
+        else:
+            stage_dev[:total].copy_(stage[:total], non_blocking=True)
         self._stage_evt = torch.cuda.Event()
         self._stage_evt.record()
         ws = self._grow("_ws", need, device=dev)

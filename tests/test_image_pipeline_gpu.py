@@ -106,6 +106,19 @@ def test_full_size_batch_properties_and_buffer_reuse():
     assert np.array_equal(again[::-1], got)
 
 
+def test_pinned_pageable_and_device_images_in_one_batch():
+    from fiber_b200.transforms import BatchImageTransform
+    rng = np.random.default_rng(4)
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(90, 120), (64, 48), (33, 77), (120, 90), (50, 50), (71, 19)]]
+    mixed = [torch.from_numpy(images[0]).pin_memory(), images[1], torch.from_numpy(images[2]).cuda(),
+             torch.from_numpy(images[3]).pin_memory(), torch.from_numpy(images[4]), torch.from_numpy(images[5]).pin_memory()]
+    tr = BatchImageTransform(64)
+    for _ in range(2):   # second call reuses the staging buffers
+        got = tr(mixed).cpu().numpy()
+        for i, img in enumerate(images):
+            assert np.array_equal(got[i], O.albef_transform(img, 64)), i
+
+
 def test_errors_are_loud():
     from fiber_b200.transforms import BatchImageTransform
     with pytest.raises(RuntimeError, match="uint8"):
