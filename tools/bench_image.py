@@ -36,7 +36,35 @@ def _peak_gbs():
     return 6551.0, "SURVEY.md §9 (measured copy bandwidth)"
 
 
-def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, warmup=5, cpu_sample=16, sweep=False):
+def _ref_one(args):
+    """One image through the libraries the reference's `albef` transform calls (worker-process body)."""
+    from PIL import Image
+    from torchvision import transforms as T
+    a, size = args
+    tr = T.Compose([T.Resize((size, size), interpolation=T.InterpolationMode.BICUBIC), T.ToTensor(),
+                    T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+    return float(tr(Image.fromarray(a))[0, 0, 0])
+
+
+def _all_cores_baseline(images, size):
+    """The same per-image transform on every host core, one process each (the reference's DataLoader runs
+    `num_workers` such processes, config.py:91).  Spawned, not forked: the parent holds a CUDA context."""
+    try:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        with mp.get_context("spawn").Pool(cores, initializer=torch.set_num_threads, initargs=(1,)) as pool:
+            work = [(a, size) for a in images] * max(1, (8 * cores) // len(images))
+            pool.map(_ref_one, work[:cores])          # warm the workers
+            t0 = time.perf_counter()
+            pool.map(_ref_one, work, chunksize=1)
+            return {"value": len(work) / (time.perf_counter() - t0), "unit": "images/s", "cores": cores,
+                    "sample": "%d transforms over %d worker processes" % (len(work), cores)}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, warmup=5, cpu_sample=16, sweep=False,
+                           all_cores_baseline=False):
     from fiber_b200 import lib
     from fiber_b200.transforms import albef_transform
     h, w = src
@@ -115,7 +143,10 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
         outs = [ref(p) for p in pil]
         t_cpu = (time.perf_counter() - t0) / len(pil)
         same = bool(torch.equal(torch.stack(outs), tr(host[:cpu_sample]).cpu()))
-        rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "images/s", "cores": 1, "kind": "reference",
+        all_cores = None
+        if all_cores_baseline:
+            all_cores = _all_cores_baseline(host[:cpu_sample], size)
+        rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "images/s", "cores": 1, "kind": "reference", "all_cores": all_cores,
                                "sample": "%d of the batch's images through Pillow %s resize + torchvision ToTensor/Normalize "
                                          "(what transforms/transform.py:10-17 runs per image in a DataLoader worker)"
                                          % (len(pil), Image.__version__),
@@ -137,7 +168,7 @@ def main():
     h, w = (int(v) for v in a.src.split("x"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup, sweep=a.sweep)))
+    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup, sweep=a.sweep, all_cores_baseline=True)))
 
 
 if __name__ == "__main__":
