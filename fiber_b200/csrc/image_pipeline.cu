@@ -57,14 +57,15 @@ __global__ void __launch_bounds__(256) image_vpass_kernel(const fiber_image_desc
 }
 
 // "image_variant": bit 0 = the horizontal pass reads the source as aligned words (hpass_words_body) instead of bytes,
-// bit 1 = eight output columns per thread in the vertical pass instead of four.  Same bytes out either way.
+// bit 1 = eight output columns per thread in the vertical pass instead of four, bit 2 = sixteen; bit 3 = eight source rows
+// per thread in the word-form horizontal pass instead of four.  Same bytes out either way.
 // FIBER_IMAGE_VARIANT.
 static std::atomic<int> g_variant{-1};
 static int option_variant() {
   int v = g_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_IMAGE_VARIANT");
-    v = e ? (atoi(e) & 3) : kDefaultVariant;
+    v = e ? (atoi(e) & 15) : kDefaultVariant;
     g_variant.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -73,7 +74,7 @@ static int option_variant() {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace img
-void set_image_variant(int v) { img::g_variant.store(v < 0 ? -1 : (v & 3), std::memory_order_relaxed); }
+void set_image_variant(int v) { img::g_variant.store(v < 0 ? -1 : (v & 15), std::memory_order_relaxed); }
 int get_image_variant() { return img::option_variant(); }
 }  // namespace fiber
 
@@ -139,17 +140,22 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
   const dim3 g1(((out_w + out_h > 768 ? out_w + out_h : 768) + 127) / 128, n);
   FIBER_CUDA(fiber::launch_k(image_coeffs_kernel, g1, dim3(128), 0, stream, dd, ws, norm, out_h, out_w));
   const int variant = option_variant();
-  const int R = 4, W = (variant & 2) ? 2 : 1;
+  const int R = (variant & 9) == 9 ? 8 : 4, W = (variant & 4) ? 4 : ((variant & 2) ? 2 : 1);
   const long long hwork = static_cast<long long>((max_box_h + R - 1) / R) * out_w;
   const long long vwork = static_cast<long long>(out_h) * ((out_w / 4 + W - 1) / W);
   FIBER_CHECK(hwork < (1LL << 31) && vwork < (1LL << 31), "image_transform: image too large for 32-bit indexing");
   const dim3 g2(static_cast<unsigned>((hwork + 255) / 256), n);
-  if (variant & 1)
+  if (R == 8)
+    FIBER_CUDA(fiber::launch_k(image_hpass_words_kernel<8>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
+  else if (variant & 1)
     FIBER_CUDA(fiber::launch_k(image_hpass_words_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
   else
     FIBER_CUDA(fiber::launch_k(image_hpass_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
   const dim3 g3(static_cast<unsigned>((vwork + 255) / 256), n);
-  if (W == 2)
+  if (W == 4)
+    FIBER_CUDA(fiber::launch_k(image_vpass_kernel<4>, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), out, out_h,
+                               out_w));
+  else if (W == 2)
     FIBER_CUDA(fiber::launch_k(image_vpass_kernel<2>, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), out, out_h,
                                out_w));
   else

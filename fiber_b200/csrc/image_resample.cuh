@@ -299,6 +299,24 @@ FIBER_HD void hpass_words_body(const fiber_image_desc* descs, void* ws, int out_
   }
 }
 
+// W consecutive plane words (4 W pixels) in one load; the address is 4 W-byte aligned by construction.
+template <int W>
+FIBER_HD void load_words(const uint8_t* p, uint32_t (&v)[W]) {
+#ifdef __CUDA_ARCH__
+  if constexpr (W == 4) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else if constexpr (W == 2) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = q.x; v[1] = q.y;
+  } else {
+    v[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+  }
+#else
+  for (int w = 0; w < W; ++w) v[w] = reinterpret_cast<const uint32_t*>(p)[w];
+#endif
+}
+
 // ---- kernel 3: vertical pass + ToTensor + Normalize (+ horizontal flip).  idx in [0, out_h * ceil(out_w / (4 W)))
 // per image: 4 W consecutive output columns of one row, all three channels (12 W accumulators per coefficient load);
 // float32 NCHW out.  lut = the [3][256] table of normalised values (shared memory on the device).  W = 1 or 2
@@ -327,10 +345,12 @@ FIBER_HD void vpass_body(const fiber_image_desc* descs, const void* ws, const fl
     const int32_t k = ldg(kp);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+      // x % (4 W) == 0 and pitch % 16 == 0: aligned; the pitch padding keeps a partial last group inside the plane row
+      uint32_t pw[W];
+      load_words<W>(col + c * plane, pw);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        // x % 4 == 0 and pitch % 16 == 0: aligned; the pitch padding keeps a partial last group inside the plane row
-        const uint32_t p = ldg(reinterpret_cast<const uint32_t*>(col + c * plane) + w);
+        const uint32_t p = pw[w];
         a[c][w][0] += static_cast<int32_t>(p & 0xff) * k;
         a[c][w][1] += static_cast<int32_t>((p >> 8) & 0xff) * k;
         a[c][w][2] += static_cast<int32_t>((p >> 16) & 0xff) * k;

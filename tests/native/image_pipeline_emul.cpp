@@ -36,13 +36,18 @@ static int run(const fiber_image_desc* d, int n, int out_h, int out_w, const flo
   return 0;
 }
 
-// variant: the library's "image_variant" option (bit 0: word-form horizontal pass, bit 1: eight columns per thread)
+// variant: the library's "image_variant" option (bit 0: word-form horizontal pass, bit 1 / 2: eight / sixteen
+// columns per thread, bit 3: eight rows per thread)
 extern "C" int emul_image_transform(const fiber_image_desc* d, int n, int out_h, int out_w, const float* mean,
                                     const float* stdv, void* ws, float* out, int variant) {
-  switch (variant & 3) {
+  switch (variant & 15) {
     case 0: return run<4, 1, false>(d, n, out_h, out_w, mean, stdv, ws, out);
     case 1: return run<4, 1, true>(d, n, out_h, out_w, mean, stdv, ws, out);
     case 2: return run<4, 2, false>(d, n, out_h, out_w, mean, stdv, ws, out);
-    default: return run<4, 2, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 3: return run<4, 2, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 5: case 7: return run<4, 4, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 11: return run<8, 2, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    case 13: case 15: return run<8, 4, true>(d, n, out_h, out_w, mean, stdv, ws, out);
+    default: return -1;
   }
 }

@@ -88,7 +88,7 @@ def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, 
     return out
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7, 11, 15])
 def test_kernel_bodies_match_oracle_ragged_batch(emul, variant):
     rng = np.random.default_rng(11)
     sizes = [(97, 131), (48, 64), (64, 64), (7, 5), (211, 89), (30, 300), (64, 65), (1, 1), (130, 64)]
