@@ -89,7 +89,9 @@ size_t fiber_image_transform_plan(fiber_image_desc* d, int32_t n, int32_t out_h,
   size_t off = kLutBytes;
   for (int i = 0; i < n; ++i) {
     fiber_image_desc& e = d[i];
-    if (!e.src || e.h <= 0 || e.w <= 0 || e.stride < 3LL * e.w || e.box_w <= 0 || e.box_h <= 0 || e.box_x < 0 || e.box_y < 0 ||
+    const bool layout_ok = e.planar ? (e.planar == 1 && e.stride >= e.w && e.chan_stride >= static_cast<int64_t>(e.h - 1) * e.stride + e.w)
+                                    : e.stride >= 3LL * e.w;
+    if (!e.src || e.h <= 0 || e.w <= 0 || !layout_ok || e.box_w <= 0 || e.box_h <= 0 || e.box_x < 0 || e.box_y < 0 ||
         e.box_x + e.box_w > e.w || e.box_y + e.box_h > e.h) {
       fiber::set_last_error("image_transform_plan: image %d: bad size, stride or crop box", i);
       return 0;
@@ -100,7 +102,6 @@ size_t fiber_image_transform_plan(fiber_image_desc* d, int32_t n, int32_t out_h,
     }
     e.ksize_x = ksize_for(e.box_w, out_w);
     e.ksize_y = ksize_for(e.box_h, out_h);
-    e.reserved = 0;
     e.coef_off = static_cast<int64_t>(off);
     off = align_up(off + static_cast<size_t>(table_ints(e, out_h, out_w)) * sizeof(int32_t), 16);
   }
@@ -122,8 +123,10 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
   FIBER_CHECK(n <= 65535, "image_transform: at most 65535 images per call");
   int max_box_h = 0;
   size_t need = 0;
+  bool any_planar = false;
   for (int i = 0; i < n; ++i) {
     const fiber_image_desc& e = dh[i];
+    any_planar = any_planar || e.planar != 0;
     FIBER_CHECK(e.ksize_x == ksize_for(e.box_w, out_w) && e.ksize_y == ksize_for(e.box_h, out_h) && e.coef_off >= kLutBytes &&
                     e.tmp_off >= 0,
                 "image_transform: descriptor %d was not planned for this output size (fiber_image_transform_plan)", i);
@@ -139,7 +142,7 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
   }
   const dim3 g1(((out_w + out_h > 768 ? out_w + out_h : 768) + 127) / 128, n);
   FIBER_CUDA(fiber::launch_k(image_coeffs_kernel, g1, dim3(128), 0, stream, dd, ws, norm, out_h, out_w));
-  const int variant = option_variant();
+  const int variant = any_planar ? (option_variant() & ~9) : option_variant();  // planar sources: byte-form horizontal pass
   const int R = (variant & 9) == 9 ? 8 : 4, W = (variant & 4) ? 4 : ((variant & 2) ? 2 : 1);
   const long long hwork = static_cast<long long>((max_box_h + R - 1) / R) * out_w;
   const long long vwork = static_cast<long long>(out_h) * ((out_w / 4 + W - 1) / W);

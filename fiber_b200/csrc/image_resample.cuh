@@ -168,7 +168,7 @@ FIBER_HD void coeffs_body(const fiber_image_desc* descs, void* ws, int out_h, in
 // ---- kernel 2: horizontal pass.  idx in [0, ceil(box_h / R) * out_w) per image: one output column of R consecutive
 // source rows, all three channels (3 R accumulators per coefficient load); interleaved RGB bytes in, three byte planes
 // [3][box_h][pitch] out.  Rows past the box are computed on a duplicate of the last row and not stored, so the tap
-// loop carries no predicates. ----------------------------------------------------
+// loop carries no predicates.  Handles both source layouts (the word form below is for interleaved bytes only). ----------------------------------------------------
 template <int R>
 FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int out_w, int image, int idx) {
   const fiber_image_desc d = descs[image];
@@ -180,11 +180,13 @@ FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int
   const Tables t = tables_of(d, ws, out_h, out_w);
   const int xmin = ldg(t.bx + 2 * x), n = ldg(t.bx + 2 * x + 1);
   const int rows = d.box_h - y0 < R ? d.box_h - y0 : R;
+  // byte addressing of both layouts: pixel step ps and channel step cs (3 / 1 interleaved, 1 / chan_stride planar)
+  const int64_t ps = d.planar ? 1 : 3, cs = d.planar ? d.chan_stride : 1;
   const uint8_t* p[R];
 #pragma unroll
   for (int r = 0; r < R; ++r)
     p[r] = d.src + static_cast<int64_t>(d.box_y + y0 + (r < rows ? r : rows - 1)) * d.stride +
-           static_cast<int64_t>(d.box_x + xmin) * 3;
+           static_cast<int64_t>(d.box_x + xmin) * ps;
   int32_t acc[R][3];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
@@ -194,9 +196,9 @@ FIBER_HD void hpass_body(const fiber_image_desc* descs, void* ws, int out_h, int
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       acc[r][0] += static_cast<int32_t>(ldg(p[r])) * k;
-      acc[r][1] += static_cast<int32_t>(ldg(p[r] + 1)) * k;
-      acc[r][2] += static_cast<int32_t>(ldg(p[r] + 2)) * k;
-      p[r] += 3;
+      acc[r][1] += static_cast<int32_t>(ldg(p[r] + cs)) * k;
+      acc[r][2] += static_cast<int32_t>(ldg(p[r] + 2 * cs)) * k;
+      p[r] += ps;
     }
   }
   const int pitch = tmp_pitch(out_w);

@@ -82,8 +82,8 @@ class ImageDesc(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("stride", C.c_int64), ("h", C.c_int32), ("w", C.c_int32),
         ("box_x", C.c_int32), ("box_y", C.c_int32), ("box_w", C.c_int32), ("box_h", C.c_int32),
-        ("flip", C.c_int32), ("ksize_x", C.c_int32), ("ksize_y", C.c_int32), ("reserved", C.c_int32),
-        ("coef_off", C.c_int64), ("tmp_off", C.c_int64),
+        ("flip", C.c_int32), ("ksize_x", C.c_int32), ("ksize_y", C.c_int32), ("planar", C.c_int32),
+        ("coef_off", C.c_int64), ("tmp_off", C.c_int64), ("chan_stride", C.c_int64),
     ]
 
 

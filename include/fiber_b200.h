@@ -285,19 +285,20 @@ int fiber_adamw_multi(const void* tensors, const void* chunks, int32_t n_chunks,
  * fixed-point coefficients evaluated in double precision, each pass rounded and clamped to a byte) and torchvision's
  * float32 (v / 255 - mean) / std.  JPEG decoding and RandomAugment's photometric / affine operations stay with the caller.
  *
- * One fiber_image_desc per image.  The caller fills src .. flip; fiber_image_transform_plan (host only, no CUDA call)
+ * One fiber_image_desc per image.  The caller fills src .. flip, planar and chan_stride; fiber_image_transform_plan (host only, no CUDA call)
  * fills the rest and returns the workspace size in bytes (0 on error).  Images are ragged: every descriptor has its own
  * size, row stride and crop box.  Pillow >= 11 resamples the vertical axis first when h > 100 w; such boxes are rejected. */
 typedef struct fiber_image_desc {
-  const uint8_t* src;                  /* DEVICE pointer: row 0, column 0 of the decoded image, RGB interleaved */
-  int64_t stride;                      /* bytes between source rows (>= 3 w) */
+  const uint8_t* src;                  /* DEVICE pointer: row 0, column 0 (channel 0) of the decoded image */
+  int64_t stride;                      /* bytes between source rows (>= 3 w interleaved, >= w planar) */
   int32_t h, w;                        /* decoded size */
   int32_t box_x, box_y, box_w, box_h;  /* crop (torchvision resized_crop: left, top, width, height); whole image = 0,0,w,h */
   int32_t flip;                        /* 1: RandomHorizontalFlip applied after the resize */
   int32_t ksize_x, ksize_y;            /* plan: taps per output sample, horizontal / vertical */
-  int32_t reserved;
+  int32_t planar;                      /* 0: RGB bytes interleaved (PIL / numpy HWC); 1: three byte planes (CHW, what nvJPEG decoders return) */
   int64_t coef_off;                    /* plan: byte offset of this image's coefficient tables in the workspace */
   int64_t tmp_off;                     /* plan: byte offset of its horizontally resampled byte planes [3][box_h][pitch] */
+  int64_t chan_stride;                 /* planar only: bytes between channel planes (>= h stride) */
 } fiber_image_desc;
 size_t fiber_image_transform_plan(fiber_image_desc* descs_host, int32_t n, int32_t out_h, int32_t out_w);
 /* descs_host: the planned descriptors (read on the host for grid sizes); descs_dev: a DEVICE copy of the same array;

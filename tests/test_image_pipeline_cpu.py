@@ -60,7 +60,7 @@ def emul(tmp_path_factory):
     return C.CDLL(str(so))
 
 
-def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, variant=0):
+def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, variant=0, planar=None):
     from fiber_b200 import lib as L
     lib = L.load()
     n = len(images)
@@ -70,12 +70,22 @@ def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, 
         h, w = img.shape[:2]
         stride = strides[i] if strides else 3 * w
         lead = 16 + i % 4       # every byte alignment of the first pixel; padding for the word-form pass's aligned words
-        raw = np.full(lead + h * stride + 16, 0xAB, np.uint8)
-        buf = raw[lead:lead + h * stride].reshape(h, stride)
-        buf[:, :3 * w] = img.reshape(h, 3 * w)
-        keep.append(raw)
         d = descs[i]
-        d.src, d.stride, d.h, d.w = buf.ctypes.data, stride, h, w
+        if planar and planar[i]:   # three byte planes [3][h][w + pad], a gap between the planes
+            pstride, gap = w + i % 3, 5 * (i % 2)
+            raw = np.full(lead + 3 * (h * pstride + gap) + 16, 0xAB, np.uint8)
+            for c in range(3):
+                o = lead + c * (h * pstride + gap)
+                raw[o:o + h * pstride].reshape(h, pstride)[:, :w] = img[:, :, c]
+            keep.append(raw)
+            d.src, d.stride, d.h, d.w = raw.ctypes.data + lead, pstride, h, w
+            d.planar, d.chan_stride = 1, h * pstride + gap
+        else:
+            raw = np.full(lead + h * stride + 16, 0xAB, np.uint8)
+            buf = raw[lead:lead + h * stride].reshape(h, stride)
+            buf[:, :3 * w] = img.reshape(h, 3 * w)
+            keep.append(raw)
+            d.src, d.stride, d.h, d.w = buf.ctypes.data, stride, h, w
         d.box_x, d.box_y, d.box_w, d.box_h = boxes[i] if boxes else (0, 0, w, h)
         d.flip = int(flips[i]) if flips else 0
     need = lib.fiber_image_transform_plan(descs, n, out_h, out_w)
@@ -114,6 +124,19 @@ def test_kernel_bodies_match_library_golden_with_crop_and_flip(emul, variant):
         assert np.array_equal(got[1], GOLD["crop_%d" % i])
 
 
+@pytest.mark.parametrize("variant", [0, 2])
+def test_kernel_bodies_planar_sources(emul, variant):
+    """Three byte planes per image (what GPU JPEG decoders return) next to interleaved ones in the same batch."""
+    rng = np.random.default_rng(12)
+    sizes = [(97, 131), (48, 64), (7, 5), (130, 64), (33, 200)]
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    boxes = [(3, 2, w - 5, h - 4) if min(h, w) > 10 else (0, 0, w, h) for h, w in sizes]
+    got = _run_emul(emul, images, 40, 72, boxes=boxes, flips=[0, 1, 0, 1, 1], variant=variant,
+                    planar=[True, False, True, True, True])
+    for i, img in enumerate(images):
+        assert np.array_equal(got[i], O.albef_transform_hw(img, 40, 72, box=boxes[i], flip=bool([0, 1, 0, 1, 1][i]))), sizes[i]
+
+
 def test_plan_rejects_bad_descriptors():
     from fiber_b200 import lib as L
     lib = L.load()
@@ -134,6 +157,10 @@ def test_plan_rejects_bad_descriptors():
     tall[0].box_w, tall[0].box_h = 1, 1000
     assert lib.fiber_image_transform_plan(tall, 1, 8, 8) == 0        # Pillow's rows-first special case
     assert lib.fiber_image_transform_plan(d, 0, 8, 8) == 0
+    d[0].stride, d[0].planar, d[0].chan_stride = 10, 1, 99           # planes overlap: chan_stride < (h - 1) stride + w
+    assert lib.fiber_image_transform_plan(d, 1, 8, 8) == 0
+    d[0].chan_stride = 100
+    assert lib.fiber_image_transform_plan(d, 1, 8, 8) > 0
 
 
 def test_random_draws_follow_torchvision_modules():

@@ -119,6 +119,56 @@ def test_pinned_pageable_and_device_images_in_one_batch():
             assert np.array_equal(got[i], O.albef_transform(img, 64)), i
 
 
+def test_planar_sources_equal_interleaved():
+    from fiber_b200.transforms import BatchImageTransform
+    rng = np.random.default_rng(6)
+    images = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in [(90, 120), (64, 48), (333, 500), (71, 19)]]
+    chw = [torch.from_numpy(a).permute(2, 0, 1).contiguous() for a in images]
+    mixed = [chw[0].cuda(), images[1], chw[2], chw[3].pin_memory()]
+    tr = BatchImageTransform((64, 96))
+    got = tr(mixed).cpu().numpy()
+    for i, img in enumerate(images):
+        assert np.array_equal(got[i], O.albef_transform_hw(img, 64, 96)), i
+    torch.manual_seed(3)
+    a = BatchImageTransform(64, random_crop=True)(images).cpu()
+    torch.manual_seed(3)
+    b = BatchImageTransform(64, random_crop=True)([c.cuda() for c in chw]).cpu()
+    assert torch.equal(a, b)
+
+
+def test_jpeg_decode_front_end():
+    """nvJPEG through torchvision, then the exact transform: equals the transform of the SAME decoded pixels bit for bit,
+    and stays within decoder rounding of the PIL-decoded path."""
+    Image = pytest.importorskip("PIL.Image")
+    import io
+    from fiber_b200.transforms import albef_transform, decode_jpegs
+    rng = np.random.default_rng(9)
+    yy, xx = np.mgrid[0:240, 0:320]
+    imgs = [np.clip(127 + 100 * (np.sin(xx / (9.0 + i)) * np.cos(yy / 7.0))[..., None] * np.array([1, 0.8, 0.6])
+                    + rng.normal(0, 4, (240, 320, 3)), 0, 255).astype(np.uint8) for i in range(3)]
+    data = []
+    for a in imgs:
+        buf = io.BytesIO()
+        Image.fromarray(a).save(buf, format="JPEG", quality=92, subsampling=0)
+        data.append(buf.getvalue())
+    try:
+        decoded = decode_jpegs(data)
+    except Exception as e:  # noqa: BLE001  (torchvision built without nvJPEG)
+        pytest.skip("GPU JPEG decode unavailable: %s" % e)
+    assert all(t.is_cuda and t.dtype == torch.uint8 and tuple(t.shape) == (3, 240, 320) for t in decoded)
+    tr = albef_transform(96)
+    got = tr(decoded).cpu().numpy()
+    for i, t in enumerate(decoded):
+        assert np.array_equal(got[i], O.albef_transform(t.permute(1, 2, 0).cpu().numpy(), 96)), i
+    pil = [np.asarray(Image.open(io.BytesIO(b)).convert("RGB")) for b in data]
+    ref = tr(pil).cpu().numpy()
+    lut = O.normalize_lut()
+    step = float(lut[0][1] - lut[0][0])                       # one grey level after normalisation
+    diff = np.abs(got - ref)
+    print("nvJPEG vs libjpeg after the transform: max %.2f grey levels, mean %.3f" % (diff.max() / step, diff.mean() / step))
+    assert diff.max() <= 8.5 * step and diff.mean() <= 1.0 * step
+
+
 def test_errors_are_loud():
     from fiber_b200.transforms import BatchImageTransform
     with pytest.raises(RuntimeError, match="uint8"):

@@ -46,6 +46,45 @@ def _ref_one(args):
     return float(tr(Image.fromarray(a))[0, 0, 0])
 
 
+def _measure_from_jpeg(tr, host, out, size, steps, warmup, cpu_sample):
+    """Encoded JPEG bytes -> batch: nvJPEG decode on the GPU (torchvision.io, a library call) + the transform, against
+    PIL decode + the per-image CPU transform on one core.  The decoders differ by rounding, so this leg is timed, not
+    compared bit for bit (tests/test_image_pipeline_gpu.py::test_jpeg_decode_front_end bounds the difference)."""
+    try:
+        import io
+        from PIL import Image
+        from torchvision import transforms as T
+        from fiber_b200.transforms import decode_jpegs
+        yy, xx = np.mgrid[0:host[0].shape[0], 0:host[0].shape[1]]
+        data = []
+        for i in range(len(host)):   # photo-like content (noise would make the files incompressible)
+            a = np.clip(127 + 100 * (np.sin(xx / (9.0 + i % 7)) * np.cos(yy / (5.0 + i % 5)))[..., None] * np.array([1, 0.8, 0.6])
+                        + host[i].astype(np.float32) * 0.05, 0, 255).astype(np.uint8)
+            buf = io.BytesIO()
+            Image.fromarray(a).save(buf, format="JPEG", quality=90)
+            data.append(buf.getvalue())
+        bufs = [torch.frombuffer(bytearray(b), dtype=torch.uint8) for b in data]
+        for _ in range(warmup):
+            tr(decode_jpegs(bufs), out=out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tr(decode_jpegs(bufs), out=out)
+        torch.cuda.synchronize()
+        t_gpu = (time.perf_counter() - t0) / steps
+        ref = T.Compose([T.Resize((size, size), interpolation=T.InterpolationMode.BICUBIC), T.ToTensor(),
+                         T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+        t0 = time.perf_counter()
+        for b in data[:cpu_sample]:
+            ref(Image.open(io.BytesIO(b)).convert("RGB"))
+        t_cpu = (time.perf_counter() - t0) / cpu_sample
+        return {"value": len(data) / t_gpu, "unit": "images/s", "jpeg_bytes_per_batch": sum(len(b) for b in data),
+                "decoder": "nvJPEG via torchvision.io.decode_jpeg(device='cuda') (library)", "cpu_one_core": 1.0 / t_cpu,
+                "note": "host wall clock: H2D of the encoded bytes, GPU decode to planar uint8, three transform kernels"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def _all_cores_baseline(images, size):
     """The same per-image transform on every host core, one process each (the reference's DataLoader runs
     `num_workers` such processes, config.py:91).  Spawned, not forked: the parent holds a CUDA context."""
@@ -64,7 +103,7 @@ def _all_cores_baseline(images, size):
 
 
 def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, warmup=5, cpu_sample=16, sweep=False,
-                           all_cores_baseline=False):
+                           all_cores_baseline=False, jpeg=False):
     from fiber_b200 import lib
     from fiber_b200.transforms import albef_transform
     h, w = src
@@ -131,6 +170,8 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
     }
     if variants:
         rec["variant_ms_per_batch"] = variants
+    if jpeg:
+        rec["from_jpeg_bytes"] = _measure_from_jpeg(tr, host, out, size, steps, warmup, cpu_sample)
     try:  # the reference's own per-image path on the host: PIL resize + torchvision ToTensor / Normalize
         from PIL import Image
         from torchvision import transforms as T
@@ -168,7 +209,7 @@ def main():
     h, w = (int(v) for v in a.src.split("x"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup, sweep=a.sweep, all_cores_baseline=True)))
+    print(json.dumps(measure_image_pipeline(dev, a.batch, (h, w), a.size, a.steps, a.warmup, sweep=a.sweep, all_cores_baseline=True, jpeg=True)))
 
 
 if __name__ == "__main__":
