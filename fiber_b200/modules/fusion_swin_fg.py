@@ -97,9 +97,10 @@ class SwinTransformerBlock(nn.Module):  # :233-347
         z = z.reshape(B, T, C)
         s = self.drop_path.sample_scale(B, x.device)
         x = x + (z if s is None else z * s.view(B, 1, 1).to(z.dtype))
-        m = self.mlp(self.norm2(x))
         s = self.drop_path.sample_scale(B, x.device)
-        return x + (m if s is None else m * s.view(B, 1, 1).to(m.dtype))
+        # LN2 -> fc1 -> GELU -> fc2 (+ residual, DropPath scale) as one node (no padding in this half)
+        return ops.MlpResidualFn.apply(x, s, self.norm2.weight, self.norm2.bias, self.norm2.eps, self.mlp.fc1.weight,
+                                       self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
 
 
 class PatchMerging(nn.Module):  # :348-390

@@ -609,6 +609,43 @@ class MlpFn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2
 
 
+class MlpResidualFn(torch.autograd.Function):
+    """The MLP half of a Swin block as one node: out = x + s * fc2(GELU(fc1(LN(x)))) with the residual and the DropPath
+    row scale in the fc2 epilogue and the residual gradient inside the LayerNorm backward — the second half of
+    SwinBlockFn, for callers whose attention half needs torch ops in between (padded window grids of the fine-grained
+    backbone, fusion_swin_transformer_v2.py:340-346).  x [B, T, C]; s [B] per-sample scale (0 or 1 / keep) or None."""
+
+    @staticmethod
+    def forward(ctx, x, s, n_w, n_b, eps, w1, b1, w2, b2):
+        B, T, C = x.shape
+        x1 = _to_bf16_2d(x)
+        g = n_w.detach()
+        ln, mean, rstd, _ = K.layernorm_fwd(x1, g, n_b.detach(), eps)
+        w1b, w1t = CACHE.weights((w1,))
+        h = torch.empty((B * T, w1.shape[0]), device=x.device, dtype=BF16)
+        a, cached = _fc1_gelu(ln, w1b, b1.detach(), h)
+        w2b, w2t = CACHE.weights((w2,))
+        out = K.gemm(a, w2b, bias=b2.detach(), residual=x1, row_scale=s, rows_per_scale=T)
+        ctx.saved = (x1, ln, mean, rstd, g, h, a, cached, w1t, w2t, s, (B, T, C))
+        return out.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x1, ln, mean, rstd, g, h, a, cached, w1t, w2t, s, (B, T, C) = ctx.saved
+        d_out = _to_bf16_2d(dout)
+        dz = K.scale_rows(d_out, s, T) if s is not None else d_out
+        db2 = torch.zeros(C, device=dz.device, dtype=F32)
+        dw2 = _wgrad(dz, a, db=db2)
+        dh = _fc2_dgrad_gelu(dz, w2t, h, cached)
+        db1 = torch.zeros(dh.shape[1], device=dz.device, dtype=F32)
+        dw1 = _wgrad(dh, ln, db=db1)
+        dln = K.gemm(dh, w1t)
+        dg, dbeta = torch.zeros_like(g), torch.zeros_like(g)
+        dx = K.layernorm_bwd(dln, x1, mean, rstd, g, dres=d_out, dgamma=dg, dbeta=dbeta)
+        ctx.saved = None
+        return dx.view(B, T, C), None, dg, dbeta, None, dw1, db1, dw2, db2
+
+
 # ---------------------------------------------------------------------------------------------
 # RoBERTa
 # ---------------------------------------------------------------------------------------------
