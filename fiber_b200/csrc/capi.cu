@@ -164,6 +164,7 @@ int axpy_dispatch(const bf16*, long long, const bf16*, long long, const float*, 
                   cudaStream_t);
 int cast_transpose_dispatch(const float*, long long, int, int, bf16*, long long, bf16*, long long, cudaStream_t);
 int patch_gather_dispatch(const float*, bf16*, int, int, int, cudaStream_t);
+int grid_copy_dispatch(const bf16*, bf16*, const bf16*, const float*, int, int, int, int, int, int, cudaStream_t);
 int embed_dispatch(const long long*, int, int, int, int, const float*, const float*, const float*, bf16*, long long,
                    cudaStream_t);
 int embed_scatter_dispatch(const long long*, int, int, int, int, const bf16*, long long, float*, float*, cudaStream_t);
@@ -321,6 +322,10 @@ int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t s) {
 int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void* w_out, int64_t ld_out, void* wt_out,
                          int64_t ldt_out, fiber_stream_t s) {
   return fiber::cast_transpose_dispatch(w, ldw, n, k, FIBER_BM(w_out), ld_out, FIBER_BM(wt_out), ldt_out, FIBER_S(s));
+}
+int fiber_grid_copy(const void* src, void* dst, const void* add, const float* row_scale, int32_t batch, int32_t hs, int32_t ws,
+                    int32_t hd, int32_t wd, int32_t c, fiber_stream_t s) {
+  return fiber::grid_copy_dispatch(FIBER_B(src), FIBER_BM(dst), FIBER_B(add), row_scale, batch, hs, ws, hd, wd, c, FIBER_S(s));
 }
 int fiber_patch_gather(const float* img, void* out, int32_t batch, int32_t r, fiber_stream_t s) {
   return fiber::patch_gather_dispatch(img, FIBER_BM(out), batch, r, r, FIBER_S(s));

@@ -820,6 +820,46 @@ __global__ void __launch_bounds__(256) rowwise_scale_kernel(const bf16* x, long 
   }
 }
 
+// Crop / zero-pad of a token grid with the DropPath scale and the residual fused:
+//   dst[b, h, w, :] = (h < Hs && w < Ws ? src[b, h, w, :] * row_scale[b] : 0) + add[b, h, w, :]      (h < Hd, w < Wd)
+// src [B, Hs, Ws, C], dst / add [B, Hd, Wd, C], contiguous bf16; row_scale and add optional.  Hd <= Hs crops (the
+// fine-grained block's `x = shortcut + drop_path(x[:, :H, :W])`, fusion_swin_transformer_v2.py:336-343), Hd > Hs pads
+// with zeros (its backward, and the F.pad of :316-321).
+__global__ void __launch_bounds__(256) grid_copy_kernel(const bf16* src, bf16* dst, const bf16* add, const float* row_scale,
+                                                        int B, int Hs, int Ws, int Hd, int Wd, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int vec_per_row = C / 8;
+  const long long total = static_cast<long long>(B) * Hd * Wd * vec_per_row;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const long long tok = i / vec_per_row;
+    const int w = static_cast<int>(tok % Wd);
+    const int h = static_cast<int>((tok / Wd) % Hd);
+    const int b = static_cast<int>(tok / (static_cast<long long>(Wd) * Hd));
+    float v[8];
+    if (h < Hs && w < Ws) {
+      load8(src + ((static_cast<long long>(b) * Hs + h) * Ws + w) * C + c, v);
+      if (row_scale) {
+        const float s = row_scale[b];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= s;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    }
+    if (add) {
+      float a[8];
+      load8(add + tok * C + c, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += a[e];
+    }
+    store8(dst + tok * C + c, v);
+  }
+}
+
 // out = add + (*alpha) * x   (gate: a + alpha_t2i * c, roberta.py:483; plain residual add when alpha == null)
 __global__ void __launch_bounds__(256) axpy_kernel(const bf16* x, long long ldx, const bf16* add, long long lda,
                                                    const float* alpha, bf16* out, long long ldo, long long M, int N) {
@@ -1009,6 +1049,17 @@ int rowwise_scale_dispatch(const bf16* x, long long ldx, bf16* y, long long ldy,
   FIBER_CHECK(mode == 0 ? (p >= 0.f && p < 1.f) : row_scale != nullptr, "bad rowwise op arguments");
   FIBER_CUDA(launch_k(rowwise_scale_kernel, dim3(ew_grid(M * (N / 8))), dim3(256), 0, stream, x, ldx, y, ldy, M, N, mode, p, seed, row_scale,
                                                                 rps > 0 ? rps : 1));
+  FIBER_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int grid_copy_dispatch(const bf16* src, bf16* dst, const bf16* add, const float* row_scale, int B, int Hs, int Ws, int Hd,
+                       int Wd, int C, cudaStream_t stream) {
+  FIBER_CHECK(src && dst && B > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0 && C > 0 && C % 8 == 0,
+              "grid_copy: empty grid or C not a multiple of 8");
+  FIBER_CUDA(launch_k(grid_copy_kernel, dim3(ew_grid(static_cast<long long>(B) * Hd * Wd * (C / 8))), dim3(256), 0, stream, src, dst,
+                      add, row_scale, B, Hs, Ws, Hd, Wd, C));
   FIBER_CUDA(cudaGetLastError());
   count_launch();
   return 0;

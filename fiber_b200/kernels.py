@@ -388,6 +388,26 @@ def cast_transpose(w, w_out=None, wt_out=None):
         _ptr(wt_out), 0 if wt_out is None else wt_out.stride(0), _stream()), "cast_transpose")
 
 
+def grid_copy(src, out_hw, row_scale=None, add=None):
+    """src [B, Hs, Ws, C] bf16 contiguous -> [B, Hd, Wd, C]: crop (Hd <= Hs) or zero-pad (Hd >= Hs), optionally scaled
+    per sample (fp32 [B]) and added to `add` [B, Hd, Wd, C]."""
+    _req(src, BF16, "src")
+    if src.dim() != 4 or not src.is_contiguous():
+        raise RuntimeError("fiber_b200.grid_copy expects a contiguous [B, H, W, C] tensor")
+    B, Hs, Ws, Cc = src.shape
+    Hd, Wd = out_hw
+    out = torch.empty((B, Hd, Wd, Cc), device=src.device, dtype=BF16)
+    if add is not None:
+        _req(add, BF16, "add")
+        if tuple(add.shape) != (B, Hd, Wd, Cc) or not add.is_contiguous():
+            raise RuntimeError("fiber_b200.grid_copy: add must be contiguous [B, Hd, Wd, C]")
+    if row_scale is not None:
+        _req(row_scale, F32, "row_scale")
+    _lib.check(_lib.load().fiber_grid_copy(src.data_ptr(), out.data_ptr(), _ptr(add), _ptr(row_scale), B, Hs, Ws, Hd, Wd, Cc,
+                                           _stream()), "grid_copy")
+    return out
+
+
 def patch_gather(img):
     """im2row of the 4x4 / stride-4 patch embedding: fp32 [B,3,H,W] -> bf16 [B*(H/4)*(W/4), 64] (48 values + zero pad)."""
     _req(img, F32, "img")

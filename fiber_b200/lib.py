@@ -125,6 +125,7 @@ def load():
     lib.fiber_cast_f32_bf16.argtypes = [V, V, I64, V]
     lib.fiber_axpy.argtypes = [V, I64, V, I64, V, V, I64, I64, I32, V]
     lib.fiber_cast_transpose.argtypes = [V, I64, I32, I32, V, I64, V, I64, V]
+    lib.fiber_grid_copy.argtypes = [V, V, V, V, I32, I32, I32, I32, I32, I32, V]
     lib.fiber_patch_gather.argtypes = [V, V, I32, I32, V]
     lib.fiber_patch_gather_hw.argtypes = [V, V, I32, I32, I32, V]
     lib.fiber_embed_gather.argtypes = [V, I32, I32, I32, I32, V, V, V, V, I64, V]

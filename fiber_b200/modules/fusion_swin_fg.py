@@ -91,12 +91,8 @@ class SwinTransformerBlock(nn.Module):  # :233-347
             km = None if mask_text is None else mask_text.reshape(B, L).float()
             y = a.proj_i2t(ops.CrossAttnFn.apply(q2, kvt, km, B, Hp * Wp, L, self.num_heads))
             z = (z.float() + a.alpha_i2t * y.float()).to(BF16)
-        z = z.view(B, Hp, Wp, C)
-        if padded:
-            z = z[:, :H, :W]
-        z = z.reshape(B, T, C)
         s = self.drop_path.sample_scale(B, x.device)
-        x = x + (z if s is None else z * s.view(B, 1, 1).to(z.dtype))
+        x = ops.CropScaleAddFn.apply(x, z, s, (H, W), (Hp, Wp))   # shortcut + drop_path(z[:, :H, :W]) in one pass
         s = self.drop_path.sample_scale(B, x.device)
         # LN2 -> fc1 -> GELU -> fc2 (+ residual, DropPath scale) as one node (no padding in this half)
         return ops.MlpResidualFn.apply(x, s, self.norm2.weight, self.norm2.bias, self.norm2.eps, self.mlp.fc1.weight,

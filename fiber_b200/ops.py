@@ -609,6 +609,28 @@ class MlpFn(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2
 
 
+class CropScaleAddFn(torch.autograd.Function):
+    """out[b, h, w] = x[b, h, w] + s[b] * z[b, h, w] for h < H, w < W with z on a (zero-padded) Hp x Wp grid: the crop,
+    DropPath scale and residual add of the fine-grained Swin block (fusion_swin_transformer_v2.py:336-343) in one pass;
+    backward: dx = dout, dz = zero-padded s * dout in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, z, s, hw, hw_padded):
+        (H, W), (Hp, Wp) = hw, hw_padded
+        B, T, C = x.shape
+        out = K.grid_copy(z.reshape(B, Hp, Wp, C).contiguous(), (H, W), row_scale=s, add=_to_bf16_2d(x).view(B, H, W, C))
+        ctx.saved = (s, hw, hw_padded, z.shape)
+        return out.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        s, (H, W), (Hp, Wp), zshape = ctx.saved
+        B, T, C = dout.shape
+        d = dout.to(BF16).contiguous().view(B, H, W, C)
+        dz = K.grid_copy(d, (Hp, Wp), row_scale=s)
+        return dout, dz.view(zshape), None, None, None
+
+
 class MlpResidualFn(torch.autograd.Function):
     """The MLP half of a Swin block as one node: out = x + s * fc2(GELU(fc1(LN(x)))) with the residual and the DropPath
     row scale in the fc2 epilogue and the residual gradient inside the LayerNorm backward — the second half of

@@ -241,6 +241,12 @@ int fiber_scale_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t m
  * un-normalised residual of RobertaOutput with last_norm=False (roberta.py:420-423) */
 int fiber_axpy(const void* x, int64_t ldx, const void* add, int64_t ldadd, const float* alpha, void* out, int64_t ldo,
                int64_t m, int32_t n, fiber_stream_t stream);
+/* Crop / zero-pad of a bf16 token grid with the DropPath scale and the residual fused (fine-grained Swin block,
+ * fine_grained/maskrcnn_benchmark/modeling/backbone/fusion_swin_transformer_v2.py:316-321 F.pad, :336-343 crop + residual):
+ * dst[b,h,w,:] = (h < hs && w < ws ? src[b,h,w,:] * row_scale[b] : 0) + add[b,h,w,:] for h < hd, w < wd; src [B,hs,ws,C],
+ * dst / add [B,hd,wd,C] contiguous; row_scale (fp32 [B]) and add may be NULL; C % 8 == 0. */
+int fiber_grid_copy(const void* src, void* dst, const void* add, const float* row_scale, int32_t batch, int32_t hs, int32_t ws,
+                    int32_t hd, int32_t wd, int32_t c, fiber_stream_t stream);
 int fiber_cast_f32_bf16(const float* x, void* y, int64_t n, fiber_stream_t stream);
 /* fp32 master weight [n,k] -> bf16 copy [n,k] (ld_out) and/or transposed bf16 copy [k,n] (ldt_out) */
 int fiber_cast_transpose(const float* w, int64_t ldw, int32_t n, int32_t k, void* w_out, int64_t ld_out, void* wt_out,

@@ -236,3 +236,28 @@ def test_fused_mlm_decoder_cross_entropy(cuda_dev, rows, V, frac):
     assert l2rel(wp.grad, wr.grad) < 6e-3, l2rel(wp.grad, wr.grad)
     assert l2rel(bp.grad, br.grad) < 6e-3, l2rel(bp.grad, br.grad)
     assert hp.grad[~keep].abs().max().item() == 0.0 if bool((~keep).any()) else True
+
+
+@pytest.mark.parametrize("B,H,W,Hp,Wp,C,scaled", [(2, 50, 84, 60, 84, 128, True), (3, 7, 10, 12, 12, 1024, True),
+                                                   (2, 24, 24, 24, 24, 256, False), (1, 25, 42, 36, 48, 512, True)])
+def test_grid_copy_crop_scale_add_fwd_bwd(cuda_dev, B, H, W, Hp, Wp, C, scaled):
+    """fiber_grid_copy through ops.CropScaleAddFn against the torch expression of the fine-grained block
+    (fusion_swin_transformer_v2.py:336-343: crop, DropPath scale, residual) — same bf16 roundings, so bit for bit."""
+    from fiber_b200 import kernels as K
+    from fiber_b200 import ops
+    x = _rand((B, H * W, C), cuda_dev, 1).requires_grad_(True)
+    z = _rand((B * Hp * Wp, C), cuda_dev, 2).requires_grad_(True)
+    s = (torch.tensor([0.0, 1.25, 1.25][:B], device=cuda_dev) if scaled else None)
+    dout = _rand((B, H * W, C), cuda_dev, 3)
+    out = ops.CropScaleAddFn.apply(x, z, s, (H, W), (Hp, Wp))
+    out.backward(dout)
+    xr, zr = x.detach().clone().requires_grad_(True), z.detach().clone().requires_grad_(True)
+    zc = zr.view(B, Hp, Wp, C)[:, :H, :W].reshape(B, H * W, C)
+    ref = (xr.float() + (zc.float() * s.view(B, 1, 1) if scaled else zc.float())).to(torch.bfloat16)
+    ref.backward(dout)
+    assert torch.equal(out, ref)
+    assert torch.equal(x.grad, xr.grad)
+    assert torch.equal(z.grad, zr.grad.to(torch.bfloat16))
+    # zero padding alone (the F.pad of :316-321)
+    src = _rand((B, H, W, C), cuda_dev, 4)
+    assert torch.equal(K.grid_copy(src, (Hp, Wp)), F.pad(src, (0, 0, 0, Wp - W, 0, Hp - H)))
