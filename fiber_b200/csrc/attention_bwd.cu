@@ -8,6 +8,8 @@
 // WINDOW mode additionally reduces d(relative-position-bias table): every thread owns fixed (i,j)
 // score positions, so dS is summed over all windows a CTA processes in registers and flushed once
 // (shared-memory atomics -> one global atomic per table entry per CTA).
+#include <algorithm>
+
 #include "attention.cuh"
 #include "../../include/fiber_b200.h"
 
@@ -64,7 +66,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
   const int r_lo = lane >> 2;
   const bool acc_dq_smem = nqc > 1 && nkc > 1;
   const bool db_regs = Lq <= BW_QROWS;  // fixed (i,j) ownership only with a single query/key chunk
-
+  // Several chunks (18 x 18 windows: 324 tokens = 3 x 3 tiles of 144): d(bias) as DIAGONAL SUMS of the dS tile.  With
+  // tiles that hold whole window rows (144 % ws == 0), the ws x ws block of dS between query window-row QR and key
+  // window-row KR contributes the sum of its diagonal qw - kw = d to table entry (QR - KR, d).  Warp w owns the table
+  // rows (QR - KR + ws - 1) % 9 == w — at most one block per query window-row and tile, 7-8 blocks per warp and full
+  // tile, and nobody else ever touches those rows.  Lane L < ws walks a block with a skew, column (L + qw) mod ws of
+  // row qw, so that it only ever meets the diagonals d = -L (before the wrap) and d = ws - L (after it): two running
+  // sums per owned table row, at most four rows per warp, kept in registers over all windows of the CTA and written
+  // once.  No atomics (the generic path's per-element shared-memory float atomics compile to compare-and-swap spin
+  // loops: 105 k contended ones per window-head, two thirds of the 576-px configuration's step).
+  const int dg_rows = WINDOW ? BW_QROWS / ws : 1;
+  const bool db_diag = WINDOW && !db_regs && BW_NWARPS == 9 && BW_QROWS % ws == 0 && dg_rows <= 9 && ws <= 32 &&
+                       2 * ws - 1 <= 36 && Lq == ws * ws && Lk == Lq;
   float dbacc[WINDOW ? 18 : 1][4];
   if (WINDOW) {
 #pragma unroll
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
                   if (WINDOW) {
                     if (db_regs) {
                       dbacc[sub * 6 + nt][e] += ds;
-                    } else if (qi < Lq && j < Lk) {
+                    } else if (!db_diag && qi < Lq && j < Lk) {
                       atomicAdd(&sdTbl[(static_cast<int>(sTh[qi]) - static_cast<int>(sTh[j]) + ws - 1) * tw2 +
                                        static_cast<int>(sTw[qi]) - static_cast<int>(sTw[j]) + ws - 1], ds);
                     }
@@ -280,6 +293,31 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
           }
         }
         __syncthreads();
+
+        if (WINDOW && db_diag) {   // d(bias): skewed diagonal sums of this tile's dS (read-only on sdS, like phase B)
+          const int rq = nq / ws, rk = nk / ws;
+          const int offa = lane, offb = lane - ws, thr = ws - lane;   // column before / after the wrap, first wrapped row
+          for (int qr = 0; qr < rq; ++qr) {
+            // the one key window-row of this tile whose table row (QR - KR + ws - 1) this warp owns
+            const int base = qc * dg_rows + qr - kc * dg_rows + ws - 1;        // QR - kc * rows + ws - 1 >= 0
+            const int kr = ((base - warp) % 9 + 9) % 9;
+            if (kr < rk && lane < ws) {
+              const int ri = (base - kr) / 9;                                  // which of the warp's (up to four) rows
+              const bf16* e0 = sdS + (qr * ws) * BW_SP + kr * ws;
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll 6
+              for (int qw = 0; qw < ws; ++qw) {
+                const bool wr = qw >= thr;
+                const float v = __bfloat162float(e0[qw * BW_SP + (wr ? offb : offa) + qw]);
+                a0 += wr ? 0.f : v;
+                a1 += wr ? v : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i == ri) { dbacc[i][0] += a0; dbacc[i][1] += a1; }
+            }
+          }
+        }
 
         // ================= phase B =================
         if (warp < n_ktiles) {
@@ -383,6 +421,16 @@ __global__ void __launch_bounds__(NW * 32, NW == 9 ? 1 : (NW == 3 ? 4 : 3)) attn
                     dbacc[t][e]);
       }
     }
+    if (db_diag && lane < ws) {   // rows warp, warp + 9, ... of the table: this warp is their only writer
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = warp + 9 * i;
+        if (row < tw2) {
+          sdTbl[row * tw2 + ws - 1 - lane] += dbacc[i][0];                       // d = -lane
+          if (lane > 0) sdTbl[row * tw2 + 2 * ws - 1 - lane] += dbacc[i][1];     // d = ws - lane
+        }
+      }
+    }
     __syncthreads();
     for (int t = tid; t < tw2 * tw2; t += blockDim.x) atomicAdd(&p.dbias_table[t * p.nH + h], sdTbl[t]);
   }
@@ -421,7 +469,9 @@ static int launch_bwd(const AttnParams& p, cudaStream_t stream) {
   const int n_groups = WINDOW ? p.G * (p.H / p.ws) * (p.W / p.ws) : p.G;
   int gy = n_groups;
   if (WINDOW) {  // persistent over windows so d(bias) is flushed once per CTA
-    const int target = (2 * num_sms() + p.nH - 1) / p.nH;
+    int resident = 1;   // CTAs per SM at this shared-memory size: one wave, no tail
+    FIBER_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, BW_NWARPS * 32, smem));
+    const int target = std::max(1, (std::max(1, resident) * num_sms()) / p.nH);
     if (gy > target) gy = target;
   }
   dim3 grid(p.nH, gy);
