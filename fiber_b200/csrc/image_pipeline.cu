@@ -56,16 +56,31 @@ __global__ void __launch_bounds__(256) image_vpass_kernel(const fiber_image_desc
   vpass_body<W>(descs, ws, lut, out, out_h, out_w, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+template <int W>
+__global__ void __launch_bounds__(256) image_vpass_staged_kernel(const fiber_image_desc* descs, const void* ws, float* out,
+                                                                 int out_h, int out_w) {
+  extern __shared__ __align__(16) uint8_t staged[];   // [3 * 256] float look-up table, then the band's plane rows
+  float* lut = reinterpret_cast<float*>(staged);
+  pdl_trigger();
+  pdl_wait();
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) lut[i] = static_cast<const float*>(ws)[i];
+  vstage_load(descs, ws, staged + kLutBytes, out_h, out_w, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x);
+  __syncthreads();
+  vstage_compute<W>(descs, ws, staged + kLutBytes, lut, out, out_h, out_w, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x);
+}
+
 // "image_variant": bit 0 = the horizontal pass reads the source as aligned words (hpass_words_body) instead of bytes,
 // bit 1 = eight output columns per thread in the vertical pass instead of four, bit 2 = sixteen; bit 3 = eight source rows
-// per thread in the word-form horizontal pass instead of four.  Same bytes out either way.
+// per thread in the word-form horizontal pass instead of four; bit 4 = the vertical pass per band of 16 output rows with
+// its plane rows staged in shared memory (falls back to the global form when a band needs more than 200 KB).  Same bytes
+// out either way.
 // FIBER_IMAGE_VARIANT.
 static std::atomic<int> g_variant{-1};
 static int option_variant() {
   int v = g_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("FIBER_IMAGE_VARIANT");
-    v = e ? (atoi(e) & 15) : kDefaultVariant;
+    v = e ? (atoi(e) & 31) : kDefaultVariant;
     g_variant.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -74,7 +89,7 @@ static int option_variant() {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace img
-void set_image_variant(int v) { img::g_variant.store(v < 0 ? -1 : (v & 15), std::memory_order_relaxed); }
+void set_image_variant(int v) { img::g_variant.store(v < 0 ? -1 : (v & 31), std::memory_order_relaxed); }
 int get_image_variant() { return img::option_variant(); }
 }  // namespace fiber
 
@@ -154,6 +169,26 @@ int fiber_image_transform(const fiber_image_desc* dh, const fiber_image_desc* dd
     FIBER_CUDA(fiber::launch_k(image_hpass_words_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
   else
     FIBER_CUDA(fiber::launch_k(image_hpass_kernel<4>, g2, dim3(256), 0, stream, dd, ws, out_h, out_w));
+  if (variant & 16) {   // staged form: shared memory for the band that needs the most plane rows
+    int max_rows = 0;
+    for (int i = 0; i < n; ++i)
+      for (int y0 = 0; y0 < out_h; y0 += kBandRows) {
+        const int y1 = y0 + kBandRows < out_h ? y0 + kBandRows : out_h;
+        int f0, c0, f1, c1;
+        bounds_one(dh[i].box_h, out_h, y0, &f0, &c0);
+        bounds_one(dh[i].box_h, out_h, y1 - 1, &f1, &c1);
+        max_rows = f1 + c1 - f0 > max_rows ? f1 + c1 - f0 : max_rows;
+      }
+    const size_t smem = kLutBytes + 3ull * max_rows * tmp_pitch(out_w);
+    if (smem <= 200 * 1024) {
+      auto kern = W == 4 ? image_vpass_staged_kernel<4> : (W == 2 ? image_vpass_staged_kernel<2> : image_vpass_staged_kernel<1>);
+      FIBER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      const dim3 gs((out_h + kBandRows - 1) / kBandRows, n);
+      FIBER_CUDA(fiber::launch_k(kern, gs, dim3(256), smem, stream, dd, static_cast<const void*>(ws), out, out_h, out_w));
+      fiber::count_launch(3);
+      return 0;
+    }
+  }
   const dim3 g3(static_cast<unsigned>((vwork + 255) / 256), n);
   if (W == 4)
     FIBER_CUDA(fiber::launch_k(image_vpass_kernel<4>, g3, dim3(256), 0, stream, dd, static_cast<const void*>(ws), out, out_h,

@@ -67,17 +67,26 @@ FIBER_HD int ksize_for(int in_size, int out_size) {
 // Fixed-point coefficients of output sample xx (full-image box: in0 = 0, in1 = in_size), written tap-major:
 // k[t * out_size] for t in [0, ksize) (zero past the tap count; ksize may be the padded table height);
 // bounds[0] = first source sample, bounds[1] = tap count.
-FIBER_HD void coeffs_one(int in_size, int out_size, int xx, int ksize, int32_t* k, int32_t* bounds) {
+// First source sample and tap count of output sample xx (the bounds[] of Resample.c: precompute_coeffs).
+FIBER_HD void bounds_one(int in_size, int out_size, int xx, int* first, int* count) {
   const double scale = ddiv(static_cast<double>(in_size), static_cast<double>(out_size));
-  const double fs = scale < 1.0 ? 1.0 : scale;
-  const double support = dmul(2.0, fs);
-  const double ss = ddiv(1.0, fs);
+  const double support = dmul(2.0, scale < 1.0 ? 1.0 : scale);
   const double center = dadd(0.0, dmul(static_cast<double>(xx) + 0.5, scale));
   int xmin = static_cast<int>(dadd(dsub(center, support), 0.5));
   if (xmin < 0) xmin = 0;
   int xmax = static_cast<int>(dadd(dadd(center, support), 0.5));
   if (xmax > in_size) xmax = in_size;
-  const int n = xmax - xmin;
+  *first = xmin;
+  *count = xmax - xmin;
+}
+
+FIBER_HD void coeffs_one(int in_size, int out_size, int xx, int ksize, int32_t* k, int32_t* bounds) {
+  const double scale = ddiv(static_cast<double>(in_size), static_cast<double>(out_size));
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double ss = ddiv(1.0, fs);
+  const double center = dadd(0.0, dmul(static_cast<double>(xx) + 0.5, scale));
+  int xmin, n;
+  bounds_one(in_size, out_size, xx, &xmin, &n);
   double ww = 0.0;
   for (int x = 0; x < n; ++x)
     ww = dadd(ww, bicubic(dmul(dadd(dsub(static_cast<double>(x + xmin), center), 0.5), ss)));
@@ -301,22 +310,70 @@ FIBER_HD void hpass_words_body(const fiber_image_desc* descs, void* ws, int out_
   }
 }
 
-// W consecutive plane words (4 W pixels) in one load; the address is 4 W-byte aligned by construction.
-template <int W>
+// W consecutive plane words (4 W pixels) in one load; the address is 4 W-byte aligned by construction.  SMEM: the planes
+// were staged in shared memory (plain loads; ld.global.nc is for global addresses only).
+template <int W, bool SMEM = false>
 FIBER_HD void load_words(const uint8_t* p, uint32_t (&v)[W]) {
 #ifdef __CUDA_ARCH__
   if constexpr (W == 4) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 q = SMEM ? *reinterpret_cast<const uint4*>(p) : __ldg(reinterpret_cast<const uint4*>(p));
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
   } else if constexpr (W == 2) {
-    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const uint2 q = SMEM ? *reinterpret_cast<const uint2*>(p) : __ldg(reinterpret_cast<const uint2*>(p));
     v[0] = q.x; v[1] = q.y;
   } else {
-    v[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    v[0] = SMEM ? *reinterpret_cast<const uint32_t*>(p) : __ldg(reinterpret_cast<const uint32_t*>(p));
   }
 #else
   for (int w = 0; w < W; ++w) v[w] = reinterpret_cast<const uint32_t*>(p)[w];
 #endif
+}
+
+// The vertical taps of 4 W output columns x .. x + 4 W - 1 of one output row, three channels: col = first tap row of
+// channel 0 at column x, plane = bytes between channels; look-up and 128-bit stores (reversed for a flip).
+template <int W, bool SMEM>
+FIBER_HD void vpass_core(const uint8_t* col, int64_t plane, int pitch, int n, const int32_t* kp, int out_h, int out_w,
+                         const float* lut, float* row, int x, int flip) {
+  int32_t a[3][W][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int w = 0; w < W; ++w) a[c][w][0] = a[c][w][1] = a[c][w][2] = a[c][w][3] = 1 << (kPrecisionBits - 1);
+  for (int tp = 0; tp < n; ++tp, kp += out_h, col += pitch) {
+    const int32_t k = ldg(kp);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // x % (4 W) == 0 and pitch % 16 == 0: aligned; the pitch padding keeps a partial last group inside the plane row
+      uint32_t pw[W];
+      load_words<W, SMEM>(col + c * plane, pw);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t p = pw[w];
+        a[c][w][0] += static_cast<int32_t>(p & 0xff) * k;
+        a[c][w][1] += static_cast<int32_t>((p >> 8) & 0xff) * k;
+        a[c][w][2] += static_cast<int32_t>((p >> 16) & 0xff) * k;
+        a[c][w][3] += static_cast<int32_t>(p >> 24) * k;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {   // out 16-byte aligned, out_w % 4 == 0: one 128-bit store per channel and group
+    const float* l = lut + c * 256;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int xw = x + 4 * w;
+      if (xw < out_w) {
+        const float v0 = l[clip8(a[c][w][0])], v1 = l[clip8(a[c][w][1])], v2 = l[clip8(a[c][w][2])], v3 = l[clip8(a[c][w][3])];
+        Float4 v;
+        if (flip) {
+          v.a = v3; v.b = v2; v.c = v1; v.d = v0;
+        } else {
+          v.a = v0; v.b = v1; v.c = v2; v.d = v3;
+        }
+        *reinterpret_cast<Float4*>(row + static_cast<int64_t>(c) * out_h * out_w + (flip ? out_w - 4 - xw : xw)) = v;
+      }
+    }
+  }
 }
 
 // ---- kernel 3: vertical pass + ToTensor + Normalize (+ horizontal flip).  idx in [0, out_h * ceil(out_w / (4 W)))
@@ -337,47 +394,62 @@ FIBER_HD void vpass_body(const fiber_image_desc* descs, const void* ws, const fl
   const int pitch = tmp_pitch(out_w);
   const int64_t plane = static_cast<int64_t>(d.box_h) * pitch;
   const uint8_t* col = static_cast<const uint8_t*>(ws) + d.tmp_off + static_cast<int64_t>(ymin) * pitch + x;
-  int32_t a[3][W][4];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int w = 0; w < W; ++w) a[c][w][0] = a[c][w][1] = a[c][w][2] = a[c][w][3] = 1 << (kPrecisionBits - 1);
-  const int32_t* kp = t.ky + yy;
-  for (int tp = 0; tp < n; ++tp, kp += out_h, col += pitch) {
-    const int32_t k = ldg(kp);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      // x % (4 W) == 0 and pitch % 16 == 0: aligned; the pitch padding keeps a partial last group inside the plane row
-      uint32_t pw[W];
-      load_words<W>(col + c * plane, pw);
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint32_t p = pw[w];
-        a[c][w][0] += static_cast<int32_t>(p & 0xff) * k;
-        a[c][w][1] += static_cast<int32_t>((p >> 8) & 0xff) * k;
-        a[c][w][2] += static_cast<int32_t>((p >> 16) & 0xff) * k;
-        a[c][w][3] += static_cast<int32_t>(p >> 24) * k;
-      }
-    }
-  }
   float* row = out + (static_cast<int64_t>(image) * 3 * out_h + yy) * out_w;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {   // out 16-byte aligned, out_w % 4 == 0: one 128-bit store per channel and group
-    const float* l = lut + c * 256;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      const int xw = x + 4 * w;
-      if (xw < out_w) {
-        const float v0 = l[clip8(a[c][w][0])], v1 = l[clip8(a[c][w][1])], v2 = l[clip8(a[c][w][2])], v3 = l[clip8(a[c][w][3])];
-        Float4 v;
-        if (d.flip) {
-          v.a = v3; v.b = v2; v.c = v1; v.d = v0;
-        } else {
-          v.a = v0; v.b = v1; v.c = v2; v.d = v3;
-        }
-        *reinterpret_cast<Float4*>(row + static_cast<int64_t>(c) * out_h * out_w + (d.flip ? out_w - 4 - xw : xw)) = v;
-      }
-    }
+  vpass_core<W, false>(col, plane, pitch, n, t.ky + yy, out_h, out_w, lut, row, x, d.flip);
+}
+
+// ---- kernel 3, staged form ("image_variant" bit 4): one CTA = one image and a band of kBandRows output rows.  The
+// plane rows the band's taps read ([first, first + count): band rows x scale + support) are copied into shared memory
+// with 128-bit loads first, so the tap loop waits on shared-memory latency instead of an L2 round trip per tap
+// (the global form runs at 48 % issue-active with 7.8 cycles of long-scoreboard stall per instruction). --------------
+constexpr int kBandRows = 16;
+
+FIBER_HD void copy16(uint8_t* dst, const uint8_t* src) {   // 16 aligned bytes, global (read-only path) -> shared
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+#else
+  for (int i = 0; i < 16; ++i) dst[i] = src[i];
+#endif
+}
+
+FIBER_HD void band_span(const int32_t* by, int out_h, int band, int* y0, int* y1, int* first, int* count) {
+  *y0 = band * kBandRows;
+  *y1 = *y0 + kBandRows < out_h ? *y0 + kBandRows : out_h;
+  *first = ldg(by + 2 * *y0);
+  *count = ldg(by + 2 * (*y1 - 1)) + ldg(by + 2 * (*y1 - 1) + 1) - *first;
+}
+
+// phase 1: thread tid of nthreads copies its share of the band's plane rows ([3][count][pitch] bytes, 16 per load)
+FIBER_HD void vstage_load(const fiber_image_desc* descs, const void* ws, uint8_t* smem, int out_h, int out_w, int image,
+                          int band, int tid, int nthreads) {
+  const fiber_image_desc d = descs[image];
+  const Tables t = tables_of(d, ws, out_h, out_w);
+  int y0, y1, first, count;
+  band_span(t.by, out_h, band, &y0, &y1, &first, &count);
+  const int pitch = tmp_pitch(out_w), vec_per_row = pitch / 16;
+  const uint8_t* src = static_cast<const uint8_t*>(ws) + d.tmp_off;
+  for (int i = tid; i < 3 * count * vec_per_row; i += nthreads) {
+    const int v = i % vec_per_row, r = (i / vec_per_row) % count, c = i / (vec_per_row * count);
+    copy16(smem + (static_cast<int64_t>(c) * count + r) * pitch + 16 * v,
+           src + (static_cast<int64_t>(c) * d.box_h + first + r) * pitch + 16 * v);
+  }
+}
+
+// phase 2 (after a barrier): the band's outputs, 4 W columns x three channels per item, from the staged rows
+template <int W>
+FIBER_HD void vstage_compute(const fiber_image_desc* descs, const void* ws, const uint8_t* smem, const float* lut, float* out,
+                             int out_h, int out_w, int image, int band, int tid, int nthreads) {
+  const fiber_image_desc d = descs[image];
+  const Tables t = tables_of(d, ws, out_h, out_w);
+  int y0, y1, first, count;
+  band_span(t.by, out_h, band, &y0, &y1, &first, &count);
+  const int pitch = tmp_pitch(out_w), per_row = ((out_w >> 2) + W - 1) / W;
+  for (int i = tid; i < (y1 - y0) * per_row; i += nthreads) {
+    const int yy = y0 + i / per_row, x = (i % per_row) * (4 * W);
+    const int ymin = ldg(t.by + 2 * yy), n = ldg(t.by + 2 * yy + 1);
+    float* row = out + (static_cast<int64_t>(image) * 3 * out_h + yy) * out_w;
+    vpass_core<W, true>(smem + static_cast<int64_t>(ymin - first) * pitch + x, static_cast<int64_t>(count) * pitch, pitch, n,
+                        t.ky + yy, out_h, out_w, lut, row, x, d.flip);
   }
 }
 

@@ -50,7 +50,8 @@ int64_t fiber_launch_count(void);
  * default 0, FIBER_PDL.
  * "image_variant": work per thread of fiber_image_transform's two passes — bit 0 the horizontal pass reads aligned words
  * instead of bytes, bit 1 / bit 2 eight / sixteen output columns per thread in the vertical pass instead of four, bit 3 (with
- * bit 0) eight source rows per thread instead of four; default 3 or FIBER_IMAGE_VARIANT; the bytes out are the same.
+ * bit 0) eight source rows per thread instead of four, bit 4 the vertical pass per 16-row band with its plane rows staged in
+ * shared memory; default 3 or FIBER_IMAGE_VARIANT; the bytes out are the same.
  * "tq_trace" (debug): 1 makes the fourth-generation window backward record an event trace of one CTA (tools/tq_trace.py).
  * Results are the same attention (swin_transformer.py:195-224) either way.  Returns 0, or -1 for an unknown name;
  * fiber_get_option returns the value ("winattn_tc_launches" / "attn_sk_launches", read-only: launches of the tcgen05

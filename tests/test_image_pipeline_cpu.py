@@ -98,7 +98,7 @@ def _run_emul(emul, images, out_h, out_w, boxes=None, flips=None, strides=None, 
     return out
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7, 11, 15])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7, 11, 15, 18, 19, 23])
 def test_kernel_bodies_match_oracle_ragged_batch(emul, variant):
     rng = np.random.default_rng(11)
     sizes = [(97, 131), (48, 64), (64, 64), (7, 5), (211, 89), (30, 300), (64, 65), (1, 1), (130, 64)]
@@ -113,7 +113,7 @@ def test_kernel_bodies_match_oracle_ragged_batch(emul, variant):
             assert np.array_equal(got[i], want), (sizes[i], out_h, out_w)
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 19])
 def test_kernel_bodies_match_library_golden_with_crop_and_flip(emul, variant):
     for i, (h, w, s) in enumerate(CASES):
         src = GOLD["src_%d" % i]
@@ -124,7 +124,7 @@ def test_kernel_bodies_match_library_golden_with_crop_and_flip(emul, variant):
         assert np.array_equal(got[1], GOLD["crop_%d" % i])
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 18])
 def test_kernel_bodies_planar_sources(emul, variant):
     """Three byte planes per image (what GPU JPEG decoders return) next to interleaved ones in the same batch."""
     rng = np.random.default_rng(12)

@@ -46,7 +46,7 @@ def variant(request):
     lib.set_option("image_variant", -1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7, 11, 15], indirect=True)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7, 11, 15, 19, 23], indirect=True)
 def test_ragged_batch_vs_oracle_rectangular_output_and_strides(variant):
     from fiber_b200.transforms import BatchImageTransform
     rng = np.random.default_rng(3)

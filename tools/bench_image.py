@@ -134,7 +134,7 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
 
     variants = {}
     if sweep:   # every "image_variant" (rows / columns per thread), same bytes out
-        for v in (0, 1, 2, 3, 7, 11, 15):
+        for v in (0, 1, 2, 3, 7, 11, 15, 19, 23):
             lib.set_option("image_variant", v)
             run(resident, warmup, False)
             variants[str(v)] = run(resident, steps, False) * 1e3
