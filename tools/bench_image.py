@@ -178,11 +178,13 @@ def measure_image_pipeline(dev, batch=64, src=(480, 640), size=384, steps=20, wa
         ref = T.Compose([T.Resize((size, size), interpolation=T.InterpolationMode.BICUBIC), T.ToTensor(),
                          T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
         pil = [Image.fromarray(a) for a in host[:cpu_sample]]
+        nt = torch.get_num_threads()
         torch.set_num_threads(1)
         ref(pil[0])
         t0 = time.perf_counter()
         outs = [ref(p) for p in pil]
         t_cpu = (time.perf_counter() - t0) / len(pil)
+        torch.set_num_threads(nt)
         same = bool(torch.equal(torch.stack(outs), tr(host[:cpu_sample]).cpu()))
         all_cores = None
         if all_cores_baseline:
