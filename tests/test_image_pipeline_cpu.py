@@ -188,3 +188,37 @@ def test_transform_needs_cuda():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         albef_transform(32)([np.zeros((8, 8, 3), np.uint8)])
+
+
+def test_image_layout_detection_on_the_host():
+    """fiber_b200.transforms._as_image: what counts as interleaved / planar, and what is rejected (host logic only)."""
+    from fiber_b200.transforms import _as_image
+    hwc = np.zeros((5, 7, 3), np.uint8)
+    t, planar = _as_image(hwc)
+    assert not planar and tuple(t.shape) == (5, 7, 3) and t.stride(2) == 1 and t.stride(1) == 3
+    chw = torch.zeros(3, 5, 7, dtype=torch.uint8)
+    t, planar = _as_image(chw)
+    assert planar and tuple(t.shape) == (3, 5, 7) and t.stride(2) == 1
+    wide = torch.zeros(5, 9, 3, dtype=torch.uint8)[:, :7]            # row stride > 3 w: read in place
+    t, planar = _as_image(wide)
+    assert not planar and t.data_ptr() == wide.data_ptr() and t.stride(0) == 27
+    sliced = torch.zeros(3, 5, 14, dtype=torch.uint8)[:, :, ::2]     # pixel stride 2: copied
+    t, planar = _as_image(sliced)
+    assert planar and t.stride(2) == 1
+    Image = pytest.importorskip("PIL.Image")
+    t, planar = _as_image(Image.fromarray(np.zeros((4, 6), np.uint8)))   # grey PIL image -> RGB, as get_raw_image does
+    assert not planar and tuple(t.shape) == (4, 6, 3)
+    for bad in (np.zeros((5, 7, 3), np.float32), np.zeros((5, 7), np.uint8), np.zeros((5, 7, 4), np.uint8)):
+        with pytest.raises(RuntimeError, match="uint8"):
+            _as_image(bad)
+
+
+def test_transform_keys_mirror_the_reference():
+    """Same keys as coarse_grained/fiber/transforms/__init__.py:6-9 (parsed from the reference when it is present)."""
+    from fiber_b200 import transforms as T
+    assert set(T._transforms) == {"albef", "albef_randaug"}
+    ref = "/root/reference/coarse_grained/fiber/transforms/__init__.py"
+    if os.path.exists(ref):
+        import re
+        keys = set(re.findall(r'"(\w+)":\s*\w+', open(ref).read()))
+        assert keys == set(T._transforms)
